@@ -1,0 +1,368 @@
+#!/usr/bin/env python
+"""bench.py -- CHOMP trajectory-iterations/s on B200 (BASELINE.json metric), one JSON line.
+
+  python bench.py --gpus N --steps K --warmup W          the sm_100a engine (this repo)
+  python bench.py --impl reference --gpus N ...          the reference's CPU path (oracle port) on host cores
+
+A "step" is ONE CHOMP iteration (Optimizer.optimize equivalent: cost + gradient + covariant update +
+joint-limit projection) over the whole trajectory batch.  Workload at N=1: BASELINE config 2 stand-in
+(1024 trajectories x 30 waypoints x 7-DOF Panda, 10 synthetic SDFs at 128^3, reference default mode:
+goal-set projection with standoff, top_k_collision=1000).  N>1: every rank runs its own 1024 trajectories
+against a replicated scene (weak scaling), one NCCL all-gather of final costs after the timed region.
+
+value     = trajectories x steps / device time (CUDA events per step, inputs resident in HBM, L2 flushed
+            between steps), max over ranks.
+e2e       = the same through the host-buffer C-ABI entry point (omgb_chomp_step_host): pinned host xi ->
+            H2D -> fused kernel -> D2H xi + info, every step.
+roofline  = SURVEY 8(d) algorithmic bytes (128*P_in + 8*n*9 + 4*(2+c)*9 per trajectory-iteration, P_in
+            counted by the kernel) / kernel time, against MEASURED_PEAKS.json hbm_gbs.
+"""
+import argparse
+import json
+import multiprocessing as mp
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+DEFAULT_MODE = dict(goal_set_proj=True, use_standoff=True, top_k_collision=1000)
+FULLSUM_MODE = dict(goal_set_proj=True, use_standoff=True, top_k_collision=0)
+
+
+def workload_name(a):
+    return ("config2-standin: %d traj x %d wpt x 7-DOF Panda, %d synthetic SDFs @%d^3, %s"
+            % (a.batch, a.waypoints, a.objects, a.grid,
+               "goal-set+standoff top_k=1000 (reference defaults)" if a.mode == "default" else "goal-set+standoff full-sum"))
+
+
+# --------------------------------------------------------------------------------------------------
+# CPU arm: the reference's per-trajectory Python path (oracle port), one process per host core
+# --------------------------------------------------------------------------------------------------
+def _cpu_worker(chunk, scene, mode, n, xi, st, en, tails, barrier, total_steps):
+    from oracle import chomp_ref as R
+
+    robot = R.PandaRef()
+    opts = []
+    for b in chunk:
+        cfg = R.RefConfig(timesteps=n, **mode)
+        opts.append(R.ChompRef(robot, scene, cfg, xi[b], st[b], en[b], tails[b]))
+    for _ in range(total_steps):
+        barrier.wait()
+        for o in opts:
+            o.step()
+        barrier.wait()
+
+
+def run_cpu(a, scene, mode, sample, steps, warmup):
+    """Returns (traj-iter/s, cores, description)."""
+    from omg_planner_b200 import scene as S
+    from omg_planner_b200.robot import PandaConstants
+
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    cores = max(1, min(cores, sample))
+    robot = PandaConstants()
+    xi, st, en, tails = S.make_trajectories(sample, a.waypoints, robot.joint_lower_limit, robot.joint_upper_limit, seed=0)
+    ctx = mp.get_context("fork")
+    barrier = ctx.Barrier(cores + 1)
+    chunks = [list(range(w, sample, cores)) for w in range(cores)]
+    procs = [ctx.Process(target=_cpu_worker, args=(chunks[w], scene, mode, a.waypoints, xi, st, en, tails, barrier,
+                                                   steps + warmup), daemon=True) for w in range(cores)]
+    for p in procs:
+        p.start()
+    total = 0.0
+    for s in range(steps + warmup):
+        barrier.wait()
+        t0 = time.perf_counter()
+        barrier.wait()
+        if s >= warmup:
+            total += time.perf_counter() - t0
+    for p in procs:
+        p.join(timeout=30)
+    value = sample * steps / total
+    desc = ("%d of %d trajectories of the workload, %d processes x 1 thread, numpy oracle port of omg/cost.py + "
+            "omg/optimizer.py with the C restatement of the SDF op; %d warm-up + %d timed iterations"
+            % (sample, a.batch, cores, warmup, steps))
+    return value, cores, desc, total / steps * 1e3
+
+
+# --------------------------------------------------------------------------------------------------
+# clocks
+# --------------------------------------------------------------------------------------------------
+class ClockSampler(object):
+    def __init__(self, cuda_index):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thr = None
+        try:
+            import pynvml
+            import torch
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            h = None
+            try:
+                uuid = str(torch.cuda.get_device_properties(cuda_index).uuid)
+                h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid) if not uuid.startswith("GPU-") else uuid)
+            except Exception:
+                h = pynvml.nvmlDeviceGetHandleByIndex(cuda_index)
+            self.h = h
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+        except Exception as e:  # noqa: BLE001
+            self.nv, self.err = None, repr(e)
+
+    def _loop(self):
+        nv = self.nv
+        names = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40,
+                 "hw_power_brake": 0x80, "sync_boost": 0x10, "applications_clocks": 0x2, "display_clocks": 0x100}
+        while not self._stop.is_set():
+            try:
+                self.samples.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                r = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:  # noqa: BLE001
+                pass
+            time.sleep(0.002)
+
+    def start(self):
+        if self.nv:
+            self._thr = threading.Thread(target=self._loop, daemon=True)
+            self._thr.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._thr:
+            self._thr.join(timeout=2)
+        med = float(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# --------------------------------------------------------------------------------------------------
+# B200 arm
+# --------------------------------------------------------------------------------------------------
+def run_b200(a):
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    mode = DEFAULT_MODE if a.mode == "default" else FULLSUM_MODE
+
+    from omg_planner_b200 import scene as S
+    from omg_planner_b200.config import ChompConfig
+    from omg_planner_b200.robot import PandaConstants
+
+    scene = S.make_scene(num_objects=a.objects, grid=a.grid, seed=0)
+
+    # CPU baseline first (forks; must precede CUDA initialisation), rank 0 at N=1 only
+    cpu = None
+    if rank == 0 and world == 1 and not a.no_cpu_baseline:
+        v, cores, desc, ms = run_cpu(a, scene, mode, a.cpu_sample, a.cpu_steps, 2)
+        cpu = {"value": v, "unit": "trajectory-iterations/s", "cores": cores, "kind": "port", "sample": desc,
+               "ms_per_step": ms}
+
+    import torch
+    import torch.distributed as dist
+
+    from omg_planner_b200.engine import ChompEngine
+
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    cfg = ChompConfig(timesteps=a.waypoints, **mode)
+    robot = PandaConstants()
+    eng = ChompEngine(robot=robot).load_scene(scene, cfg)
+    B, n, c = a.batch, a.waypoints, cfg.constraint_rows
+    xi0, st, en, tails = S.make_trajectories(B, n, robot.joint_lower_limit, robot.joint_upper_limit, seed=rank)
+    dev = lambda x: torch.from_numpy(np.ascontiguousarray(x)).cuda()
+    xi, d_st, d_en, d_tails = dev(xi0), dev(st), dev(en), dev(tails)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")   # > 126 MB L2
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    it = 0
+
+    def one_step(timed_events=None):
+        nonlocal it
+        cfg.obstacle_weight, cfg.smoothness_weight, cfg.step_size = cfg.schedule(it + 1)
+        it += 1
+        flush.zero_()
+        if timed_events is not None:
+            timed_events[0].record()
+        out = eng.step(cfg, xi, d_st, d_en, d_tails)
+        if timed_events is not None:
+            timed_events[1].record()
+        return out
+
+    for _ in range(max(a.warmup, 3)):
+        one_step()
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(a.steps)]
+    pins = []
+    t_wall = time.perf_counter()
+    for k in range(a.steps):
+        out = one_step(evs[k])
+        pins.append(out["info"][:, 12].sum())
+    barrier()
+    t_wall = time.perf_counter() - t_wall
+    clocks = sampler.stop()
+    dev_ms = sum(s.elapsed_time(e) for s, e in evs)
+    p_in_per_launch = float(torch.stack(pins).mean().item())
+    t = torch.tensor([dev_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms_max = float(t.item())
+
+    # warm-L2 variant (what a real plan sees: 70 back-to-back iterations, SDFs resident in L2)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for k in range(a.steps):
+        cfg.obstacle_weight, cfg.smoothness_weight, cfg.step_size = cfg.schedule(it + 1)
+        it += 1
+        eng.step(cfg, xi, d_st, d_en, d_tails)
+    e1.record()
+    barrier()
+    warm_ms = e0.elapsed_time(e1)
+
+    # end to end through the host-buffer C-ABI call, pinned host memory
+    h_xi = torch.from_numpy(xi0.copy()).pin_memory()
+    h_st, h_en, h_tails = (torch.from_numpy(np.ascontiguousarray(x)).pin_memory() for x in (st, en, tails))
+    n_xi, n_se, n_goal, n_info = B * n * 9, B * 9, B * c * 9, B * 16
+    it_h = 0
+
+    def host_step(events=None):
+        nonlocal it_h
+        cfg.obstacle_weight, cfg.smoothness_weight, cfg.step_size = cfg.schedule(it_h + 1)
+        it_h += 1
+        flush.zero_()
+        if events is not None:
+            events[0].record()
+        eng.step_host(cfg, h_xi.numpy(), h_st.numpy(), h_en.numpy(), h_tails.numpy())
+        if events is not None:
+            events[1].record()
+
+    for _ in range(3):
+        host_step()
+    barrier()
+    hevs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(a.steps)]
+    for k in range(a.steps):
+        host_step(hevs[k])
+    barrier()
+    e2e_ms = sum(s.elapsed_time(e) for s, e in hevs)
+    t = torch.tensor([e2e_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_ms_max = float(t.item())
+
+    # the one collective of the path: all-gather of the final per-trajectory costs
+    final_cost = out["info"][:, 2].contiguous()
+    if world > 1:
+        from omg_planner_b200 import dist as D
+        gathered = D.all_gather_costs(final_cost)
+        assert gathered.shape[0] == world * B
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    bytes_per_launch = 128.0 * p_in_per_launch + B * (8.0 * n * 9 + 4.0 * (2 + c) * 9)
+    kern_ms = dev_ms / a.steps
+    achieved = bytes_per_launch / (kern_ms * 1e-3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get("%s:%s" % (a.mode, "flush"))
+    total = B * world * a.steps
+    line = {
+        "metric": "CHOMP trajectory-iterations/s (batch traj x waypt)", "value": total / (dev_ms_max * 1e-3),
+        "unit": "trajectory-iterations/s", "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
+        "ms_per_step": dev_ms_max / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64 state/FK/gradient, f32 SDF operator (as the reference)", "data": "synthetic",
+        "config": {"workload": workload_name(a), "batch_per_gpu": B, "waypoints": n, "objects": a.objects,
+                   "grid": a.grid, "parallelism": "dp%d (trajectory batch sharded, scene replicated)" % world,
+                   "l2": "flushed between timed steps (256 MiB write); value_warm_l2 = back-to-back steps",
+                   "timing": "CUDA events around each step on the launch stream, summed; max over ranks"},
+        "value_warm_l2_rank0": B * a.steps / (warm_ms * 1e-3),
+        "e2e": {"value": total / (e2e_ms_max * 1e-3), "unit": "trajectory-iterations/s",
+                "h2d_bytes_per_step": 8 * (n_xi + 2 * n_se + n_goal), "d2h_bytes_per_step": 8 * (n_xi + n_info),
+                "ms_per_step": e2e_ms_max / a.steps, "api": "omgb_chomp_step_host (pinned host buffers)"},
+        "gpu_launches": a.steps,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": traffic, "peak_source": peak_src, "kernel": "chomp_step_kernel<16>",
+                     "algorithmic_bytes_per_launch": bytes_per_launch, "p_in_per_launch": p_in_per_launch,
+                     "kernel_ms": kern_ms,
+                     "note": "gather-bound: the 84 MB of SDFs stay in L2; see DESIGN.md for DRAM vs L2 traffic"},
+        "clocks": clocks, "wall_s_timed_region": t_wall,
+    }
+    if cpu is not None:
+        line["cpu_baseline"] = cpu
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_reference(a):
+    """The reference arm: the reference's own CPU implementation of the path (numpy Python + C operator;
+    the oracle port, because /root/reference does not travel to the GPU box) on all host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    from omg_planner_b200 import scene as S
+
+    mode = DEFAULT_MODE if a.mode == "default" else FULLSUM_MODE
+    scene = S.make_scene(num_objects=a.objects, grid=a.grid, seed=0)
+    sample = a.cpu_sample
+    steps, warmup = max(1, a.steps), max(1, min(a.warmup, 3))
+    v, cores, desc, ms = run_cpu(a, scene, mode, sample, steps, warmup)
+    line = {
+        "impl": "reference", "metric": "CHOMP trajectory-iterations/s (batch traj x waypt)", "value": v,
+        "unit": "trajectory-iterations/s", "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": ms,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64 numpy + f32 SDF operator",
+        "data": "synthetic",
+        "config": {"workload": workload_name(a), "batch_per_gpu": a.batch, "waypoints": a.waypoints,
+                   "objects": a.objects, "grid": a.grid, "sample_trajectories_per_step": sample},
+        "cpu_baseline": {"value": v, "unit": "trajectory-iterations/s", "cores": cores, "kind": "port", "sample": desc},
+        "e2e": {"value": v, "unit": "trajectory-iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=1024)
+    ap.add_argument("--waypoints", type=int, default=30)
+    ap.add_argument("--objects", type=int, default=10)
+    ap.add_argument("--grid", type=int, default=128)
+    ap.add_argument("--mode", default="default", choices=["default", "fullsum"])
+    ap.add_argument("--cpu-sample", type=int, default=64)
+    ap.add_argument("--cpu-steps", type=int, default=8)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    a = ap.parse_args()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_b200(a)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,171 @@
+/*
+ * omgb200.h -- C ABI of libomgb200.so: the B200-native (sm_100a) CHOMP hot path of OMG-Planner.
+ *
+ * Plain C: device/host pointers, sizes, a cudaStream_t passed as void*.  No torch types.  Every entry
+ * point returns 0 on success or a negative omgb_status; omgb_last_error() gives the message.  Nothing
+ * here ever calls exit() (the reference does: layers/sdf_matching_loss_kernel.cu:241-246).
+ * The caller owns all buffers; the library allocates device memory only inside omgb_scene_* calls.
+ *
+ * Reference interfaces replaced (file:line under the reference tree):
+ *   omgb_sdf_loss              omg_cuda.sdf_loss_forward            layers/omg_layers.cpp:24-49,
+ *                                                                   layers/sdf_matching_loss_kernel.cu:204-262
+ *   omgb_scene_set_sdf         Env.combine_sdfs output              omg/core.py:366-411
+ *   omgb_scene_set_objects     per-object parameters                omg/cost.py:303-335
+ *   omgb_scene_set_robot       robot_kinematics constants + Robot   ycb_render/robotPose/robot_pykdl.py:98-112,
+ *                                                                   omg/core.py:152-164
+ *   omgb_scene_set_metric      cfg.Ainv + goal-set projection       omg/config.py:199-220, omg/optimizer.py:102-107
+ *   omgb_chomp_step            Optimizer.optimize(force_update)     omg/optimizer.py:115-135 -> omg/cost.py:451-532
+ *   omgb_chomp_plan            the fixed-goal inner loop of plan()  omg/planner.py:612-627
+ *   omgb_chomp_step_host       same as omgb_chomp_step, HOST buffers (H2D + D2H inside the call)
+ *   omgb_batch_obstacle_cost   Cost.batch_obstacle_cost             omg/cost.py:192-286
+ */
+#ifndef OMGB200_H_
+#define OMGB200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OMGB_VERSION 100
+#define OMGB_NUM_LINKS 10      /* 7 arm links, hand, 2 fingers (omg/core.py:171-182) */
+#define OMGB_NUM_DOF 9         /* 7 arm + 2 finger joints (omg/core.py:28) */
+#define OMGB_MAX_OBJECTS 64
+#define OMGB_MAX_BODY_POINTS 32
+#define OMGB_INFO_STRIDE 16
+
+typedef enum {
+    OMGB_OK = 0,
+    OMGB_ERR_INVALID = -1,   /* bad argument (what AT_ASSERT raised in layers/omg_layers.cpp:5-7) */
+    OMGB_ERR_CUDA = -2,      /* CUDA runtime error (the reference exit(-1)s) */
+    OMGB_ERR_STATE = -3,     /* scene not fully configured */
+    OMGB_ERR_UNSUPPORTED = -4
+} omgb_status;
+
+/* Layout of the per-trajectory info row written by omgb_chomp_step ([B, OMGB_INFO_STRIDE] doubles);
+ * the fields of the reference's info dict (omg/cost.py:509-530, omg/optimizer.py:173-174). */
+enum {
+    OMGB_INFO_OBS = 0,            /* info["obs"] (x n inflated in top-k mode, SURVEY A-3) */
+    OMGB_INFO_SMOOTH = 1,         /* info["smooth"] */
+    OMGB_INFO_COST = 2,           /* info["cost"] */
+    OMGB_INFO_COLLIDE = 3,        /* info["collide"] (a count, SURVEY A-17) */
+    OMGB_INFO_REACH = 4,          /* info["reach"] goal distance */
+    OMGB_INFO_GRAD_NORM = 5,      /* info["grad"] */
+    OMGB_INFO_WOBS_GRAD_NORM = 6, /* info["weighted_obs_grad"] */
+    OMGB_INFO_WSMOOTH_GRAD_NORM = 7,
+    OMGB_INFO_TERMINATE = 8,      /* after check_joint_limit (omg/optimizer.py:174) */
+    OMGB_INFO_VIOLATE_LIMIT = 9,
+    OMGB_INFO_EXECUTE = 10,
+    OMGB_INFO_FAILURE_TERMINATE = 11,
+    OMGB_INFO_P_IN = 12,          /* in-bounds (body point, enabled object) pairs this iteration */
+    OMGB_INFO_NONZERO = 13,       /* body points with non-zero potential */
+    OMGB_INFO_LIMIT_ROUNDS = 14,  /* rounds of handle_joint_limit taken */
+    OMGB_INFO_RESERVED = 15
+};
+
+typedef struct omgb_scene omgb_scene_t;
+
+/* Scalars Cost/Optimizer read from cfg on every call (omg/config.py:29-104); the host mirror snapshots
+ * them per call because Optimizer.update() writes the schedules back into cfg (omg/optimizer.py:68-80). */
+typedef struct {
+    int32_t n_waypoints;           /* cfg.timesteps */
+    int32_t goal_set_proj;         /* cfg.goal_set_proj */
+    int32_t constraint_rows;       /* c: reach_tail_length with use_standoff, else 1; 0 when !goal_set_proj */
+    int32_t top_k_collision;       /* cfg.top_k_collision; 0 = sum over all points */
+    int32_t uncheck_finger_collision; /* cfg.uncheck_finger_collision (0 or -1) */
+    int32_t consider_finger;       /* must be 0 (cfg.consider_finger) */
+    int32_t allow_collision_point; /* cfg.allow_collision_point */
+    int32_t pre_terminate;         /* cfg.pre_terminate */
+    int32_t joint_limit_max_steps; /* cfg.joint_limit_max_steps */
+    int32_t update;                /* 0: info_only=True; 1: always update (force_update=True);
+                                      2: update unless this iteration reports terminate (optimizer.py:124) */
+    double time_interval;          /* cfg.time_interval */
+    double obstacle_weight;        /* cfg.obstacle_weight (after Optimizer.update) */
+    double smoothness_weight;      /* cfg.smoothness_weight */
+    double step_size;              /* cfg.step_size */
+    double clip_grad_scale;        /* cfg.clip_grad_scale */
+    double terminate_smooth_loss;  /* cfg.terminate_smooth_loss */
+    double link_smooth_weight[OMGB_NUM_DOF]; /* cfg.link_smooth_weight */
+} omgb_step_params_t;
+
+int omgb_version(void);
+const char *omgb_last_error(void);
+
+/* ---- scene: everything that is constant across CHOMP iterations, resident in HBM ------------------- */
+int omgb_scene_create(omgb_scene_t **out, int device);
+int omgb_scene_destroy(omgb_scene_t *scene);
+
+/* Kinematic constants (HOST pointers, fp64): pose_0 [10,4,4], tip2joint [10,4,4], joint_axis [10,3],
+ * center_offset [10,4,4] (robot_p3.pkl via robot_pykdl.py:101-110; "origin" is aliased to joint_axis as
+ * in :104 unless use_true_joint_origin != 0, then joint_origin [10,3] must be given), body_points
+ * [10,p,3] in the centre-offset link frames (Robot.collision_points, omg/core.py:166-190), padded joint
+ * limits lower/upper [9] (omg/core.py:157-164). */
+int omgb_scene_set_robot(omgb_scene_t *scene, const double *pose_0, const double *tip2joint,
+                         const double *joint_axis, const double *joint_origin, int use_true_joint_origin,
+                         const double *center_offset, const double *body_points, int points_per_link,
+                         const double *lower, const double *upper);
+
+/* Packed SDFs exactly as Env.combine_sdfs leaves them: d_sdf_grids DEVICE [O,X,Y,Z] fp32 (borrowed, not
+ * copied: zero-copy on env.sdf_torch), h_sdf_limits HOST [O,10] fp32. */
+int omgb_scene_set_sdf(omgb_scene_t *scene, const float *d_sdf_grids, const float *h_sdf_limits,
+                       int num_objects, int dim_x, int dim_y, int dim_z);
+
+/* Per-object parameters built by Cost.compute_obstacle_cost_layer (omg/cost.py:303-335), HOST arrays:
+ * pose_inv [O,4,4] fp32 (world->object), epsilons, padding_scales, clearances, disables [O] fp32. */
+int omgb_scene_set_objects(omgb_scene_t *scene, const float *pose_inv, const float *epsilons,
+                           const float *padding_scales, const float *clearances, const float *disables,
+                           void *stream);
+
+/* Smoothness metric: h_Ainv HOST [n,n] fp64 (cfg.Ainv), h_proj HOST [n,c] fp64 = Ainv C^T (C Ainv C^T)^-1
+ * (omg/optimizer.py:107) or NULL when c == 0. */
+int omgb_scene_set_metric(omgb_scene_t *scene, int n_waypoints, const double *h_Ainv, int constraint_rows,
+                          const double *h_proj);
+
+/* ---- the raw operator (drop-in for omg_cuda.sdf_loss_forward); all pointers DEVICE, fp32 ------------ */
+size_t omgb_sdf_loss_workspace_bytes(int num_objects);
+int omgb_sdf_loss(const float *pose_init, const float *sdf_grids, const float *sdf_limits,
+                  const float *points, const float *epsilons, const float *padding_scales,
+                  const float *clearances, const float *disables, int num_points, int num_objects,
+                  int dim_x, int dim_y, int dim_z, float *potentials, float *potential_grads,
+                  float *collides, void *workspace, void *stream);
+
+/* ---- one fused CHOMP iteration over a batch of trajectories; all pointers DEVICE --------------------
+ * xi [B,n,9] fp64 in/out (Trajectory.data), start [B,9], end [B,9] (traj.start / traj.end),
+ * goal_rows [B,c,9] (reach_grasps[goal_idx] or goal_set[goal_idx]; NULL when c == 0),
+ * active [B] uint8 or NULL (0 = leave this trajectory untouched),
+ * grad_out [B,n,9] fp64 or NULL (info["gradient"]), info [B,OMGB_INFO_STRIDE] fp64,
+ * dbg_potentials [B,n,10,p] fp32 or NULL, dbg_points [B,n,10,p,3] fp32 or NULL (collision_pts columns),
+ * row_obs [B,n] fp64 or NULL, zero-initialised by the caller (obstacle part of info["cost_traj"]). */
+int omgb_chomp_step(omgb_scene_t *scene, const omgb_step_params_t *params, int batch, double *xi,
+                    const double *start, const double *end, const double *goal_rows, const uint8_t *active,
+                    double *grad_out, double *info, float *dbg_potentials, float *dbg_points, double *row_obs,
+                    void *stream);
+
+/* `iters` iterations with per-iteration schedules (HOST arrays [iters]: obstacle_weight, smoothness_weight,
+ * step_size as Optimizer.update() would set them).  stop_on_terminate != 0 freezes a trajectory once an
+ * iteration with index > 0 reports terminate (omg/planner.py:627); done [B] uint8 DEVICE scratch/out. */
+int omgb_chomp_plan(omgb_scene_t *scene, const omgb_step_params_t *params, int iters,
+                    const double *obstacle_weights, const double *smoothness_weights, const double *step_sizes,
+                    int stop_on_terminate, int batch, double *xi, const double *start, const double *end,
+                    const double *goal_rows, uint8_t *done, double *info, void *stream);
+
+/* Same as omgb_chomp_step with HOST buffers (pinned or pageable): copies xi/start/end/goal_rows to the
+ * scene's staging buffers, runs the step, copies xi and info back, synchronises the stream. */
+int omgb_chomp_step_host(omgb_scene_t *scene, const omgb_step_params_t *params, int batch, double *h_xi,
+                         const double *h_start, const double *h_end, const double *h_goal_rows,
+                         double *h_info, void *stream);
+
+/* Cost.batch_obstacle_cost (omg/cost.py:192-286): joints DEVICE [M,9] fp64 (rad);
+ * arc_length <= 0: plain potentials; > 0: joints are G groups of arc_length configurations, potentials
+ * are multiplied by the workspace speed |x_i - x_{i-1}|/dt with x_{-1} = FK(start [9]) (omg/config.py:162-187);
+ * out potentials [M,10,p], grads [M,10,p,3] (or NULL), collides [M,10,p] fp32 DEVICE. */
+int omgb_batch_obstacle_cost(omgb_scene_t *scene, const double *joints, int num_configs, int arc_length,
+                             const double *start, double time_interval, int uncheck_finger_collision,
+                             float *potentials, float *grads, float *collides, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OMGB200_H_ */

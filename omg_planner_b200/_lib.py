@@ -1,0 +1,94 @@
+"""ctypes binding of libomgb200.so (include/omgb200.h).  There is NO fallback: if the CUDA library is
+missing or fails to load, importing the product fails loudly."""
+import ctypes
+import os
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(_HERE)
+LIB_PATH = os.path.join(_HERE, "lib", "libomgb200.so")
+SOURCES = [os.path.join(_HERE, "csrc", f) for f in ("omgb200.cu", "chomp_kernels.cuh", "sdf_device.cuh")] + [
+    os.path.join(ROOT, "include", "omgb200.h")]
+
+INFO_STRIDE = 16
+INFO_KEYS = ["obs", "smooth", "cost", "collide", "reach", "grad", "weighted_obs_grad", "weighted_smooth_grad",
+             "terminate", "violate_limit", "execute", "failure_terminate", "p_in", "nonzero", "limit_rounds",
+             "reserved"]
+
+EXPORTS = ["omgb_version", "omgb_last_error", "omgb_scene_create", "omgb_scene_destroy", "omgb_scene_set_robot",
+           "omgb_scene_set_sdf", "omgb_scene_set_objects", "omgb_scene_set_metric",
+           "omgb_sdf_loss_workspace_bytes", "omgb_sdf_loss", "omgb_chomp_step", "omgb_chomp_plan",
+           "omgb_chomp_step_host", "omgb_batch_obstacle_cost"]
+
+
+class StepParams(ctypes.Structure):
+    """omgb_step_params_t"""
+    _fields_ = [
+        ("n_waypoints", ctypes.c_int32), ("goal_set_proj", ctypes.c_int32), ("constraint_rows", ctypes.c_int32),
+        ("top_k_collision", ctypes.c_int32), ("uncheck_finger_collision", ctypes.c_int32),
+        ("consider_finger", ctypes.c_int32), ("allow_collision_point", ctypes.c_int32),
+        ("pre_terminate", ctypes.c_int32), ("joint_limit_max_steps", ctypes.c_int32), ("update", ctypes.c_int32),
+        ("time_interval", ctypes.c_double), ("obstacle_weight", ctypes.c_double),
+        ("smoothness_weight", ctypes.c_double), ("step_size", ctypes.c_double), ("clip_grad_scale", ctypes.c_double),
+        ("terminate_smooth_loss", ctypes.c_double), ("link_smooth_weight", ctypes.c_double * 9),
+    ]
+
+
+def nvcc_command(out=LIB_PATH):
+    return ["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-shared",
+            "-Xcompiler", "-fPIC,-ffp-contract=off", "-o", out, SOURCES[0]]
+
+
+def build(force=False, verbose=False):
+    """Compile libomgb200.so for sm_100a in-tree (nvcc cross-compiles without a GPU)."""
+    newest = max(os.path.getmtime(s) for s in SOURCES)
+    if not force and os.path.exists(LIB_PATH) and os.path.getmtime(LIB_PATH) >= newest:
+        return LIB_PATH
+    os.makedirs(os.path.dirname(LIB_PATH), exist_ok=True)
+    cmd = nvcc_command()
+    if verbose:
+        cmd.insert(1, "-Xptxas=-v")
+    subprocess.check_call(cmd)
+    return LIB_PATH
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            "libomgb200.so is not built (%s). Run `python -c 'import __graft_entry__ as g; g.build()'`. "
+            "There is no CPU fallback for the CHOMP hot path." % LIB_PATH)
+    L = ctypes.CDLL(LIB_PATH)
+    vp, ci, cd = ctypes.c_void_p, ctypes.c_int, ctypes.c_double
+    L.omgb_version.restype = ci
+    L.omgb_last_error.restype = ctypes.c_char_p
+    L.omgb_scene_create.argtypes = [ctypes.POINTER(vp), ci]
+    L.omgb_scene_destroy.argtypes = [vp]
+    L.omgb_scene_set_robot.argtypes = [vp, vp, vp, vp, vp, ci, vp, vp, ci, vp, vp]
+    L.omgb_scene_set_sdf.argtypes = [vp, vp, vp, ci, ci, ci, ci]
+    L.omgb_scene_set_objects.argtypes = [vp, vp, vp, vp, vp, vp, vp]
+    L.omgb_scene_set_metric.argtypes = [vp, ci, vp, ci, vp]
+    L.omgb_sdf_loss_workspace_bytes.restype = ctypes.c_size_t
+    L.omgb_sdf_loss_workspace_bytes.argtypes = [ci]
+    L.omgb_sdf_loss.argtypes = [vp] * 8 + [ci] * 5 + [vp] * 5
+    L.omgb_chomp_step.argtypes = [vp, ctypes.POINTER(StepParams), ci] + [vp] * 11
+    L.omgb_chomp_plan.argtypes = [vp, ctypes.POINTER(StepParams), ci, vp, vp, vp, ci, ci] + [vp] * 7
+    L.omgb_chomp_step_host.argtypes = [vp, ctypes.POINTER(StepParams), ci] + [vp] * 6
+    L.omgb_batch_obstacle_cost.argtypes = [vp, vp, ci, ci, vp, cd, ci, vp, vp, vp, vp]
+    for name in EXPORTS:
+        fn = getattr(L, name)
+        if name not in ("omgb_version", "omgb_last_error", "omgb_sdf_loss_workspace_bytes"):
+            fn.restype = ci
+    _lib = L
+    return L
+
+
+def check(rc, what=""):
+    if rc != 0:
+        msg = lib().omgb_last_error()
+        raise RuntimeError("%s failed (status %d): %s" % (what or "libomgb200", rc, msg.decode() if msg else "?"))

@@ -1,0 +1,227 @@
+"""Cost: the reference's plugin surface for the obstacle/smoothness cost (omg/cost.py:12-532), with every
+number produced by the fused sm_100a kernels.  Constructor arguments, public method names, argument
+meaning and the info dict keys follow the reference so Planner/Learner keep working unchanged
+(omg/planner.py:100-101,115; omg/online_learner.py:134).
+
+Batched extension: a trajectory object whose .data is [B,n,9] (and .start/.end [B,9]) is processed in one
+launch; a plain [n,9] trajectory behaves exactly like the reference."""
+import numpy as np
+import torch
+
+from .engine import ChompEngine
+from .sdf_matching_loss import SDFLoss
+
+
+class _RobotView(object):
+    """What ChompEngine.set_robot needs, read from the reference's Robot/robot_kinematics objects
+    (omg/core.py:140-164; robot_pykdl.py:101-110)."""
+
+    def __init__(self, robot):
+        rk = robot.robot_kinematics
+        f = lambda a: np.ascontiguousarray(np.array(a), dtype=np.float64)
+        self.pose_0, self.tip2joint, self.joint_axis = f(rk._pose_0), f(rk._tip2joint), f(rk._joint_axis)
+        # whatever the reference object holds as "origin" (aliased to the axis list at robot_pykdl.py:104)
+        self.joint_origin_true = f(rk._joint_origin)
+        self.center_offset = f(rk.center_offset)
+        self.collision_points = f(robot.collision_points)
+        self.joint_lower_limit, self.joint_upper_limit = f(robot.joint_lower_limit), f(robot.joint_upper_limit)
+
+
+def se3_inverse_f32(rt):
+    """World->object pose as fp32 (omg/util.py:129-135 semantics: fp64 product rounded to fp32)."""
+    rt = np.asarray(rt, dtype=np.float64)
+    out = np.eye(4, dtype=np.float32)
+    out[:3, :3] = rt[:3, :3].T
+    out[:3, 3] = -(rt[:3, :3].T @ rt[:3, 3])
+    return out
+
+
+class Cost(object):
+    def __init__(self, env):
+        self.env = env
+        self.cfg = env.config
+        self.sdf_loss = SDFLoss()
+        if len(self.env.objects) > 0:
+            self.target_obj = self.env.objects[self.env.target_idx]
+        self.engine = ChompEngine()
+        self._robot_sig = None
+        self._sdf_sig = None
+        self._obj_sig = None
+
+    # ---- scene synchronisation (host) ----------------------------------------------------------------
+    def object_params(self):
+        """Per-object operator parameters (omg/cost.py:303-328)."""
+        cfg, objs = self.cfg, self.env.objects
+        num = len(objs)
+        poses = np.zeros((num, 4, 4), np.float32)
+        eps = np.full(num, cfg.epsilon, np.float32)
+        pad = np.ones(num, np.float32)
+        clr = np.full(num, cfg.clearance, np.float32)
+        dis = np.zeros(num, np.float32)
+        for i, ob in enumerate(objs):
+            if ob.name == "floor" or ob.name in cfg.disable_collision_set:
+                dis[i] = 1
+            poses[i] = se3_inverse_f32(ob.pose_mat)
+        t = self.env.target_idx
+        clr[t], eps[t] = cfg.target_clearance, cfg.target_epsilon
+        if getattr(objs[t], "attached", False):   # placing: table parameters (cost.py:325-328)
+            clr[-1], eps[-1], pad[-1] = 0.0, 0.05, 0.5
+        return poses, eps, pad, clr, dis
+
+    def sync(self):
+        robot = self.env.robot
+        sig = (np.asarray(robot.collision_points, dtype=np.float64).tobytes(),
+               np.asarray(robot.joint_lower_limit).tobytes(), np.asarray(robot.joint_upper_limit).tobytes())
+        if sig != self._robot_sig:
+            self.engine.set_robot(_RobotView(robot), use_true_joint_origin=True)
+            self._robot_sig = sig
+        grids = self.env.sdf_torch
+        ssig = (grids.data_ptr(), tuple(grids.shape), getattr(grids, "_version", 0))
+        if ssig != self._sdf_sig:
+            self.engine.set_sdf(grids, self.env.sdf_limits)
+            self._sdf_sig, self._obj_sig = ssig, None
+        params = self.object_params()
+        osig = b"".join(p.tobytes() for p in params)
+        if osig != self._obj_sig:
+            self.engine.set_objects(*params)
+            self._obj_sig = osig
+
+    # ---- reference API ----------------------------------------------------------------------------------
+    def _traj_tensors(self, traj):
+        dev = self.engine.device
+        data = np.asarray(traj.data, dtype=np.float64)
+        batched = data.ndim == 3
+        xi = torch.from_numpy(np.ascontiguousarray(data if batched else data[None])).to(dev)
+        B = xi.shape[0]
+        bc = lambda a: torch.from_numpy(np.ascontiguousarray(
+            np.broadcast_to(np.asarray(a, dtype=np.float64).reshape((-1, 9))[-B:] if np.ndim(a) > 1
+                            else np.asarray(a, dtype=np.float64)[None], (B, 9)))).to(dev)
+        start, end = bc(traj.start), bc(traj.end)
+        rows = None
+        if self.cfg.goal_set_proj:
+            c = self.engine_cfg().constraint_rows
+            if self.cfg.use_standoff:   # omg/optimizer.py:93-98
+                goal = np.asarray(self.target_obj.reach_grasps)[np.atleast_1d(traj.goal_idx).astype(int)]
+            else:
+                goal = np.asarray(traj.goal_set)[np.atleast_1d(traj.goal_idx).astype(int)][:, None]
+            rows = torch.from_numpy(np.ascontiguousarray(np.broadcast_to(goal, (B, c, 9)), dtype=np.float64)).to(dev)
+        return xi, start, end, rows, batched
+
+    def engine_cfg(self):
+        """Snapshot of cfg with the derived fields ChompEngine reads."""
+        cfg = self.cfg
+        if not hasattr(cfg, "constraint_rows"):
+            class _View(object):
+                pass
+            v = _View()
+            v.__dict__.update(dict(cfg) if isinstance(cfg, dict) else cfg.__dict__)
+            v.constraint_rows = 0 if not cfg.goal_set_proj else (cfg.reach_tail_length if cfg.use_standoff else 1)
+            ainv = np.asarray(cfg.Ainv)
+
+            def projection_matrix(c, ainv=ainv):
+                if c == 0:
+                    return None
+                n = ainv.shape[0]
+                C = np.zeros([c, n]); C[-c:, -c:] = np.eye(c)
+                return ainv.dot(C.T).dot(np.linalg.inv(C.dot(ainv.dot(C.T))))
+            v.projection_matrix = projection_matrix
+            return v
+        return cfg
+
+    def _info_dicts(self, cfg, out, xi_before, update_mode):
+        info_t = out["info"].cpu().numpy()
+        grad = out["grad"].cpu().numpy()
+        rows = out["row_obs"].cpu().numpy()
+        infos = []
+        n = xi_before.shape[1]
+        for b in range(info_t.shape[0]):
+            r = info_t[b]
+            smooth_rows = self._smooth_rows(cfg, xi_before[b])
+            info = {
+                "collision_pts": None, "obs": r[0], "smooth": r[1], "grasp": 0, "weighted_obs": cfg.obstacle_weight * r[0],
+                "weighted_smooth": cfg.smoothness_weight * r[1], "weighted_smooth_grad": r[7], "weighted_obs_grad": r[6],
+                "weighted_grasp_grad": 0, "weighted_grasp": 0, "gradient": grad[b], "failure_terminate": bool(r[11]),
+                "cost": r[2], "grad": r[5], "terminate": bool(r[8]), "collide": r[3],
+                "standoff_idx": n - cfg.reach_tail_length if cfg.use_standoff else n - 1, "reach": r[4],
+                "execute": bool(r[10]), "violate_limit": bool(r[9]),
+                "cost_traj": cfg.obstacle_weight * rows[b] + cfg.smoothness_weight * smooth_rows[:-1],
+                "p_in": r[12],
+            }
+            infos.append(info)
+        return infos
+
+    @staticmethod
+    def _smooth_rows(cfg, xi):
+        """Per-row smoothness loss (omg/cost.py:429-445) on the host, only for info['cost_traj']."""
+        w = np.asarray(cfg.link_smooth_weight)[None]
+        vel = np.asarray(cfg.diff_matrices[0]).dot(xi)
+        return 0.5 * np.linalg.norm(vel * w, axis=1) ** 2
+
+    def evaluate(self, traj, update_mode=0):
+        """One fused iteration; update_mode as omgb_step_params_t.update.  Returns (infos, new_xi, batched)."""
+        self.sync()
+        cfg = self.engine_cfg()
+        xi, start, end, rows, batched = self._traj_tensors(traj)
+        before = xi.cpu().numpy()
+        want_dbg = bool(getattr(self.cfg, "vis", False))
+        out = self.engine.step(cfg, xi, start, end, rows, update=update_mode, want_grad=True, debug=want_dbg,
+                               want_row_obs=True)
+        infos = self._info_dicts(cfg, out, before, update_mode)
+        if want_dbg:
+            self._fill_collision_pts(infos, out)
+        return infos, xi.cpu().numpy(), batched
+
+    def _fill_collision_pts(self, infos, out):
+        """info['collision_pts'] [n,10,p,12] (omg/cost.py:355-358): xyz, potential, potential gradient."""
+        pts, pot = out["points"], out["potentials"]
+        B, n, m, p = pot.shape
+        poses, eps, pad, clr, dis = (torch.from_numpy(a).to(pts.device) for a in self.object_params())
+        _, grads, _ = self.sdf_loss(poses, self.env.sdf_torch, self.env.sdf_limits.to(pts.device).float().contiguous(),
+                                    pts.reshape(-1, 3).contiguous(), eps, pad, clr, dis)
+        grads = grads.reshape(B, n, m, p, 3).cpu().numpy()
+        for b, info in enumerate(infos):
+            vis = np.zeros([n, m, p, 12])
+            vis[..., :3] = pts[b].cpu().numpy(); vis[..., 6] = pot[b].cpu().numpy(); vis[..., 9:] = grads[b]
+            info["collision_pts"] = vis
+
+    def compute_total_loss(self, traj):
+        """(cost, grad, info) like omg/cost.py:451-532 (no update)."""
+        infos, _, batched = self.evaluate(traj, update_mode=0)
+        if batched:
+            return (np.array([i["cost"] for i in infos]), np.stack([i["gradient"] for i in infos]), infos)
+        return infos[0]["cost"], infos[0]["gradient"], infos[0]
+
+    def compute_obstacle_cost_layer(self, ws_positions, vis_pts=None, special_check_id=0,
+                                    uncheck_finger_collision=-1, grad_free=True):
+        """omg/cost.py:288-360: ws_positions [n,m,p,3] torch CUDA fp32 -> potentials, grads, collides."""
+        n, m, p, _ = ws_positions.shape
+        dev = ws_positions.device
+        poses, eps, pad, clr, dis = (torch.from_numpy(a).to(dev) for a in self.object_params())
+        pot, grad, col = self.sdf_loss(poses, self.env.sdf_torch, self.env.sdf_limits.float().contiguous(),
+                                       ws_positions.reshape(-1, 3).contiguous().float(), eps, pad, clr, dis)
+        pot, grad, col = pot.reshape(n, m, p), grad.reshape(n, m, p, 3), col.reshape(n, m, p)
+        if uncheck_finger_collision == -1:
+            pot[:, -2:] *= 0.1; grad[:, -2:] *= 0.1; col[:, -2:] = 0
+        if vis_pts is not None:
+            vis_pts[:, :m, :, :3] = ws_positions.detach().cpu().numpy()
+            vis_pts[:, :m, :, 6] = pot.detach().cpu().numpy()
+            vis_pts[:, :m, :, 9:] = grad.detach().cpu().numpy()
+        return pot, grad, col
+
+    def batch_obstacle_cost(self, joints, arc_length=-1, only_collide=False, special_check_id=0,
+                            uncheck_finger_collision=-1, start=None, end=None):
+        """omg/cost.py:192-286.  Returns (potentials [M,10,p], grad [M,10,p,3], vis_pts, collide) as CUDA
+        tensors (vis_pts: numpy [M,10,p,12] with xyz unset unless cfg.vis)."""
+        self.sync()
+        dev = self.engine.device
+        q = torch.from_numpy(np.ascontiguousarray(np.asarray(joints, dtype=np.float64).reshape(-1, 9))).to(dev)
+        st = None
+        if arc_length > 0:
+            st = torch.from_numpy(np.ascontiguousarray(np.asarray(start, dtype=np.float64).reshape(9))).to(dev)
+        pot, grad, col = self.engine.batch_obstacle_cost(q, arc_length, st, float(self.cfg.time_interval),
+                                                         uncheck_finger_collision, want_grad=True)
+        if only_collide:   # cost.py:279-284
+            thr = 0.5 * (self.cfg.epsilon - self.cfg.clearance) ** 2 / self.cfg.epsilon
+            pot = pot * (pot > thr).any()
+        vis_pts = np.zeros([pot.shape[0], pot.shape[1], pot.shape[2], 12])
+        return pot, grad, vis_pts, col

@@ -1,0 +1,568 @@
+// libomgb200.so -- C ABI (include/omgb200.h) over the sm_100a kernels.  No torch, no Eigen, no Sophus.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/omgb200.h"
+#include "chomp_kernels.cuh"
+#include "sdf_device.cuh"
+
+namespace omgb {
+
+static thread_local std::string g_err;
+
+static int fail(int code, const std::string &msg) {
+    g_err = msg;
+    return code;
+}
+
+#define OMGB_CUDA(call)                                                                      \
+    do {                                                                                     \
+        cudaError_t e_ = (call);                                                             \
+        if (e_ != cudaSuccess)                                                               \
+            return fail(OMGB_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); \
+    } while (0)
+
+// ----------------------------------------------------------------------------------------------------
+// per-object preparation: quaternion of the pose (what Sophus::SE3<float>(Matrix4) holds,
+// se3.hpp:387-389 / so3.hpp:392), its rotation matrix (so3().matrix(), kernel.cu:126), grid constants.
+// All ops separately rounded (no contraction) so the record is bit-identical to oracle/sdf_loss_ref.c.
+// ----------------------------------------------------------------------------------------------------
+__global__ void prep_objects_kernel(const float *__restrict__ pose, const float *__restrict__ limits,
+                                    const float *__restrict__ eps, const float *__restrict__ pad,
+                                    const float *__restrict__ clr, const float *__restrict__ dis, int num_objects,
+                                    ObjRec *__restrict__ out) {
+    const int o = blockIdx.x * blockDim.x + threadIdx.x;
+    if (o >= num_objects) return;
+    const float *P = pose + 16 * o;
+    float m[3][3] = {{P[0], P[1], P[2]}, {P[4], P[5], P[6]}, {P[8], P[9], P[10]}};
+    float q[3], w;
+    float t = __fadd_rn(__fadd_rn(m[0][0], m[1][1]), m[2][2]);
+    if (t > 0.0f) {
+        t = __fsqrt_rn(__fadd_rn(t, 1.0f));
+        w = __fmul_rn(0.5f, t);
+        t = __fdiv_rn(0.5f, t);
+        q[0] = __fmul_rn(__fsub_rn(m[2][1], m[1][2]), t);
+        q[1] = __fmul_rn(__fsub_rn(m[0][2], m[2][0]), t);
+        q[2] = __fmul_rn(__fsub_rn(m[1][0], m[0][1]), t);
+    } else {
+        int i = 0;
+        if (m[1][1] > m[0][0]) i = 1;
+        if (m[2][2] > m[i][i]) i = 2;
+        const int j = (i + 1) % 3, k = (j + 1) % 3;
+        t = __fsqrt_rn(__fadd_rn(__fsub_rn(__fsub_rn(m[i][i], m[j][j]), m[k][k]), 1.0f));
+        q[i] = __fmul_rn(0.5f, t);
+        t = __fdiv_rn(0.5f, t);
+        w = __fmul_rn(__fsub_rn(m[k][j], m[j][k]), t);
+        q[j] = __fmul_rn(__fadd_rn(m[j][i], m[i][j]), t);
+        q[k] = __fmul_rn(__fadd_rn(m[k][i], m[i][k]), t);
+    }
+    ObjRec r;
+    r.qw = w; r.qx = q[0]; r.qy = q[1]; r.qz = q[2];
+    r.tx = P[3]; r.ty = P[7]; r.tz = P[11];
+    const float tx = __fmul_rn(2.0f, q[0]), ty = __fmul_rn(2.0f, q[1]), tz = __fmul_rn(2.0f, q[2]);
+    const float twx = __fmul_rn(tx, w), twy = __fmul_rn(ty, w), twz = __fmul_rn(tz, w);
+    const float txx = __fmul_rn(tx, q[0]), txy = __fmul_rn(ty, q[0]), txz = __fmul_rn(tz, q[0]);
+    const float tyy = __fmul_rn(ty, q[1]), tyz = __fmul_rn(tz, q[1]), tzz = __fmul_rn(tz, q[2]);
+    r.r[0] = __fsub_rn(1.0f, __fadd_rn(tyy, tzz)); r.r[1] = __fsub_rn(txy, twz); r.r[2] = __fadd_rn(txz, twy);
+    r.r[3] = __fadd_rn(txy, twz); r.r[4] = __fsub_rn(1.0f, __fadd_rn(txx, tzz)); r.r[5] = __fsub_rn(tyz, twx);
+    r.r[6] = __fsub_rn(txz, twy); r.r[7] = __fadd_rn(tyz, twx); r.r[8] = __fsub_rn(1.0f, __fadd_rn(txx, tyy));
+    const float *lim = limits + 10 * o;
+    r.minx = lim[0]; r.miny = lim[1]; r.minz = lim[2];
+    r.ex = __fsub_rn(lim[3], lim[0]); r.ey = __fsub_rn(lim[4], lim[1]); r.ez = __fsub_rn(lim[5], lim[2]);
+    r.d0 = (int)lim[6]; r.d1 = (int)lim[7]; r.d2 = (int)lim[8];
+    r.fd0 = (float)r.d0; r.fd1 = (float)r.d1; r.fd2 = (float)r.d2;
+    r.delta = lim[9];
+    r.eps = eps[o]; r.pad = pad[o]; r.clr = clr[o]; r.dis = dis[o];
+    r.inv2eps = __fdiv_rn(1.0f, __fmul_rn(2.0f, r.eps));
+    r.inveps = __fdiv_rn(1.0f, r.eps);
+    const float sx = r.ex / r.fd0, sy = r.ey / r.fd1, sz = r.ez / r.fd2;
+    r.lox = r.minx - 0.5f * sx; r.hix = r.minx + (r.fd0 - 0.5f) * sx;
+    r.loy = r.miny - 0.5f * sy; r.hiy = r.miny + (r.fd1 - 0.5f) * sy;
+    r.loz = r.minz - 0.5f * sz; r.hiz = r.minz + (r.fd2 - 0.5f) * sz;
+    // An out-of-bounds sample reads 1.0 (kernel.cu:47-48): it contributes nothing iff eps < 1 and
+    // clearance <= 1.  Otherwise the cull must never reject.
+    r.cull_pad = (r.eps < 1.0f && r.clr <= 1.0f) ? (1e-3f + fmaxf(sx, fmaxf(sy, sz))) : 1e30f;
+    r.grid_offset = (long long)o * r.d0 * r.d1 * r.d2;
+    out[o] = r;
+}
+
+// ----------------------------------------------------------------------------------------------------
+// raw operator: drop-in for omg_cuda.sdf_loss_forward (one thread per point, objects in ascending order)
+// ----------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) sdf_loss_kernel(const ObjRec *__restrict__ objs, int num_objects,
+                                                       const float *__restrict__ grids,
+                                                       const float *__restrict__ points, int num_points,
+                                                       float *__restrict__ potentials,
+                                                       float *__restrict__ potential_grads,
+                                                       float *__restrict__ collides) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    ObjRec *s_objs = reinterpret_cast<ObjRec *>(smem_raw);
+    {
+        const int words = (int)(sizeof(ObjRec) / 4) * num_objects;
+        const uint32_t *src = reinterpret_cast<const uint32_t *>(objs);
+        uint32_t *dst = reinterpret_cast<uint32_t *>(s_objs);
+        for (int k = threadIdx.x; k < words; k += blockDim.x) dst[k] = src[k];
+    }
+    __syncthreads();
+    for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < num_points; n += gridDim.x * blockDim.x) {
+        const float x = points[3 * n], y = points[3 * n + 1], z = points[3 * n + 2];
+        float pot = 0.0f, gx = 0.0f, gy = 0.0f, gz = 0.0f, col = 0.0f;
+        for (int o = 0; o < num_objects; ++o) {
+            const ObjRec &ob = s_objs[o];
+            if (ob.dis > 0.0f) continue;   // kernel.cu:115
+            float po, ax, ay, az, co;
+            pair_full(ob, grids, x, y, z, po, ax, ay, az, co);
+            pot = __fadd_rn(pot, po);
+            gx = __fadd_rn(gx, ax); gy = __fadd_rn(gy, ay); gz = __fadd_rn(gz, az);
+            col = __fadd_rn(col, co);
+        }
+        potentials[n] = pot;
+        potential_grads[3 * n] = gx; potential_grads[3 * n + 1] = gy; potential_grads[3 * n + 2] = gz;
+        collides[n] = col;
+    }
+}
+
+// ----------------------------------------------------------------------------------------------------
+// Cost.batch_obstacle_cost (omg/cost.py:192-286): FK + operator (+ arc-length weighting) for M configs
+// ----------------------------------------------------------------------------------------------------
+constexpr int BOC_CFG = 8;   // configurations per CTA
+
+__global__ void __launch_bounds__(256) batch_obstacle_cost_kernel(
+    const ObjRec *__restrict__ objs, int num_objects, const float *__restrict__ grids,
+    const RobotConst *__restrict__ rc, const double *__restrict__ joints, int num_configs, int arc_length,
+    const double *__restrict__ start, float inv_dt, int finger_soft, float *__restrict__ potentials,
+    float *__restrict__ grads, float *__restrict__ collides) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    ObjRec *s_objs = reinterpret_cast<ObjRec *>(smem_raw);
+    double *s_frames = reinterpret_cast<double *>(smem_raw + align_up(sizeof(ObjRec) * num_objects, 16));
+    // frames of configs m0-1 (halo / start), m0 .. m0+BOC_CFG-1
+    const int m0 = blockIdx.x * BOC_CFG;
+    {
+        const int words = (int)(sizeof(ObjRec) / 4) * num_objects;
+        const uint32_t *src = reinterpret_cast<const uint32_t *>(objs);
+        uint32_t *dst = reinterpret_cast<uint32_t *>(s_objs);
+        for (int k = threadIdx.x; k < words; k += blockDim.x) dst[k] = src[k];
+    }
+    if (threadIdx.x < BOC_CFG + 2) {
+        // slot 0: config m0-1 (halo), slots 1..BOC_CFG: configs m0.., slot BOC_CFG+1: FK(start)
+        const int m = m0 - 1 + (int)threadIdx.x;
+        const double *q = nullptr;
+        if (threadIdx.x == BOC_CFG + 1) {
+            if (arc_length > 0) q = start;
+        } else if (threadIdx.x == 0) {
+            if (arc_length > 0 && m >= 0) q = joints + (size_t)m * ND;
+        } else if (m < num_configs) {
+            q = joints + (size_t)m * ND;
+        }
+        if (q) {
+            double ql[ND];
+#pragma unroll
+            for (int d = 0; d < ND; ++d) ql[d] = q[d];
+            panda_fk(rc, ql, s_frames + (size_t)threadIdx.x * NL * 12, nullptr);
+        }
+    }
+    __syncthreads();
+    const int P = rc->p;
+    const int per_cfg = NL * P;
+    for (int k = threadIdx.x; k < BOC_CFG * per_cfg; k += blockDim.x) {
+        const int lc = k / per_cfg, r = k - lc * per_cfg;
+        const int m = m0 + lc;
+        if (m >= num_configs) break;
+        const int j = r / P, p = r - j * P;
+        const double *F = s_frames + ((size_t)(lc + 1) * NL + j) * 12;
+        double X, Y, Z;
+        xform(F, rc->pts[j][p][0], rc->pts[j][p][1], rc->pts[j][p][2], X, Y, Z);
+        const float x = (float)X, y = (float)Y, z = (float)Z;
+        float pot = 0.0f, gx = 0.0f, gy = 0.0f, gz = 0.0f, col = 0.0f;
+        for (int o = 0; o < num_objects; ++o) {
+            const ObjRec &ob = s_objs[o];
+            if (ob.dis > 0.0f) continue;
+            float po, ax, ay, az, co;
+            pair_full(ob, grids, x, y, z, po, ax, ay, az, co);
+            pot = __fadd_rn(pot, po);
+            gx = __fadd_rn(gx, ax); gy = __fadd_rn(gy, ay); gz = __fadd_rn(gz, az);
+            col = __fadd_rn(col, co);
+        }
+        if (finger_soft && j >= 8) {
+            pot = __fmul_rn(pot, 0.1f); gx = __fmul_rn(gx, 0.1f); gy = __fmul_rn(gy, 0.1f);
+            gz = __fmul_rn(gz, 0.1f); col = 0.0f;
+        }
+        if (arc_length > 0) {   // potential x |workspace velocity| (cost.py:235-275, config.py:162-187), fp32
+            // previous configuration of the same group, or FK(start) for the first of a group
+            const bool first_in_group = (m % arc_length) == 0;
+            const double *Fp = s_frames + ((size_t)(first_in_group ? BOC_CFG + 1 : lc) * NL + j) * 12;
+            double Xp, Yp, Zp;
+            xform(Fp, rc->pts[j][p][0], rc->pts[j][p][1], rc->pts[j][p][2], Xp, Yp, Zp);
+            const float vx = (x - (float)Xp) * inv_dt, vy = (y - (float)Yp) * inv_dt, vz = (z - (float)Zp) * inv_dt;
+            pot *= sqrtf(vx * vx + vy * vy + vz * vz);
+        }
+        const size_t idx = (size_t)m * per_cfg + r;
+        potentials[idx] = pot;
+        collides[idx] = col;
+        if (grads) { grads[3 * idx] = gx; grads[3 * idx + 1] = gy; grads[3 * idx + 2] = gz; }
+    }
+}
+
+}  // namespace omgb
+
+using namespace omgb;
+
+// ----------------------------------------------------------------------------------------------------
+// scene
+// ----------------------------------------------------------------------------------------------------
+struct omgb_scene {
+    int device = 0;
+    RobotConst *d_robot = nullptr;
+    bool robot_set = false;
+    int p = 0;
+    const float *d_grids = nullptr;
+    float *d_limits = nullptr;
+    int num_objects = 0, gx = 0, gy = 0, gz = 0;
+    bool sdf_set = false;
+    float *d_objparams = nullptr;   // pose[16 O] eps[O] pad[O] clr[O] dis[O]
+    ObjRec *d_objs = nullptr;
+    bool objs_set = false;
+    double *d_Ainv = nullptr, *d_proj = nullptr;
+    int n = 0, c = 0;
+    bool metric_set = false;
+    // staging for the host-buffer entry point
+    double *d_stage = nullptr;
+    size_t stage_bytes = 0;
+    int smem_optin = 0;
+};
+
+extern "C" int omgb_version(void) { return OMGB_VERSION; }
+extern "C" const char *omgb_last_error(void) { return g_err.c_str(); }
+
+extern "C" int omgb_scene_create(omgb_scene_t **out, int device) {
+    if (!out) return fail(OMGB_ERR_INVALID, "omgb_scene_create: out is null");
+    OMGB_CUDA(cudaSetDevice(device));
+    omgb_scene *s = new omgb_scene();
+    s->device = device;
+    cudaError_t e = cudaMalloc(&s->d_robot, sizeof(RobotConst));
+    if (e != cudaSuccess) { delete s; return fail(OMGB_ERR_CUDA, cudaGetErrorString(e)); }
+    cudaDeviceGetAttribute(&s->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+    *out = s;
+    return OMGB_OK;
+}
+
+extern "C" int omgb_scene_destroy(omgb_scene_t *s) {
+    if (!s) return OMGB_OK;
+    cudaSetDevice(s->device);
+    cudaFree(s->d_robot); cudaFree(s->d_limits); cudaFree(s->d_objparams); cudaFree(s->d_objs);
+    cudaFree(s->d_Ainv); cudaFree(s->d_proj); cudaFree(s->d_stage);
+    delete s;
+    return OMGB_OK;
+}
+
+static void mat34(const double *m44, double *out12) {
+    for (int r = 0; r < 3; ++r) {
+        for (int c = 0; c < 3; ++c) out12[3 * r + c] = m44[4 * r + c];
+        out12[9 + r] = m44[4 * r + 3];
+    }
+}
+
+extern "C" int omgb_scene_set_robot(omgb_scene_t *s, const double *pose_0, const double *tip2joint,
+                                    const double *joint_axis, const double *joint_origin, int use_true_origin,
+                                    const double *center_offset, const double *body_points, int p,
+                                    const double *lower, const double *upper) {
+    if (!s || !pose_0 || !tip2joint || !joint_axis || !center_offset || !body_points || !lower || !upper)
+        return fail(OMGB_ERR_INVALID, "omgb_scene_set_robot: null argument");
+    if (p < 1 || p > OMGB_MAX_BODY_POINTS) return fail(OMGB_ERR_INVALID, "points_per_link out of range");
+    if (use_true_origin && !joint_origin) return fail(OMGB_ERR_INVALID, "joint_origin required");
+    OMGB_CUDA(cudaSetDevice(s->device));
+    std::vector<RobotConst> hv(1);
+    RobotConst &h = hv[0];
+    memset(&h, 0, sizeof(h));
+    for (int i = 0; i < 10; ++i) {
+        mat34(pose_0 + 16 * i, h.P0[i]);
+        mat34(center_offset + 16 * i, h.CO[i]);
+        const double *t2j = tip2joint + 16 * i;
+        const double *ax = joint_axis + 3 * i;
+        const double *og = use_true_origin ? joint_origin + 3 * i : ax;   // robot_pykdl.py:104 aliasing
+        for (int r = 0; r < 3; ++r) {
+            h.ja[i][r] = t2j[4 * r] * ax[0] + t2j[4 * r + 1] * ax[1] + t2j[4 * r + 2] * ax[2];
+            h.jo[i][r] = t2j[4 * r] * og[0] + t2j[4 * r + 1] * og[1] + t2j[4 * r + 2] * og[2] + t2j[4 * r + 3];
+        }
+        // bounding sphere of the link's body points (centre = midpoint of the AABB)
+        double lo[3] = {1e30, 1e30, 1e30}, hi[3] = {-1e30, -1e30, -1e30};
+        for (int k = 0; k < p; ++k)
+            for (int r = 0; r < 3; ++r) {
+                const double v = body_points[((size_t)i * p + k) * 3 + r];
+                h.pts[i][k][r] = v;
+                lo[r] = v < lo[r] ? v : lo[r];
+                hi[r] = v > hi[r] ? v : hi[r];
+            }
+        double cx[3] = {0.5 * (lo[0] + hi[0]), 0.5 * (lo[1] + hi[1]), 0.5 * (lo[2] + hi[2])}, rad = 0;
+        for (int k = 0; k < p; ++k) {
+            double d2 = 0;
+            for (int r = 0; r < 3; ++r) { const double d = h.pts[i][k][r] - cx[r]; d2 += d * d; }
+            rad = d2 > rad ? d2 : rad;
+        }
+        for (int r = 0; r < 3; ++r) h.sph[i][r] = (float)cx[r];
+        h.sph[i][3] = (float)(sqrt(rad) * 1.0001 + 1e-6);
+    }
+    for (int d = 0; d < ND; ++d) { h.lower[d] = lower[d]; h.upper[d] = upper[d]; }
+    h.p = p;
+    OMGB_CUDA(cudaMemcpy(s->d_robot, &h, sizeof(h), cudaMemcpyHostToDevice));
+    s->p = p;
+    s->robot_set = true;
+    return OMGB_OK;
+}
+
+extern "C" int omgb_scene_set_sdf(omgb_scene_t *s, const float *d_sdf_grids, const float *h_sdf_limits,
+                                  int num_objects, int dx, int dy, int dz) {
+    if (!s || !d_sdf_grids || !h_sdf_limits) return fail(OMGB_ERR_INVALID, "omgb_scene_set_sdf: null argument");
+    if (num_objects < 1 || num_objects > OMGB_MAX_OBJECTS)
+        return fail(OMGB_ERR_INVALID, "num_objects must be in [1, OMGB_MAX_OBJECTS]");
+    for (int o = 0; o < num_objects; ++o) {
+        const float *l = h_sdf_limits + 10 * o;
+        if ((int)l[6] != dx || (int)l[7] != dy || (int)l[8] != dz)
+            return fail(OMGB_ERR_INVALID, "sdf_limits dims disagree with the packed grid shape");
+    }
+    OMGB_CUDA(cudaSetDevice(s->device));
+    if (num_objects != s->num_objects) {
+        cudaFree(s->d_limits); cudaFree(s->d_objparams); cudaFree(s->d_objs);
+        s->d_limits = nullptr; s->d_objparams = nullptr; s->d_objs = nullptr;
+        OMGB_CUDA(cudaMalloc(&s->d_limits, sizeof(float) * 10 * num_objects));
+        OMGB_CUDA(cudaMalloc(&s->d_objparams, sizeof(float) * 20 * num_objects));
+        OMGB_CUDA(cudaMalloc(&s->d_objs, sizeof(ObjRec) * num_objects));
+    }
+    OMGB_CUDA(cudaMemcpy(s->d_limits, h_sdf_limits, sizeof(float) * 10 * num_objects, cudaMemcpyHostToDevice));
+    s->d_grids = d_sdf_grids;
+    s->num_objects = num_objects; s->gx = dx; s->gy = dy; s->gz = dz;
+    s->sdf_set = true;
+    s->objs_set = false;
+    return OMGB_OK;
+}
+
+extern "C" int omgb_scene_set_objects(omgb_scene_t *s, const float *pose_inv, const float *eps, const float *pad,
+                                      const float *clr, const float *dis, void *stream) {
+    if (!s || !pose_inv || !eps || !pad || !clr || !dis)
+        return fail(OMGB_ERR_INVALID, "omgb_scene_set_objects: null argument");
+    if (!s->sdf_set) return fail(OMGB_ERR_STATE, "omgb_scene_set_objects: call omgb_scene_set_sdf first");
+    OMGB_CUDA(cudaSetDevice(s->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int O = s->num_objects;
+    std::vector<float> h(20 * (size_t)O);
+    memcpy(h.data(), pose_inv, sizeof(float) * 16 * O);
+    memcpy(h.data() + 16 * O, eps, sizeof(float) * O);
+    memcpy(h.data() + 17 * O, pad, sizeof(float) * O);
+    memcpy(h.data() + 18 * O, clr, sizeof(float) * O);
+    memcpy(h.data() + 19 * O, dis, sizeof(float) * O);
+    OMGB_CUDA(cudaMemcpyAsync(s->d_objparams, h.data(), sizeof(float) * 20 * O, cudaMemcpyHostToDevice, st));
+    OMGB_CUDA(cudaStreamSynchronize(st));   // h goes out of scope
+    prep_objects_kernel<<<(O + 63) / 64, 64, 0, st>>>(s->d_objparams, s->d_limits, s->d_objparams + 16 * O,
+                                                      s->d_objparams + 17 * O, s->d_objparams + 18 * O,
+                                                      s->d_objparams + 19 * O, O, s->d_objs);
+    OMGB_CUDA(cudaGetLastError());
+    s->objs_set = true;
+    return OMGB_OK;
+}
+
+extern "C" int omgb_scene_set_metric(omgb_scene_t *s, int n, const double *h_Ainv, int c, const double *h_proj) {
+    if (!s || !h_Ainv || n < 2) return fail(OMGB_ERR_INVALID, "omgb_scene_set_metric: bad argument");
+    if (c < 0 || c > n || (c > 0 && !h_proj)) return fail(OMGB_ERR_INVALID, "omgb_scene_set_metric: bad constraint rows");
+    OMGB_CUDA(cudaSetDevice(s->device));
+    cudaFree(s->d_Ainv); cudaFree(s->d_proj);
+    s->d_Ainv = nullptr; s->d_proj = nullptr;
+    OMGB_CUDA(cudaMalloc(&s->d_Ainv, sizeof(double) * n * n));
+    OMGB_CUDA(cudaMemcpy(s->d_Ainv, h_Ainv, sizeof(double) * n * n, cudaMemcpyHostToDevice));
+    if (c > 0) {
+        OMGB_CUDA(cudaMalloc(&s->d_proj, sizeof(double) * n * c));
+        OMGB_CUDA(cudaMemcpy(s->d_proj, h_proj, sizeof(double) * n * c, cudaMemcpyHostToDevice));
+    }
+    s->n = n; s->c = c;
+    s->metric_set = true;
+    return OMGB_OK;
+}
+
+// ----------------------------------------------------------------------------------------------------
+// raw operator
+// ----------------------------------------------------------------------------------------------------
+extern "C" size_t omgb_sdf_loss_workspace_bytes(int num_objects) {
+    return sizeof(ObjRec) * (size_t)(num_objects > 0 ? num_objects : 0);
+}
+
+extern "C" int omgb_sdf_loss(const float *pose_init, const float *sdf_grids, const float *sdf_limits,
+                             const float *points, const float *epsilons, const float *padding_scales,
+                             const float *clearances, const float *disables, int num_points, int num_objects,
+                             int dx, int dy, int dz, float *potentials, float *potential_grads, float *collides,
+                             void *workspace, void *stream) {
+    if (!pose_init || !sdf_grids || !sdf_limits || !epsilons || !padding_scales || !clearances || !disables ||
+        !workspace)
+        return fail(OMGB_ERR_INVALID, "omgb_sdf_loss: null argument");
+    if (num_points < 0 || num_objects < 1 || dx < 2 || dy < 2 || dz < 2)
+        return fail(OMGB_ERR_INVALID, "omgb_sdf_loss: bad sizes");
+    if (num_points == 0) return OMGB_OK;
+    if (!points || !potentials || !potential_grads || !collides)
+        return fail(OMGB_ERR_INVALID, "omgb_sdf_loss: null argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    ObjRec *recs = reinterpret_cast<ObjRec *>(workspace);
+    prep_objects_kernel<<<(num_objects + 63) / 64, 64, 0, st>>>(pose_init, sdf_limits, epsilons, padding_scales,
+                                                                clearances, disables, num_objects, recs);
+    OMGB_CUDA(cudaGetLastError());
+    const size_t smem = sizeof(ObjRec) * (size_t)num_objects;
+    if (smem > 48 * 1024)
+        OMGB_CUDA(cudaFuncSetAttribute(sdf_loss_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int blocks = (num_points + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    sdf_loss_kernel<<<blocks, 256, smem, st>>>(recs, num_objects, sdf_grids, points, num_points, potentials,
+                                               potential_grads, collides);
+    OMGB_CUDA(cudaGetLastError());
+    return OMGB_OK;
+}
+
+// ----------------------------------------------------------------------------------------------------
+// fused CHOMP iteration
+// ----------------------------------------------------------------------------------------------------
+static int check_step(const omgb_scene *s, const omgb_step_params_t *prm, int batch, const char *who) {
+    if (!s || !prm) return fail(OMGB_ERR_INVALID, std::string(who) + ": null argument");
+    if (!s->robot_set || !s->sdf_set || !s->objs_set || !s->metric_set)
+        return fail(OMGB_ERR_STATE, std::string(who) + ": scene needs robot, sdf, objects and metric");
+    if (batch < 0) return fail(OMGB_ERR_INVALID, std::string(who) + ": negative batch");
+    if (prm->n_waypoints != s->n)
+        return fail(OMGB_ERR_INVALID, std::string(who) + ": n_waypoints differs from the metric set on the scene");
+    const int c = prm->goal_set_proj ? prm->constraint_rows : 0;
+    if (c != s->c || (prm->goal_set_proj && c < 1))
+        return fail(OMGB_ERR_INVALID, std::string(who) + ": constraint_rows differs from the metric set on the scene");
+    if (prm->consider_finger) return fail(OMGB_ERR_UNSUPPORTED, std::string(who) + ": consider_finger is not supported");
+    if (prm->top_k_collision < 0) return fail(OMGB_ERR_INVALID, std::string(who) + ": negative top_k_collision");
+    if (!(prm->time_interval > 0)) return fail(OMGB_ERR_INVALID, std::string(who) + ": time_interval must be > 0");
+    return OMGB_OK;
+}
+
+static int launch_step(omgb_scene *s, const StepArgs &a, cudaStream_t st) {
+    const int lpi = s->p <= 16 ? 16 : 32;
+    const SmemLayout L = make_layout(a.prm.n_waypoints, a.prm.constraint_rows, lpi, s->num_objects, s->p);
+    if (L.total > (size_t)s->smem_optin)
+        return fail(OMGB_ERR_UNSUPPORTED, "trajectory too long for one CTA's shared memory");
+    if (a.batch == 0) return OMGB_OK;
+    if (lpi == 16) {
+        OMGB_CUDA(cudaFuncSetAttribute(chomp_step_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
+        chomp_step_kernel<16><<<a.batch, 512, L.total, st>>>(a);
+    } else {
+        OMGB_CUDA(cudaFuncSetAttribute(chomp_step_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
+        chomp_step_kernel<32><<<a.batch, 512, L.total, st>>>(a);
+    }
+    OMGB_CUDA(cudaGetLastError());
+    return OMGB_OK;
+}
+
+static StepArgs make_args(const omgb_scene *s, const omgb_step_params_t *prm, int batch, double *xi,
+                          const double *start, const double *end, const double *goal_rows, const uint8_t *active,
+                          double *grad_out, double *info, float *dbg_pot, float *dbg_pts, double *row_obs = nullptr) {
+    StepArgs a;
+    memset(&a, 0, sizeof(a));
+    a.objs = s->d_objs; a.grids = s->d_grids; a.robot = s->d_robot; a.Ainv = s->d_Ainv; a.proj = s->d_proj;
+    a.xi = xi; a.start = start; a.end = end; a.goal_rows = goal_rows; a.active = active; a.done = nullptr;
+    a.grad_out = grad_out; a.info = info; a.dbg_pot = dbg_pot; a.dbg_pts = dbg_pts; a.row_obs = row_obs;
+    a.num_objects = s->num_objects; a.batch = batch; a.iteration = 0; a.stop_on_terminate = 0;
+    a.prm = *prm;
+    if (!a.prm.goal_set_proj) a.prm.constraint_rows = 0;
+    return a;
+}
+
+extern "C" int omgb_chomp_step(omgb_scene_t *s, const omgb_step_params_t *prm, int batch, double *xi,
+                               const double *start, const double *end, const double *goal_rows,
+                               const uint8_t *active, double *grad_out, double *info, float *dbg_pot,
+                               float *dbg_pts, double *row_obs, void *stream) {
+    int rc_ = check_step(s, prm, batch, "omgb_chomp_step");
+    if (rc_) return rc_;
+    if (!xi || !start || !end || !info || (prm->goal_set_proj && !goal_rows))
+        return fail(OMGB_ERR_INVALID, "omgb_chomp_step: null buffer");
+    OMGB_CUDA(cudaSetDevice(s->device));
+    StepArgs a = make_args(s, prm, batch, xi, start, end, goal_rows, active, grad_out, info, dbg_pot, dbg_pts, row_obs);
+    return launch_step(s, a, (cudaStream_t)stream);
+}
+
+extern "C" int omgb_chomp_plan(omgb_scene_t *s, const omgb_step_params_t *prm, int iters, const double *ow,
+                               const double *sw, const double *ss, int stop_on_terminate, int batch, double *xi,
+                               const double *start, const double *end, const double *goal_rows, uint8_t *done,
+                               double *info, void *stream) {
+    int rc_ = check_step(s, prm, batch, "omgb_chomp_plan");
+    if (rc_) return rc_;
+    if (iters < 0 || !ow || !sw || !ss) return fail(OMGB_ERR_INVALID, "omgb_chomp_plan: bad schedule");
+    if (!xi || !start || !end || !info || (prm->goal_set_proj && !goal_rows) || (stop_on_terminate && !done))
+        return fail(OMGB_ERR_INVALID, "omgb_chomp_plan: null buffer");
+    OMGB_CUDA(cudaSetDevice(s->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    if (done) OMGB_CUDA(cudaMemsetAsync(done, 0, (size_t)batch, st));
+    StepArgs a = make_args(s, prm, batch, xi, start, end, goal_rows, nullptr, nullptr, info, nullptr, nullptr);
+    a.done = stop_on_terminate ? done : nullptr;
+    a.stop_on_terminate = stop_on_terminate;
+    a.prm.update = 1;
+    for (int it = 0; it < iters; ++it) {
+        a.iteration = it;
+        a.prm.obstacle_weight = ow[it];
+        a.prm.smoothness_weight = sw[it];
+        a.prm.step_size = ss[it];
+        rc_ = launch_step(s, a, st);
+        if (rc_) return rc_;
+    }
+    return OMGB_OK;
+}
+
+extern "C" int omgb_chomp_step_host(omgb_scene_t *s, const omgb_step_params_t *prm, int batch, double *h_xi,
+                                    const double *h_start, const double *h_end, const double *h_goal_rows,
+                                    double *h_info, void *stream) {
+    int rc_ = check_step(s, prm, batch, "omgb_chomp_step_host");
+    if (rc_) return rc_;
+    if (!h_xi || !h_start || !h_end || !h_info || (prm->goal_set_proj && !h_goal_rows))
+        return fail(OMGB_ERR_INVALID, "omgb_chomp_step_host: null buffer");
+    if (batch == 0) return OMGB_OK;
+    OMGB_CUDA(cudaSetDevice(s->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int n = prm->n_waypoints, c = prm->goal_set_proj ? prm->constraint_rows : 0;
+    const size_t n_xi = (size_t)batch * n * ND, n_se = (size_t)batch * ND, n_goal = (size_t)batch * c * ND,
+                 n_info = (size_t)batch * OMGB_INFO_STRIDE;
+    const size_t need = sizeof(double) * (n_xi + 2 * n_se + n_goal + n_info);
+    if (need > s->stage_bytes) {
+        cudaFree(s->d_stage);
+        s->d_stage = nullptr; s->stage_bytes = 0;
+        OMGB_CUDA(cudaMalloc(&s->d_stage, need));
+        s->stage_bytes = need;
+    }
+    double *d_xi = s->d_stage, *d_start = d_xi + n_xi, *d_end = d_start + n_se, *d_goal = d_end + n_se,
+           *d_info = d_goal + n_goal;
+    OMGB_CUDA(cudaMemcpyAsync(d_xi, h_xi, sizeof(double) * n_xi, cudaMemcpyHostToDevice, st));
+    OMGB_CUDA(cudaMemcpyAsync(d_start, h_start, sizeof(double) * n_se, cudaMemcpyHostToDevice, st));
+    OMGB_CUDA(cudaMemcpyAsync(d_end, h_end, sizeof(double) * n_se, cudaMemcpyHostToDevice, st));
+    if (c > 0) OMGB_CUDA(cudaMemcpyAsync(d_goal, h_goal_rows, sizeof(double) * n_goal, cudaMemcpyHostToDevice, st));
+    StepArgs a = make_args(s, prm, batch, d_xi, d_start, d_end, c > 0 ? d_goal : nullptr, nullptr, nullptr, d_info,
+                           nullptr, nullptr);
+    rc_ = launch_step(s, a, st);
+    if (rc_) return rc_;
+    OMGB_CUDA(cudaMemcpyAsync(h_xi, d_xi, sizeof(double) * n_xi, cudaMemcpyDeviceToHost, st));
+    OMGB_CUDA(cudaMemcpyAsync(h_info, d_info, sizeof(double) * n_info, cudaMemcpyDeviceToHost, st));
+    OMGB_CUDA(cudaStreamSynchronize(st));
+    return OMGB_OK;
+}
+
+extern "C" int omgb_batch_obstacle_cost(omgb_scene_t *s, const double *joints, int num_configs, int arc_length,
+                                        const double *start, double time_interval, int uncheck_finger_collision,
+                                        float *potentials, float *grads, float *collides, void *stream) {
+    if (!s) return fail(OMGB_ERR_INVALID, "omgb_batch_obstacle_cost: null scene");
+    if (!s->robot_set || !s->sdf_set || !s->objs_set)
+        return fail(OMGB_ERR_STATE, "omgb_batch_obstacle_cost: scene needs robot, sdf and objects");
+    if (num_configs < 0) return fail(OMGB_ERR_INVALID, "omgb_batch_obstacle_cost: negative num_configs");
+    if (num_configs == 0) return OMGB_OK;
+    if (!joints || !potentials || !collides) return fail(OMGB_ERR_INVALID, "omgb_batch_obstacle_cost: null buffer");
+    if (arc_length > 0 && (!start || num_configs % arc_length != 0 || !(time_interval > 0)))
+        return fail(OMGB_ERR_INVALID, "omgb_batch_obstacle_cost: arc_length needs start, dt and M % arc_length == 0");
+    OMGB_CUDA(cudaSetDevice(s->device));
+    const size_t smem = align_up(sizeof(ObjRec) * s->num_objects, 16) + sizeof(double) * (BOC_CFG + 2) * NL * 12;
+    OMGB_CUDA(cudaFuncSetAttribute(batch_obstacle_cost_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int blocks = (num_configs + BOC_CFG - 1) / BOC_CFG;
+    batch_obstacle_cost_kernel<<<blocks, 256, smem, (cudaStream_t)stream>>>(
+        s->d_objs, s->num_objects, s->d_grids, s->d_robot, joints, num_configs, arc_length, start,
+        arc_length > 0 ? (float)(1.0 / time_interval) : 0.0f, uncheck_finger_collision == -1 ? 1 : 0, potentials,
+        grads, collides);
+    OMGB_CUDA(cudaGetLastError());
+    return OMGB_OK;
+}

@@ -1,0 +1,152 @@
+// SDF sampling device code shared by the raw operator kernel and the fused CHOMP kernels.
+//
+// Arithmetic contract (what "results identical to the reference" means for this operator): every fp32
+// operation of layers/sdf_matching_loss_kernel.cu:97-181 is reproduced as a separately rounded IEEE op,
+// with fused multiply-adds only where written as __fmaf_rn below (the lerp a + t*(b-a), the quaternion
+// cross products, w*uv + p, and the R^T*g accumulation).  The reference's double-precision steps
+// ((p - 0.5) in double, 0.5*(f+ - f-)/delta in double, -v + 0.5*eps in double) are evaluated in fp32 in a
+// way that is bit-identical to the double path (double rounding through binary64 is innocuous for +,-,/
+// of binary32 operands since 53 >= 2*24+2; the one value where (int)(p - 0.5) would differ is handled by
+// comparing p against -0.5 directly).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace omgb {
+
+// Per-object record prepared once per pose/parameter update (prep_objects_kernel).
+struct __align__(16) ObjRec {
+    float qw, qx, qy, qz;        // unit quaternion of the world->object rotation (Eigen matrix->quaternion)
+    float tx, ty, tz, delta;     // translation; voxel size (sdf_limits[9])
+    float r[9];                  // quaternion -> rotation matrix (what so3().matrix() returns)
+    float minx, miny, minz;      // sdf_limits[0:3]
+    float ex, ey, ez;            // sdf_limits[3:6] - sdf_limits[0:3]
+    float fd0, fd1, fd2;         // (float)dims
+    int d0, d1, d2;              // dims
+    float eps, pad, clr, dis;    // epsilons, padding_scales, clearances, disables
+    float inv2eps, inveps;       // 1/(2*eps), 1/eps  (kernel.cu:167-168)
+    float lox, loy, loz;         // object-frame interval inside which a point's 8-tap cell is in bounds
+    float hix, hiy, hiz;
+    float cull_pad;              // conservative slack for the sphere cull
+    long long grid_offset;       // o * d0*d1*d2
+};
+
+__device__ __forceinline__ float lerp_ref(float a, float b, float t) {   // kernel.cu:15-18
+    return __fmaf_rn(t, __fsub_rn(b, a), a);
+}
+
+// (int)(p - 0.5) and (float)((p - 0.5) - x0) of kernel.cu:39-41, negative cell index => out of bounds.
+__device__ __forceinline__ void cell_of(float p, int &c0, float &f) {
+    const float t = __fsub_rn(p, 0.5f);
+    if (p >= 0.5f) {
+        c0 = __float2int_rz(t);
+        f = __fsub_rn(t, (float)c0);
+    } else {
+        c0 = (p > -0.5f) ? 0 : -1;
+        f = t;
+    }
+}
+
+// kernel.cu:37-64.  Returns 1.0f when any of the 8 taps is out of bounds.
+__device__ __forceinline__ float value_interp(const float *__restrict__ g, int d0, int d1, int d2, float px,
+                                              float py, float pz, bool &inb) {
+    int x0, y0, z0;
+    float fx, fy, fz;
+    cell_of(px, x0, fx);
+    cell_of(py, y0, fy);
+    cell_of(pz, z0, fz);
+    inb = (x0 >= 0) & (x0 + 1 < d0) & (y0 >= 0) & (y0 + 1 < d1) & (z0 >= 0) & (z0 + 1 < d2);
+    if (!inb) return 1.0f;
+    const float *b = g + ((size_t)x0 * d1 + y0) * d2 + z0;
+    const size_t sx = (size_t)d1 * d2;
+    const float v000 = __ldg(b), v001 = __ldg(b + 1);
+    const float v010 = __ldg(b + d2), v011 = __ldg(b + d2 + 1);
+    const float v100 = __ldg(b + sx), v101 = __ldg(b + sx + 1);
+    const float v110 = __ldg(b + sx + d2), v111 = __ldg(b + sx + d2 + 1);
+    const float dx00 = lerp_ref(v000, v100, fx);
+    const float dx01 = lerp_ref(v001, v101, fx);
+    const float dx10 = lerp_ref(v010, v110, fx);
+    const float dx11 = lerp_ref(v011, v111, fx);
+    const float dxy0 = lerp_ref(dx00, dx10, fy);
+    const float dxy1 = lerp_ref(dx01, dx11, fy);
+    return lerp_ref(dxy0, dxy1, fz);
+}
+
+// world point -> grid coordinates of object `o` (kernel.cu:125-142; so3.hpp:298-300 quaternion rotation).
+__device__ __forceinline__ void to_grid(const ObjRec &o, float x, float y, float z, float &px, float &py,
+                                        float &pz) {
+    float ux = __fmaf_rn(o.qy, z, -__fmul_rn(o.qz, y));
+    float uy = __fmaf_rn(o.qz, x, -__fmul_rn(o.qx, z));
+    float uz = __fmaf_rn(o.qx, y, -__fmul_rn(o.qy, x));
+    ux = __fadd_rn(ux, ux); uy = __fadd_rn(uy, uy); uz = __fadd_rn(uz, uz);
+    const float cx = __fmaf_rn(o.qy, uz, -__fmul_rn(o.qz, uy));
+    const float cy = __fmaf_rn(o.qz, ux, -__fmul_rn(o.qx, uz));
+    const float cz = __fmaf_rn(o.qx, uy, -__fmul_rn(o.qy, ux));
+    const float wx = __fadd_rn(__fadd_rn(__fmaf_rn(o.qw, ux, x), cx), o.tx);
+    const float wy = __fadd_rn(__fadd_rn(__fmaf_rn(o.qw, uy, y), cy), o.ty);
+    const float wz = __fadd_rn(__fadd_rn(__fmaf_rn(o.qw, uz, z), cz), o.tz);
+    px = __fmul_rn(__fdiv_rn(__fsub_rn(wx, o.minx), o.ex), o.fd0);
+    py = __fmul_rn(__fdiv_rn(__fsub_rn(wy, o.miny), o.ey), o.fd1);
+    pz = __fmul_rn(__fdiv_rn(__fsub_rn(wz, o.minz), o.ez), o.fd2);
+}
+
+// Value-only evaluation of one (point, object) pair: potential + collide flag (kernel.cu:147-171 without
+// the gradient).  Returns true if the 8-tap cell is in bounds.
+__device__ __forceinline__ bool pair_potential(const ObjRec &o, const float *__restrict__ grids, float x,
+                                               float y, float z, float &pot, float &col) {
+    float px, py, pz;
+    to_grid(o, x, y, z, px, py, pz);
+    bool inb;
+    const float v = value_interp(grids + o.grid_offset, o.d0, o.d1, o.d2, px, py, pz, inb);
+    col = (v < o.clr) ? 1.0f : 0.0f;
+    if (v <= 0.0f) {
+        pot = __fadd_rn(-v, __fmul_rn(0.5f, o.eps));
+    } else if (v <= o.eps) {
+        const float d = __fsub_rn(v, o.eps);
+        pot = __fmul_rn(__fmul_rn(__fmul_rn(o.inv2eps, d), d), o.pad);
+    } else {
+        pot = 0.0f;
+    }
+    return inb;
+}
+
+// Full evaluation: potential, world-frame potential gradient, collide flag (kernel.cu:147-180).
+__device__ __forceinline__ bool pair_full(const ObjRec &o, const float *__restrict__ grids, float x, float y,
+                                          float z, float &pot, float &gx, float &gy, float &gz, float &col) {
+    float px, py, pz;
+    to_grid(o, x, y, z, px, py, pz);
+    const float *g = grids + o.grid_offset;
+    bool inb, dummy;
+    const float v = value_interp(g, o.d0, o.d1, o.d2, px, py, pz, inb);
+    col = (v < o.clr) ? 1.0f : 0.0f;
+    pot = 0.0f; gx = gy = gz = 0.0f;
+    if (!(v <= o.eps)) return inb;    // value > eps (including the OOB 1.0 when eps < 1): kernel.cu:172-173
+    // kernel.cu:67-86: six re-interpolations, 0.5*(f+ - f-)/delta
+    const float fpx = value_interp(g, o.d0, o.d1, o.d2, __fadd_rn(px, 1.0f), py, pz, dummy);
+    const float fpy = value_interp(g, o.d0, o.d1, o.d2, px, __fadd_rn(py, 1.0f), pz, dummy);
+    const float fpz = value_interp(g, o.d0, o.d1, o.d2, px, py, __fadd_rn(pz, 1.0f), dummy);
+    const float fmx = value_interp(g, o.d0, o.d1, o.d2, __fsub_rn(px, 1.0f), py, pz, dummy);
+    const float fmy = value_interp(g, o.d0, o.d1, o.d2, px, __fsub_rn(py, 1.0f), pz, dummy);
+    const float fmz = value_interp(g, o.d0, o.d1, o.d2, px, py, __fsub_rn(pz, 1.0f), dummy);
+    const float dgx = __fdiv_rn(__fmul_rn(0.5f, __fsub_rn(fpx, fmx)), o.delta);
+    const float dgy = __fdiv_rn(__fmul_rn(0.5f, __fsub_rn(fpy, fmy)), o.delta);
+    const float dgz = __fdiv_rn(__fmul_rn(0.5f, __fsub_rn(fpz, fmz)), o.delta);
+    float vx, vy, vz;
+    if (v <= 0.0f) {                                                   // kernel.cu:158-164
+        pot = __fadd_rn(-v, __fmul_rn(0.5f, o.eps));
+        vx = -dgx; vy = -dgy; vz = -dgz;
+    } else {                                                           // kernel.cu:165-171
+        const float d = __fsub_rn(v, o.eps);
+        pot = __fmul_rn(__fmul_rn(__fmul_rn(o.inv2eps, d), d), o.pad);
+        vx = __fmul_rn(__fmul_rn(__fmul_rn(o.inveps, dgx), d), o.pad);
+        vy = __fmul_rn(__fmul_rn(__fmul_rn(o.inveps, dgy), d), o.pad);
+        vz = __fmul_rn(__fmul_rn(__fmul_rn(o.inveps, dgz), d), o.pad);
+    }
+    // rotationMatrix.transpose() * vgrad   (kernel.cu:176)
+    gx = __fmaf_rn(o.r[6], vz, __fmaf_rn(o.r[3], vy, __fmul_rn(o.r[0], vx)));
+    gy = __fmaf_rn(o.r[7], vz, __fmaf_rn(o.r[4], vy, __fmul_rn(o.r[1], vx)));
+    gz = __fmaf_rn(o.r[8], vz, __fmaf_rn(o.r[5], vy, __fmul_rn(o.r[2], vx)));
+    return inb;
+}
+
+}  // namespace omgb

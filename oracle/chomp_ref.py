@@ -355,8 +355,11 @@ class ChompRef(object):
     """One trajectory's optimizer state; .step() == Optimizer.optimize(traj, force_update=True)
     (omg/optimizer.py:115-135) on a Trajectory (omg/core.py:23-57)."""
 
-    def __init__(self, robot, scene, cfg, xi, start, end, goal_rows=None):
+    def __init__(self, robot, scene, cfg, xi, start, end, goal_rows=None, goal=None):
         self.robot, self.scene, self.cfg = robot, scene, cfg
+        # traj.goal_set[traj.goal_idx]; every assignment site keeps it equal to traj.end
+        # (omg/planner.py:222, omg/online_learner.py:101,246)
+        self.goal = np.array(end if goal is None else goal, dtype=np.float64)
         self.xi = np.array(xi, dtype=np.float64)
         self.start = np.array(start, dtype=np.float64)
         self.end = np.array(end, dtype=np.float64)
@@ -377,7 +380,7 @@ class ChompRef(object):
     def step(self, info_only=False):
         cfg, robot = self.cfg, self.robot
         self.schedule()
-        goal = self.goal_rows[-1] if cfg.goal_set_proj else None
+        goal = self.goal if cfg.goal_set_proj else None
         cost, grad, info = total_cost(robot, self.scene, cfg, self.xi, self.start, self.end, goal, self.stats)
         low = (self.xi < robot.lower - 5e-3).any()          # omg/optimizer.py:166-174 (sic)
         high = self.xi > robot.upper + 5e-3
@@ -402,3 +405,20 @@ class ChompRef(object):
         self.xi[:, -2:] = np.minimum(np.maximum(self.xi[:, -2:], 0), 0.04)
         self.xi = project_joint_limits(robot, cfg, self.xi)
         return info
+
+
+def batch_obstacle_cost(robot, scene, cfg, joints, arc_length=-1, uncheck_finger_collision=-1, start=None):
+    """omg/cost.py:192-286 (+ omg/config.py:162-187): potentials [M,10,p], grads [M,10,p,3], collides for M
+    configurations; with arc_length > 0 the potentials are weighted by the fp32 workspace speed."""
+    joints = np.asarray(joints, dtype=np.float64).reshape(-1, 9)
+    x = place_points(link_frames(robot, to_degrees_with_dummy(joints))[0], robot.body_points)   # [M,10,p,3]
+    pot, grad, col = sdf_query(scene, cfg, x, uncheck_finger_collision)
+    if arc_length > 0:
+        x32 = x.astype(np.float32).reshape(-1, arc_length, 10, x.shape[2], 3)                   # [G,n,10,p,3]
+        xs = place_points(link_frames(robot, to_degrees_with_dummy(start))[0], robot.body_points)[0].astype(np.float32)
+        inv_dt = np.float32(1.0 / cfg.time_interval)
+        prev = np.concatenate([np.broadcast_to(xs[None, None], x32[:, :1].shape), x32[:, :-1]], axis=1)
+        vel = x32 * inv_dt + prev * (-inv_dt)
+        speed = np.sqrt((vel * vel).sum(-1)).reshape(pot.shape)
+        pot = pot * speed
+    return pot, grad, col

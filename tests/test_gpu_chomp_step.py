@@ -1,0 +1,158 @@
+"""GPU: the fused CHOMP iteration through the C ABI vs the oracle and vs the fixtures produced by the
+reference's own Python.  Tolerance: 1e-4 rad per waypoint is the north-star bar; the fp64 paths agree far
+tighter, so the tests assert 1e-7 rad and report the worst case."""
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import helpers as H
+from omg_planner_b200 import scene as S
+from omg_planner_b200.config import ChompConfig
+from omg_planner_b200.robot import PandaConstants
+
+pytestmark = pytest.mark.gpu
+TOL_RAD = 1e-7
+GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "chomp_*.npz")))
+INFO_COLS = {"obs": 0, "smooth": 1, "cost": 2, "collide": 3, "reach": 4, "grad": 5, "weighted_obs_grad": 6,
+             "weighted_smooth_grad": 7, "terminate": 8, "violate_limit": 9, "execute": 10, "failure_terminate": 11}
+
+
+def _dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64)).cuda()
+
+
+def _run_gpu(eng, cfg, xi, start, end, rows, iters, want_grad=False):
+    x, s, e = _dev(xi), _dev(start), _dev(end)
+    r = None if rows is None else _dev(rows)
+    hist, infos, grads = [xi.copy()], [], []
+    for it in range(iters):
+        cfg.obstacle_weight, cfg.smoothness_weight, cfg.step_size = cfg.schedule(it + 1)
+        out = eng.step(cfg, x, s, e, r, update=1, want_grad=want_grad)
+        torch.cuda.synchronize()
+        hist.append(x.cpu().numpy().copy())
+        infos.append(out["info"].cpu().numpy().copy())
+        if want_grad:
+            grads.append(out["grad"].cpu().numpy().copy())
+    return np.stack(hist, 1), np.stack(infos, 1), (np.stack(grads, 1) if want_grad else None)
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[6:-4] for p in GOLDEN])
+def test_replay_reference_fixtures(path):
+    """25 iterations from the fixture's initial state must track the reference's recorded trajectories."""
+    g = np.load(path)
+    sc = S.make_scene(**eval(str(g["scene_args"])))
+    assert abs(sc["sdf_grids"].astype(np.float64).sum() - float(g["sdf_checksum"])) < 1e-6
+    gsp, standoff, topk = [int(v) for v in g["mode"]]
+    mode = dict(goal_set_proj=bool(gsp), use_standoff=bool(standoff), top_k_collision=topk)
+    cfg = ChompConfig(**mode)
+    robot = PandaConstants(body_points=g["body_points"])
+    eng = H.engine_for(sc, cfg, robot)
+    rows = H.goal_rows_for(mode, g["tails"], g["end"])
+    iters = g["history"].shape[1] - 1
+    hist, infos, grads = _run_gpu(eng, cfg, g["xi0"], g["start"], g["end"], rows, iters, want_grad=True)
+    err = np.abs(hist - g["history"])[..., :7].max(axis=(2, 3))           # [B, iters+1]
+    print("max |xi - xi_ref| per iteration:", err.max(0))
+    assert err.max() <= TOL_RAD, "first divergence at iteration %s" % (np.argwhere(err > TOL_RAD)[:1],)
+    keys = [str(k) for k in g["info_keys"]]
+    for k, key in enumerate(keys):
+        ref = g["infos"][..., k]
+        np.testing.assert_allclose(infos[..., INFO_COLS[key]], ref, rtol=1e-6, atol=1e-6, err_msg=key)
+    for k, key in enumerate([str(k) for k in g["flag_keys"]]):
+        np.testing.assert_array_equal(infos[..., INFO_COLS[key]].astype(int), g["flags"][..., k], err_msg=key)
+    np.testing.assert_allclose(grads, g["grads"], rtol=1e-6, atol=1e-6)
+
+
+@pytest.mark.parametrize("name", sorted(H.MODES))
+def test_single_iteration_vs_oracle_denser_scene(name):
+    """Primary gate: one iteration from identical state, on a denser scene than the fixtures
+    (10 objects at 64^3, 30 waypoints, 12 trajectories)."""
+    mode = H.MODES[name]
+    sc = S.make_scene(num_objects=10, grid=64, seed=21)
+    cfg = ChompConfig(**mode)
+    robot = PandaConstants()
+    xi, st, en, tails = S.make_trajectories(12, 30, robot.joint_lower_limit, robot.joint_upper_limit, seed=3)
+    rows = H.goal_rows_for(mode, tails, en)
+    ref_hist, ref_infos = H.oracle_steps(sc, mode, xi, st, en, rows, 3)
+    eng = H.engine_for(sc, cfg, robot)
+    hist, infos, _ = _run_gpu(eng, cfg, xi, st, en, rows, 3)
+    err = np.abs(hist - ref_hist)[..., :7].max()
+    print(name, "max |dxi| after 3 iterations:", err)
+    assert err <= TOL_RAD
+    for b in range(12):
+        for it in range(3):
+            for key in ("obs", "smooth", "cost", "collide", "reach", "grad"):
+                ref = float(ref_infos[b][it][key])
+                assert abs(infos[b, it, INFO_COLS[key]] - ref) <= 1e-6 * max(1.0, abs(ref)), (key, b, it)
+            assert bool(infos[b, it, 8]) == ref_infos[b][it]["terminate"]
+    p_in = sum(ref_infos[b][0]["p_in"] if "p_in" in ref_infos[b][0] else 0 for b in range(12))
+    assert infos[:, 0, 12].sum() > 0
+
+
+def test_seventy_iterations_default_mode():
+    """Secondary gate: the reference's full schedule (50 + 20 iterations) in its default mode."""
+    mode = H.MODES["goalset_standoff_topk"]
+    sc = S.make_scene(num_objects=8, grid=48, seed=31)
+    cfg = ChompConfig(**mode)
+    robot = PandaConstants()
+    xi, st, en, tails = S.make_trajectories(4, 30, robot.joint_lower_limit, robot.joint_upper_limit, seed=8)
+    ref_hist, _ = H.oracle_steps(sc, mode, xi, st, en, tails, 70)
+    eng = H.engine_for(sc, cfg, robot)
+    hist, _, _ = _run_gpu(eng, cfg, xi, st, en, tails, 70)
+    err = np.abs(hist - ref_hist)[..., :7].max(axis=(2, 3))
+    print("fraction within 1e-4 rad:", (err.max(1) <= 1e-4).mean(), "worst:", err.max())
+    assert err.max() <= 1e-4
+
+
+def test_info_only_and_update_unless_terminate():
+    mode = H.MODES["fixed_topk"]
+    sc = S.make_scene(num_objects=4, grid=32, seed=2)
+    cfg = ChompConfig(**mode)
+    robot = PandaConstants()
+    xi, st, en, tails = S.make_trajectories(5, 30, robot.joint_lower_limit, robot.joint_upper_limit, seed=1)
+    eng = H.engine_for(sc, cfg, robot)
+    x = _dev(xi)
+    out = eng.step(cfg, x, _dev(st), _dev(en), None, update=0)
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(x.cpu().numpy(), xi)           # info_only leaves the trajectory alone
+    term = out["info"][:, 8].cpu().numpy().astype(bool)
+    out2 = eng.step(cfg, x, _dev(st), _dev(en), None, update=2)  # update unless terminate
+    torch.cuda.synchronize()
+    moved = np.abs(x.cpu().numpy() - xi).max(axis=(1, 2)) > 0
+    np.testing.assert_array_equal(moved, ~term)
+
+
+def test_plan_equals_repeated_steps_and_host_entry_point():
+    mode = H.MODES["goalset_standoff_topk"]
+    sc = S.make_scene(num_objects=6, grid=48, seed=11, grid_choices=[32, 40, 48])
+    cfg = ChompConfig(**mode)
+    robot = PandaConstants()
+    xi, st, en, tails = S.make_trajectories(7, 30, robot.joint_lower_limit, robot.joint_upper_limit, seed=2)
+    eng = H.engine_for(sc, cfg, robot)
+    hist, infos, _ = _run_gpu(eng, cfg, xi, st, en, tails, 10)
+    x = _dev(xi)
+    out = eng.plan(cfg, x, _dev(st), _dev(en), _dev(tails), iters=10)
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(x.cpu().numpy(), hist[:, -1])
+    np.testing.assert_array_equal(out["info"].cpu().numpy(), infos[:, -1])
+    # host-buffer entry point: same numbers, copies inside
+    xh = xi.copy()
+    for it in range(10):
+        cfg.obstacle_weight, cfg.smoothness_weight, cfg.step_size = cfg.schedule(it + 1)
+        info = eng.step_host(cfg, xh, np.ascontiguousarray(st), np.ascontiguousarray(en), np.ascontiguousarray(tails))
+    np.testing.assert_array_equal(xh, hist[:, -1])
+    np.testing.assert_array_equal(info, infos[:, -1])
+    # stop_on_terminate freezes trajectories the iteration after they report terminate (planner.py:627)
+    x = _dev(xi)
+    out = eng.plan(cfg, x, _dev(st), _dev(en), _dev(tails), iters=25, stop_on_terminate=True)
+    torch.cuda.synchronize()
+    done = out["done"].cpu().numpy().astype(bool)
+    hist25, infos25, _ = _run_gpu(eng, cfg, xi, st, en, tails, 25)
+    term = infos25[:, :, 8].astype(bool); term[:, 0] = False
+    first = np.where(term.any(1), term.argmax(1), -1)
+    np.testing.assert_array_equal(done, first >= 0)
+    for b in range(7):
+        expect = hist25[b, first[b] + 1] if first[b] >= 0 else hist25[b, -1]
+        np.testing.assert_array_equal(x[b].cpu().numpy(), expect)
