@@ -136,7 +136,7 @@ class Cost(object):
         n = xi_before.shape[1]
         for b in range(info_t.shape[0]):
             r = info_t[b]
-            smooth_rows = self._smooth_rows(cfg, xi_before[b])
+            smooth_rows = self._smooth_rows(cfg, xi_before[b], self._last_start[b], self._last_end[b])
             info = {
                 "collision_pts": None, "obs": r[0], "smooth": r[1], "grasp": 0, "weighted_obs": cfg.obstacle_weight * r[0],
                 "weighted_smooth": cfg.smoothness_weight * r[1], "weighted_smooth_grad": r[7], "weighted_obs_grad": r[6],
@@ -151,10 +151,13 @@ class Cost(object):
         return infos
 
     @staticmethod
-    def _smooth_rows(cfg, xi):
+    def _smooth_rows(cfg, xi, start, end):
         """Per-row smoothness loss (omg/cost.py:429-445) on the host, only for info['cost_traj']."""
         w = np.asarray(cfg.link_smooth_weight)[None]
         vel = np.asarray(cfg.diff_matrices[0]).dot(xi)
+        vel[0] -= start / cfg.time_interval
+        if not cfg.goal_set_proj:
+            vel[-1] += end / cfg.time_interval
         return 0.5 * np.linalg.norm(vel * w, axis=1) ** 2
 
     def evaluate(self, traj, update_mode=0):
@@ -163,6 +166,7 @@ class Cost(object):
         cfg = self.engine_cfg()
         xi, start, end, rows, batched = self._traj_tensors(traj)
         before = xi.cpu().numpy()
+        self._last_start, self._last_end = start.cpu().numpy(), end.cpu().numpy()
         want_dbg = bool(getattr(self.cfg, "vis", False))
         out = self.engine.step(cfg, xi, start, end, rows, update=update_mode, want_grad=True, debug=want_dbg,
                                want_row_obs=True)

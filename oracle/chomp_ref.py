@@ -265,6 +265,8 @@ def obstacle_term(robot, scene, cfg, xi, start, end, stats=None):
     v, a = time_derivatives(cfg, x, x_s, x_e)
     obs_grad = np.zeros_like(xi)
     obs_cost = np.zeros([n, 10])
+    if stats is not None:
+        stats["tie_slack"] = 0.0
     if cfg.top_k_collision == 0:
         for j in range(10):
             jt = point_jacobians(origins, axes, x[:, j], j)
@@ -275,6 +277,15 @@ def obstacle_term(robot, scene, cfg, xi, start, end, stats=None):
         order = np.argsort(pot.flatten())[-cfg.top_k_collision:]
         top_n, top_m, top_p = np.unravel_index(order, pot.shape)
         last = 10 if cfg.consider_finger else 8
+        if stats is not None and len(order) == cfg.top_k_collision and (pot > 0).sum() > cfg.top_k_collision:
+            # Which of several points tied at the k-th largest potential make the cut is decided by numpy's
+            # unstable argsort (implementation-defined; observed to vary).  tie_slack = the most info["obs"] can
+            # move with that choice: n * sum of c*|v| over the tied points of the links that are summed.
+            tau = pot[top_n[0], top_m[0], top_p[0]]
+            tn, tm, tp = np.nonzero(pot == tau)
+            if len(tn) > 1:
+                keep = tm < last
+                stats["tie_slack"] = float(n * np.sum(pot[tn, tm, tp][keep] * np.linalg.norm(v[tn, tm, tp][keep], axis=-1)))
         for j in range(last):
             mask = top_m == j
             if not mask.any():
@@ -325,6 +336,7 @@ def total_cost(robot, scene, cfg, xi, start, end, goal, stats=None):
         "cost_traj": cfg.obstacle_weight * o_loss.sum(-1) + cfg.smoothness_weight * s_loss[:-1],
         "standoff_idx": len(xi) - cfg.reach_tail_length if cfg.use_standoff else len(xi) - 1,
         "potentials": pot, "potential_grads": gpot, "points": x,
+        "tie_slack": 0.0 if stats is None else stats.get("tie_slack", 0.0),
     }
     return cost, grad, info
 

@@ -59,7 +59,11 @@ def test_replay_reference_fixtures(path):
     keys = [str(k) for k in g["info_keys"]]
     for k, key in enumerate(keys):
         ref = g["infos"][..., k]
-        np.testing.assert_allclose(infos[..., INFO_COLS[key]], ref, rtol=1e-6, atol=1e-6, err_msg=key)
+        # obs/cost: where several points tie at the top-k threshold the reference's membership is decided by
+        # numpy's unstable argsort; the kernel keeps all ties.  tie_slack bounds that difference.
+        slack = g["tie_slack"] if key in ("obs", "cost") else 0.0
+        bad = np.abs(infos[..., INFO_COLS[key]] - ref) > 1e-6 * np.maximum(1.0, np.abs(ref)) + slack * (1 + 1e-9)
+        assert not bad.any(), (key, np.argwhere(bad)[:4])
     for k, key in enumerate([str(k) for k in g["flag_keys"]]):
         np.testing.assert_array_equal(infos[..., INFO_COLS[key]].astype(int), g["flags"][..., k], err_msg=key)
     np.testing.assert_allclose(grads, g["grads"], rtol=1e-6, atol=1e-6)
@@ -85,9 +89,9 @@ def test_single_iteration_vs_oracle_denser_scene(name):
         for it in range(3):
             for key in ("obs", "smooth", "cost", "collide", "reach", "grad"):
                 ref = float(ref_infos[b][it][key])
-                assert abs(infos[b, it, INFO_COLS[key]] - ref) <= 1e-6 * max(1.0, abs(ref)), (key, b, it)
+                slack = ref_infos[b][it]["tie_slack"] * (1 + 1e-9) if key in ("obs", "cost") else 0.0
+                assert abs(infos[b, it, INFO_COLS[key]] - ref) <= 1e-6 * max(1.0, abs(ref)) + slack, (key, b, it)
             assert bool(infos[b, it, 8]) == ref_infos[b][it]["terminate"]
-    p_in = sum(ref_infos[b][0]["p_in"] if "p_in" in ref_infos[b][0] else 0 for b in range(12))
     assert infos[:, 0, 12].sum() > 0
 
 

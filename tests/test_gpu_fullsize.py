@@ -29,6 +29,7 @@ def test_batch_properties(big, name):
     sc, robot, xi, st, en, tails = big
     mode = H.MODES[name]
     cfg = ChompConfig(**mode)
+    cfg.obstacle_weight, cfg.smoothness_weight, cfg.step_size = cfg.schedule(1)   # iteration 1 of a plan
     eng = H.engine_for(sc, cfg, robot)
     rows = H.goal_rows_for(mode, tails, en)
     r = None if rows is None else _dev(rows)
@@ -66,7 +67,8 @@ def test_batch_properties(big, name):
     print(name, "spot-check max |dxi|:", err, "P_in mean:", i1[:, 12].mean().item(), "nnz mean:", i1[:, 13].mean().item())
     assert err <= 1e-7
     for k, b in enumerate(sel):
-        assert abs(i1[b, 0].item() - ref_infos[k][0]["obs"]) <= 1e-6 * max(1.0, abs(ref_infos[k][0]["obs"]))
+        assert abs(i1[b, 0].item() - ref_infos[k][0]["obs"]) <= (1e-6 * max(1.0, abs(ref_infos[k][0]["obs"]))
+                                                                   + ref_infos[k][0]["tie_slack"] * (1 + 1e-9))
         assert i1[b, 3].item() == ref_infos[k][0]["collide"]
 
 

@@ -34,11 +34,12 @@ def test_optimizer_optimize_matches_oracle_loop():
             rinfo = ref.step()
             assert np.abs(traj.data - ref.xi)[:, :7].max() <= 1e-7
             for key in ("obs", "smooth", "cost", "collide", "reach", "grad", "weighted_obs_grad", "weighted_smooth_grad"):
-                assert abs(info[key] - rinfo[key]) <= 1e-6 * max(1.0, abs(rinfo[key])), key
+                slack = rinfo["tie_slack"] * (1 + 1e-9) if key in ("obs", "cost") else 0.0
+                assert abs(info[key] - rinfo[key]) <= 1e-6 * max(1.0, abs(rinfo[key])) + slack, key
             for key in ("terminate", "violate_limit", "execute", "failure_terminate"):
                 assert bool(info[key]) == bool(rinfo[key]), key
             np.testing.assert_allclose(info["gradient"], rinfo["gradient"], rtol=1e-6, atol=1e-6)
-            np.testing.assert_allclose(info["cost_traj"], rinfo["cost_traj"], rtol=1e-6, atol=1e-6)
+            np.testing.assert_allclose(info["cost_traj"], rinfo["cost_traj"], rtol=1e-6, atol=1e-6 + rinfo["tie_slack"])
             assert info["standoff_idx"] == rinfo["standoff_idx"]
         assert abs(cfg.smoothness_weight - 0.1 * 1.02 ** 12) < 1e-15   # schedules are written back into cfg
         final = optim.optimize(traj, info_only=True)

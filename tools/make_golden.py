@@ -57,6 +57,7 @@ def main():
         infos = np.zeros((N_TRAJ, N_ITER, len(INFO_KEYS)))
         flags = np.zeros((N_TRAJ, N_ITER, len(FLAG_KEYS)), np.int8)
         grads = np.zeros((N_TRAJ, N_ITER, N_WPT, 9))
+        slack = np.zeros((N_TRAJ, N_ITER))
         for b in range(N_TRAJ):
             cost = ns.cost.Cost(env)
             opt = ns.optimizer.Optimizer(env, cost)
@@ -65,7 +66,16 @@ def main():
                 env.objects[env.target_idx].reach_grasps = [tails[b]] if cfg.use_standoff else [en[b]]
                 cost.target_obj = env.objects[env.target_idx]
             hist[b, 0] = traj.data
+            # the oracle runs alongside only to record where the reference's own output is implementation-
+            # defined (ties at the top-k threshold under numpy's unstable argsort): `tie_slack`
+            ocfg = R.RefConfig(**mode)
+            rows = None
+            if cfg.goal_set_proj:
+                rows = tails[b] if cfg.use_standoff else en[b][None]
+            shadow = R.ChompRef(robot, sc, ocfg, xi[b], st[b], en[b], rows)
             for it in range(N_ITER):
+                shadow.xi = traj.data.copy()
+                slack[b, it] = shadow.step()["tie_slack"]
                 info = opt.optimize(traj, force_update=True)
                 hist[b, it + 1] = traj.data
                 infos[b, it] = [float(info[k]) for k in INFO_KEYS]
@@ -76,7 +86,7 @@ def main():
             path, mode=np.array([int(mode["goal_set_proj"]), int(mode["use_standoff"]), mode["top_k_collision"]]),
             scene_args=np.array(repr(SCENE_ARGS)), sdf_checksum=np.float64(sc["sdf_grids"].astype(np.float64).sum()),
             body_points=robot.body_points, xi0=xi, start=st, end=en, tails=tails, history=hist, infos=infos,
-            flags=flags, grads=grads, info_keys=np.array(INFO_KEYS), flag_keys=np.array(FLAG_KEYS))
+            flags=flags, grads=grads, tie_slack=slack, info_keys=np.array(INFO_KEYS), flag_keys=np.array(FLAG_KEYS))
         print(name, "->", path, os.path.getsize(path) // 1024, "KiB; collide range",
               infos[..., 3].min(), infos[..., 3].max(), "terminated", flags[..., 0].sum())
 
