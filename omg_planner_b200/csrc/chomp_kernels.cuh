@@ -31,13 +31,24 @@ constexpr int NS = 8;   // gradient slots per link (<= 7 arm ancestors + own pri
 struct RobotConst {
     double P0[10][12];     // pose_0[i]: rotation row-major [0:9], translation [9:12]
     double CO[10][12];     // center_offset[j]
-    double ja[10][3];      // joint axis in the link frame: tip2joint_R * axis
-    double jo[10][3];      // joint "origin" in the link frame: tip2joint_R * origin + tip2joint_t
+    double jab[10][3];     // joint axis expressed in the link's BODY-POINT frame (T_j * center_offset_j)
+    double job[10][3];     // joint "origin" (robot_pykdl.py:104 aliasing included) in the body-point frame
     double pts[10][OMGB_MAX_BODY_POINTS][3];
-    float sph[10][4];      // bounding sphere of the link's body points (link frame centre, radius)
+    float sph[10][4];      // bounding sphere of the link's body points (body-point frame centre, radius)
     double lower[ND], upper[ND];
     int p;                 // body points per link
     int pad_;
+};
+
+// Lower-bound grid over the packed SDFs: one float per 2x2x2-voxel brick = the minimum voxel value over the
+// brick and its 26 neighbours (a 6^3-voxel region).  Any trilinear sample whose grid coordinate falls in the
+// brick reads taps inside that region only, and a trilinear value is bounded below by its taps, so one load
+// proves "this (body point, object) pair is farther than eps and not colliding" without touching the voxels.
+struct DilDesc {
+    const float *data;
+    long long obj_stride;
+    int bx, by, bz;
+    int enabled;
 };
 
 struct StepArgs {
@@ -57,6 +68,8 @@ struct StepArgs {
     float *dbg_pot;          // [B,n,10,p] or null
     float *dbg_pts;          // [B,n,10,p,3] or null
     double *row_obs;         // [B,n] or null: obstacle cost per waypoint row (obs_cost.sum(-1)); zeroed by the caller
+    long long *prof;         // [B,12] or null: clock64() at phase boundaries (diagnostic)
+    DilDesc dil;
     int num_objects;
     int batch;
     int iteration;           // index inside a plan (for the t > 0 rule of planner.py:627)
@@ -73,20 +86,26 @@ __device__ __forceinline__ double warp_sum(double v) {
     return v;
 }
 
-// Block-wide sum; every thread gets the result.  scratch: >= 33 doubles of shared memory.
-__device__ __forceinline__ double block_sum(double v, double *scratch) {
+// Block-wide sum of K values at once; every thread gets the results.  scratch: >= 32*K + K doubles.
+template <int K>
+__device__ __forceinline__ void block_sum_n(double (&v)[K], double *scratch) {
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
-    v = warp_sum(v);
+#pragma unroll
+    for (int k = 0; k < K; ++k) v[k] = warp_sum(v[k]);
     __syncthreads();
-    if (lane == 0) scratch[w] = v;
-    __syncthreads();
-    if (w == 0) {
-        double t = (lane < nw) ? scratch[lane] : 0.0;
-        t = warp_sum(t);
-        if (lane == 0) scratch[32] = t;
+    if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) scratch[w * K + k] = v[k];
     }
     __syncthreads();
-    return scratch[32];
+    if (threadIdx.x < K) {
+        double t = 0.0;
+        for (int q = 0; q < nw; ++q) t += scratch[q * K + threadIdx.x];
+        scratch[32 * K + threadIdx.x] = t;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < K; ++k) v[k] = scratch[32 * K + k];
 }
 
 __device__ __forceinline__ void xform(const double *F, double px, double py, double pz, double &x, double &y,
@@ -107,10 +126,10 @@ __device__ __forceinline__ void compose(const double *A, const double *B, double
     }
 }
 
-// Forward kinematics of one configuration q[9] (rad): 10 body-point frames (T_j * center_offset_j) and,
-// when jinfo != null, joint axis + reference "origin" for the 7 arm joints and the 2 finger axes.
-// robot_pykdl.py:148-215; the rotX(+-pi)/column-flip pair of :166,174-176 cancels and is omitted.
-__device__ void panda_fk(const RobotConst *__restrict__ rc, const double *q, double *frames, double *jinfo) {
+// Forward kinematics of one configuration q[9] (rad), one thread: 10 body-point frames
+// (T_j * center_offset_j).  robot_pykdl.py:148-215; the rotX(+-pi)/column-flip pair of :166,174-176 cancels
+// and is omitted.  Used by the batch-obstacle-cost kernel; the fused step uses the row-parallel form below.
+__device__ void panda_fk(const RobotConst *__restrict__ rc, const double *q, double *frames) {
     double T[12] = {1, 0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0};
     double N[12];
 #pragma unroll 1
@@ -121,9 +140,8 @@ __device__ void panda_fk(const RobotConst *__restrict__ rc, const double *q, dou
         double s, c;
         sincos(q[i], &s, &c);
         compose(T, B, N);   // T * pose_0[i]
-        // ... * Rz(q_i): rotate the first two columns
 #pragma unroll
-        for (int r = 0; r < 3; ++r) {
+        for (int r = 0; r < 3; ++r) {   // ... * Rz(q_i): rotate the first two columns
             const double a = N[3 * r], b = N[3 * r + 1];
             T[3 * r] = fma(a, c, b * s);
             T[3 * r + 1] = fma(b, c, -(a * s));
@@ -136,15 +154,6 @@ __device__ void panda_fk(const RobotConst *__restrict__ rc, const double *q, dou
         compose(T, C, N);
 #pragma unroll
         for (int k = 0; k < 12; ++k) frames[12 * i + k] = N[k];
-        if (jinfo) {
-            const double ax = rc->ja[i][0], ay = rc->ja[i][1], az = rc->ja[i][2];
-            const double ox = rc->jo[i][0], oy = rc->jo[i][1], oz = rc->jo[i][2];
-#pragma unroll
-            for (int r = 0; r < 3; ++r) {
-                jinfo[6 * i + r] = fma(T[3 * r], ax, fma(T[3 * r + 1], ay, T[3 * r + 2] * az));
-                jinfo[6 * i + 3 + r] = fma(T[3 * r], ox, fma(T[3 * r + 1], oy, fma(T[3 * r + 2], oz, T[9 + r])));
-            }
-        }
     }
     double H[12], B[12], C[12];
 #pragma unroll
@@ -166,27 +175,70 @@ __device__ void panda_fk(const RobotConst *__restrict__ rc, const double *q, dou
         compose(T, C, N);
 #pragma unroll
         for (int k = 0; k < 12; ++k) frames[12 * (8 + f) + k] = N[k];
-        if (jinfo) {
-            const double ax = rc->ja[8 + f][0], ay = rc->ja[8 + f][1], az = rc->ja[8 + f][2];
-#pragma unroll
-            for (int r = 0; r < 3; ++r) {
-                jinfo[6 * (7 + f) + r] = fma(T[3 * r], ax, fma(T[3 * r + 1], ay, T[3 * r + 2] * az));
-                jinfo[6 * (7 + f) + 3 + r] = 0.0;
-            }
-        }
     }
 }
 
-// number of gradient slots of link j and the joint-info slot / DOF column of slot s
+// One ROW of a rigid transform times a constant transform: the three rows of T_i = T_{i-1} * P0 * Rz evolve
+// independently through the kinematic chain, so FK runs on 3 threads per configuration with no exchange.
+struct Row { double a, b, c, t; };
+__device__ __forceinline__ Row row_mul(const Row &r, const double *B) {
+    Row o;
+    o.a = fma(r.a, B[0], fma(r.b, B[3], r.c * B[6]));
+    o.b = fma(r.a, B[1], fma(r.b, B[4], r.c * B[7]));
+    o.c = fma(r.a, B[2], fma(r.b, B[5], r.c * B[8]));
+    o.t = fma(r.a, B[9], fma(r.b, B[10], fma(r.c, B[11], r.t)));
+    return o;
+}
+
+// frames: this configuration's [10][12]; row index r in 0..2; sc: sin/cos pairs of the 7 arm joints.
+__device__ __forceinline__ void panda_fk_row(const RobotConst *__restrict__ rc, const double *q, const double2 *sc,
+                                             int r, double *frames) {
+    Row T;
+    T.a = (r == 0) ? 1.0 : 0.0; T.b = (r == 1) ? 1.0 : 0.0; T.c = (r == 2) ? 1.0 : 0.0; T.t = 0.0;
+#pragma unroll 1
+    for (int i = 0; i < 7; ++i) {
+        const Row N = row_mul(T, rc->P0[i]);
+        const double s = sc[i].x, c = sc[i].y;
+        T.a = fma(N.a, c, N.b * s);
+        T.b = fma(N.b, c, -(N.a * s));
+        T.c = N.c;
+        T.t = N.t;
+        const Row F = row_mul(T, rc->CO[i]);
+        double *f = frames + 12 * i;
+        f[3 * r] = F.a; f[3 * r + 1] = F.b; f[3 * r + 2] = F.c; f[9 + r] = F.t;
+    }
+    const Row H = row_mul(T, rc->P0[7]);
+    {
+        const Row F = row_mul(H, rc->CO[7]);
+        double *f = frames + 12 * 7;
+        f[3 * r] = F.a; f[3 * r + 1] = F.b; f[3 * r + 2] = F.c; f[9 + r] = F.t;
+    }
+#pragma unroll 1
+    for (int k = 0; k < 2; ++k) {
+        const double *B = rc->P0[8 + k];
+        const double ty = B[10] + ((k == 0) ? q[7] : -q[8]);   // robot_pykdl.py:181-184
+        Row G;
+        G.a = fma(H.a, B[0], fma(H.b, B[3], H.c * B[6]));
+        G.b = fma(H.a, B[1], fma(H.b, B[4], H.c * B[7]));
+        G.c = fma(H.a, B[2], fma(H.b, B[5], H.c * B[8]));
+        G.t = fma(H.a, B[9], fma(H.b, ty, fma(H.c, B[11], H.t)));
+        const Row F = row_mul(G, rc->CO[8 + k]);
+        double *f = frames + 12 * (8 + k);
+        f[3 * r] = F.a; f[3 * r + 1] = F.b; f[3 * r + 2] = F.c; f[9 + r] = F.t;
+    }
+}
+
+// number of gradient slots of link j
 __device__ __forceinline__ int link_slots(int j) { return j < 7 ? j + 1 : (j == 7 ? 7 : 8); }
 
 // CHOMP functional gradient of one body point (omg/cost.py:24-43) pulled back through the point Jacobian
-// (omg/cost.py:92-110).  x, xp, xn: the point at waypoint i, i-1, i+1.  Writes g[0..slots) and returns
-// c * |v| (the point's obstacle cost).
-__device__ __forceinline__ double functional_grad(const double *jinfo_i, int j, double x, double y, double z,
-                                                  double xpx, double xpy, double xpz, double xnx, double xny,
-                                                  double xnz, double c, double gcx, double gcy, double gcz,
-                                                  double dt, double *g) {
+// (omg/cost.py:92-110).  frames_i: the 10 body-point frames of waypoint i (joint axes and the reference's
+// "origins" are rebuilt from them: axis_k = R_k * jab[k], origin_k = R_k * job[k] + t_k).
+// x, xp, xn: the point at waypoint i, i-1, i+1.  Writes g[0..8) and returns c * |v|.
+__device__ __forceinline__ double functional_grad(const RobotConst *__restrict__ rc, const double *frames_i, int j,
+                                                  double x, double y, double z, double xpx, double xpy, double xpz,
+                                                  double xnx, double xny, double xnz, double c, double gcx,
+                                                  double gcy, double gcz, double dt, double *g) {
     const double idt = 1.0 / dt;
     const double vx = (x - xpx) * idt, vy = (y - xpy) * idt, vz = (z - xpz) * idt;
     const double idt2 = idt * idt;
@@ -202,19 +254,24 @@ __device__ __forceinline__ double functional_grad(const double *jinfo_i, int j, 
     const double wy = speed * (gcy - hy * hg) - ks * (ay - hy * ha);
     const double wz = speed * (gcz - hz * hg) - ks * (az - hz * ha);
     const int ns = link_slots(j);
-#pragma unroll
+#pragma unroll 1
     for (int s = 0; s < NS; ++s) {
         double val = 0.0;
         if (s < ns) {
+            const int k = (s < 7) ? s : j;            // joint id: arm joint s, or the finger's own joint
+            const double *F = frames_i + 12 * k;
+            const double a0 = rc->jab[k][0], a1 = rc->jab[k][1], a2 = rc->jab[k][2];
+            const double ux = fma(F[0], a0, fma(F[1], a1, F[2] * a2));
+            const double uy = fma(F[3], a0, fma(F[4], a1, F[5] * a2));
+            const double uz = fma(F[6], a0, fma(F[7], a1, F[8] * a2));
             if (s < 7) {
-                const double *ji = jinfo_i + 6 * s;
-                const double rx = x - ji[3], ry = y - ji[4], rz = z - ji[5];
-                const double jx = ji[1] * rz - ji[2] * ry, jy = ji[2] * rx - ji[0] * rz,
-                             jz = ji[0] * ry - ji[1] * rx;
-                val = jx * wx + jy * wy + jz * wz;
+                const double o0 = rc->job[k][0], o1 = rc->job[k][1], o2 = rc->job[k][2];
+                const double rx = x - fma(F[0], o0, fma(F[1], o1, fma(F[2], o2, F[9])));
+                const double ry = y - fma(F[3], o0, fma(F[4], o1, fma(F[5], o2, F[10])));
+                const double rz = z - fma(F[6], o0, fma(F[7], o1, fma(F[8], o2, F[11])));
+                val = (uy * rz - uz * ry) * wx + (uz * rx - ux * rz) * wy + (ux * ry - uy * rx) * wz;
             } else {   // prismatic finger joint: the column is the axis itself (cost.py:106-108)
-                const double *ji = jinfo_i + 6 * (j - 1);   // link 8 -> slot 7, link 9 -> slot 8
-                val = ji[0] * wx + ji[1] * wy + ji[2] * wz;
+                val = ux * wx + uy * wy + uz * wz;
             }
         }
         g[s] = val;
@@ -223,34 +280,36 @@ __device__ __forceinline__ double functional_grad(const double *jinfo_i, int j, 
 }
 
 struct SmemLayout {
-    int n, c, lpi, nobj, p;
-    size_t off_xi, off_start, off_end, off_goal, off_frames, off_jinfo, off_lg, off_grad, off_u, off_viol,
-        off_red, off_pts, off_mask, off_best, off_bestp, off_objs, off_hist, total;
+    size_t off_xi, off_start, off_end, off_goal, off_frames, off_lg, off_grad, off_u, off_viol, off_red, off_pts,
+        off_mask, off_best, off_bestp, off_act, off_objs, off_hist, total;
 };
 
 __host__ __device__ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 __host__ __device__ inline SmemLayout make_layout(int n, int c, int lpi, int nobj, int p) {
     SmemLayout L;
-    L.n = n; L.c = c; L.lpi = lpi; L.nobj = nobj; L.p = p;
     size_t o = 0;
     L.off_xi = o; o += sizeof(double) * n * ND;
     L.off_start = o; o += sizeof(double) * ND;
     L.off_end = o; o += sizeof(double) * ND;
     L.off_goal = o; o += sizeof(double) * (c > 0 ? c : 1) * ND;
     L.off_frames = o; o += sizeof(double) * (n + 2) * NL * 12;
-    L.off_jinfo = o; o += sizeof(double) * n * NJ * 6;
-    // link gradients [n*10][8] fp64; aliased with the fp32 potential array [n*10][lpi] of the top-k path
-    size_t lg = sizeof(double) * n * NL * NS, pot = sizeof(float) * n * NL * lpi;
-    L.off_lg = o; o += (lg > pot ? lg : pot);
+    // link gradients [n*10][8] fp64; aliased with (a) the sin/cos table of the FK phase and (b) the fp32
+    // potential array [n*10][lpi] of the top-k path
+    size_t lg = sizeof(double) * n * NL * NS, pot = sizeof(float) * n * NL * lpi, sc = sizeof(double2) * (n + 2) * 7;
+    size_t u = lg > pot ? lg : pot;
+    u = u > sc ? u : sc;
+    o = align_up(o, 16);   // double2 sin/cos table
+    L.off_lg = o; o += align_up(u, 16);
     L.off_grad = o; o += sizeof(double) * n * ND;
     L.off_u = o; o += sizeof(double) * n * ND;
     L.off_viol = o; o += sizeof(double) * n * ND;
-    L.off_red = o; o += sizeof(double) * 40;
+    L.off_red = o; o += sizeof(double) * (33 * 8);
     L.off_pts = o; o += sizeof(double) * NL * p * 3;
     L.off_mask = o; o += sizeof(unsigned long long) * n * NL;
     L.off_best = o; o += sizeof(float) * n * NL;
     L.off_bestp = o; o += sizeof(int) * n * NL;
+    L.off_act = o; o += sizeof(int) * (n * NL + 40);
     o = align_up(o, 16);
     L.off_objs = o; o += sizeof(ObjRec) * nobj;
     L.off_hist = o; o += sizeof(int) * 264;
@@ -258,11 +317,29 @@ __host__ __device__ inline SmemLayout make_layout(int n, int c, int lpi, int nob
     return L;
 }
 
+// True when the lower-bound grid proves that the sample of object `ob` at world point (x,y,z) is > eps and
+// >= clearance (so the pair contributes nothing) AND that its 8-tap cell is in bounds (so it counts in P_in).
+// Approximate (matrix-form, division-free) grid coordinates are enough: the 6^3 region and the 1.5-voxel
+// interior margin absorb their error.
+__device__ __forceinline__ bool far_pair(const ObjRec &ob, const DilDesc &dd, int oi, float x, float y, float z) {
+    const float qx = fmaf(ob.r[0], x, fmaf(ob.r[1], y, fmaf(ob.r[2], z, ob.tx)));
+    const float qy = fmaf(ob.r[3], x, fmaf(ob.r[4], y, fmaf(ob.r[5], z, ob.ty)));
+    const float qz = fmaf(ob.r[6], x, fmaf(ob.r[7], y, fmaf(ob.r[8], z, ob.tz)));
+    const float gx = (qx - ob.minx) * ob.isx, gy = (qy - ob.miny) * ob.isy, gz = (qz - ob.minz) * ob.isz;
+    const bool interior = (gx >= 1.5f) & (gx <= ob.fd0 - 1.5f) & (gy >= 1.5f) & (gy <= ob.fd1 - 1.5f) &
+                          (gz >= 1.5f) & (gz <= ob.fd2 - 1.5f);
+    if (!interior) return false;
+    const int ix = ((int)gx) >> 1, iy = ((int)gy) >> 1, iz = ((int)gz) >> 1;
+    const float v = __ldg(dd.data + (size_t)oi * dd.obj_stride + ((size_t)ix * dd.by + iy) * dd.bz + iz);
+    const float slack = 1e-4f + 1e-5f * fabsf(v);   // an fp32 lerp may undershoot its taps by a few ulps
+    return (v > ob.eps + slack) & (v > ob.clr + slack);
+}
+
 // ----------------------------------------------------------------------------------------------------
 // the fused iteration
 // ----------------------------------------------------------------------------------------------------
-template <int LPI>
-__global__ void __launch_bounds__(512, 1) chomp_step_kernel(const StepArgs a) {
+template <int LPI, int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB) chomp_step_kernel(const StepArgs a) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int b = blockIdx.x;
     if (b >= a.batch) return;
@@ -280,9 +357,9 @@ __global__ void __launch_bounds__(512, 1) chomp_step_kernel(const StepArgs a) {
     double *s_end = reinterpret_cast<double *>(smem + L.off_end);
     double *s_goal = reinterpret_cast<double *>(smem + L.off_goal);
     double *s_frames = reinterpret_cast<double *>(smem + L.off_frames);
-    double *s_jinfo = reinterpret_cast<double *>(smem + L.off_jinfo);
     double *s_lg = reinterpret_cast<double *>(smem + L.off_lg);
     float *s_pot = reinterpret_cast<float *>(smem + L.off_lg);
+    double2 *s_sc = reinterpret_cast<double2 *>(smem + L.off_lg);
     double *s_grad = reinterpret_cast<double *>(smem + L.off_grad);
     double *s_u = reinterpret_cast<double *>(smem + L.off_u);
     double *s_viol = reinterpret_cast<double *>(smem + L.off_viol);
@@ -291,14 +368,19 @@ __global__ void __launch_bounds__(512, 1) chomp_step_kernel(const StepArgs a) {
     unsigned long long *s_mask = reinterpret_cast<unsigned long long *>(smem + L.off_mask);
     float *s_best = reinterpret_cast<float *>(smem + L.off_best);
     int *s_bestp = reinterpret_cast<int *>(smem + L.off_bestp);
+    int *s_act = reinterpret_cast<int *>(smem + L.off_act);
     ObjRec *s_objs = reinterpret_cast<ObjRec *>(smem + L.off_objs);
     int *s_hist = reinterpret_cast<int *>(smem + L.off_hist);
 
     const int tid = threadIdx.x, nthr = blockDim.x;
+    const int lane = tid & 31, warp = tid >> 5, nwarps = nthr >> 5;
     const double dt = prm.time_interval;
     const bool topk_mode = prm.top_k_collision > 0;
     const bool goal_set = prm.goal_set_proj != 0;
+    const int n_li = n * NL;
 
+#define OMGB_PROF(slot) do { if (a.prof && tid == 0) a.prof[(size_t)b * 12 + (slot)] = clock64(); } while (0)
+    OMGB_PROF(0);
     // ---- phase 0: stage ---------------------------------------------------------------------------
     double *g_xi = a.xi + (size_t)b * n * ND;
     for (int k = tid; k < n * ND; k += nthr) s_xi[k] = g_xi[k];
@@ -317,24 +399,40 @@ __global__ void __launch_bounds__(512, 1) chomp_step_kernel(const StepArgs a) {
         const int j = k / (P * 3), r = k - j * P * 3;
         s_pts[k] = rc->pts[j][r / 3][r % 3];
     }
+    for (int k = tid; k < n_li; k += nthr) { s_best[k] = 0.0f; s_bestp[k] = 0; }
     __syncthreads();
 
+    OMGB_PROF(1);
     // ---- phase 1: forward kinematics (n waypoints, then start, then end) ---------------------------
-    for (int cfg = tid; cfg < n + 2; cfg += nthr) {
+    // 1a: sin/cos of every arm joint angle, one per thread
+    for (int k = tid; k < (n + 2) * 7; k += nthr) {
+        const int cfg = k / 7, i = k - cfg * 7;
         const double *q = (cfg < n) ? (s_xi + cfg * ND) : (cfg == n ? s_start : s_end);
-        double ql[ND];
-#pragma unroll
-        for (int d = 0; d < ND; ++d) ql[d] = q[d];
-        panda_fk(rc, ql, s_frames + (size_t)cfg * NL * 12, cfg < n ? s_jinfo + (size_t)cfg * NJ * 6 : nullptr);
+        double sn, cs;
+        sincos(q[i], &sn, &cs);
+        s_sc[k] = make_double2(sn, cs);
+    }
+    __syncthreads();
+    // 1b: three threads per configuration, one transform row each
+    for (int k = tid; k < (n + 2) * 3; k += nthr) {
+        const int cfg = k / 3, r = k - cfg * 3;
+        const double *q = (cfg < n) ? (s_xi + cfg * ND) : (cfg == n ? s_start : s_end);
+        panda_fk_row(rc, q, s_sc + cfg * 7, r, s_frames + (size_t)cfg * NL * 12);
     }
     __syncthreads();
 
-    // ---- phase 1b: sphere cull ---------------------------------------------------------------------
-    for (int li = tid; li < n * NL; li += nthr) {
+    OMGB_PROF(2);
+    // ---- phase 1c: cull.  (waypoint, link) bounding sphere vs each object:
+    //  (i)  outside the region of the grid in which an 8-tap cell is in bounds: every sample reads 1.0 and
+    //       contributes nothing (kernel.cu:47-48);
+    //  (ii) strictly inside the grid but outside the object's ACTIVE box (the AABB of all bricks whose lower
+    //       bound allows value <= eps or < clearance): nothing contributes, all P pairs count as in-bounds. ----
+    int t_pin = 0;
+    const bool use_dil = a.dil.enabled != 0;
+    for (int li = tid; li < n_li; li += nthr) {
         const int j = li % NL;
-        const double *F = s_frames + (size_t)li * 12;
         double cx, cy, cz;
-        xform(F, (double)rc->sph[j][0], (double)rc->sph[j][1], (double)rc->sph[j][2], cx, cy, cz);
+        xform(s_frames + (size_t)li * 12, (double)rc->sph[j][0], (double)rc->sph[j][1], (double)rc->sph[j][2], cx, cy, cz);
         const float fx = (float)cx, fy = (float)cy, fz = (float)cz, rad = rc->sph[j][3];
         unsigned long long m = 0ull;
         for (int o = 0; o < O; ++o) {
@@ -344,39 +442,84 @@ __global__ void __launch_bounds__(512, 1) chomp_step_kernel(const StepArgs a) {
             const float qy = ob.r[3] * fx + ob.r[4] * fy + ob.r[5] * fz + ob.ty;
             const float qz = ob.r[6] * fx + ob.r[7] * fy + ob.r[8] * fz + ob.tz;
             const float s = rad + ob.cull_pad;
-            const bool hit = (qx > ob.lox - s) & (qx < ob.hix + s) & (qy > ob.loy - s) & (qy < ob.hiy + s) &
+            const bool box = (qx > ob.lox - s) & (qx < ob.hix + s) & (qy > ob.loy - s) & (qy < ob.hiy + s) &
                              (qz > ob.loz - s) & (qz < ob.hiz + s);
-            if (hit) m |= (1ull << o);
+            if (!box) continue;
+            if (use_dil && ob.cull_pad < 1e29f && !a.dbg_pts) {
+                const bool miss = (qx + s < ob.alox) | (qx - s > ob.ahix) | (qy + s < ob.aloy) | (qy - s > ob.ahiy) |
+                                  (qz + s < ob.aloz) | (qz - s > ob.ahiz);
+                if (miss) {
+                    const bool interior =
+                        ((qx - s - ob.minx) * ob.isx >= 1.5f) & ((qx + s - ob.minx) * ob.isx <= ob.fd0 - 1.5f) &
+                        ((qy - s - ob.miny) * ob.isy >= 1.5f) & ((qy + s - ob.miny) * ob.isy <= ob.fd1 - 1.5f) &
+                        ((qz - s - ob.minz) * ob.isz >= 1.5f) & ((qz + s - ob.minz) * ob.isz <= ob.fd2 - 1.5f);
+                    if (interior) { t_pin += P; continue; }
+                }
+            }
+            m |= 1ull << o;
         }
         s_mask[li] = m;
     }
     __syncthreads();
+    OMGB_PROF(3);
+    // ordered compaction of the link instances that still have work
+    {
+        int n_act = 0;   // running count (uniform)
+        for (int base = 0; base < n_li; base += nthr) {
+            const int li = base + tid;
+            const bool on = (li < n_li) && (s_mask[li] != 0ull || a.dbg_pts != nullptr);
+            const unsigned bal = __ballot_sync(0xffffffffu, on);
+            if (lane == 0) s_hist[warp] = __popc(bal);
+            __syncthreads();
+            int before = 0, total = 0;
+            for (int w = 0; w < nwarps; ++w) {
+                const int cnt = s_hist[w];
+                if (w < warp) before += cnt;
+                total += cnt;
+            }
+            if (on) s_act[n_act + before + __popc(bal & ((1u << lane) - 1u))] = li;
+            n_act += total;
+            __syncthreads();
+        }
+        if (tid == 0) s_hist[263] = n_act;
+    }
+    if (topk_mode)
+        for (int k = tid; k < n_li * LPI; k += nthr) s_pot[k] = 0.0f;   // (the sin/cos table is dead now)
+    else
+        for (int k = tid; k < n_li * NS; k += nthr) s_lg[k] = 0.0;
+    __syncthreads();
+    const int n_act = s_hist[263];
 
+    OMGB_PROF(4);
     // ---- phase 2: body points x objects ------------------------------------------------------------
     constexpr int GPW = 32 / LPI;                 // link instances per warp
-    const int lane = tid & 31, warp = tid >> 5, nwarps = nthr >> 5;
     const int sub = lane / LPI, pl = lane % LPI;  // which instance of the warp, which body point
+    const unsigned gmask = (LPI == 32) ? 0xffffffffu : (0xffffu << (sub * 16));
     const bool finger_soft = (prm.uncheck_finger_collision == -1);
-    int t_nnz = 0, t_pin = 0, t_col = 0;
+    int t_nnz = 0, t_col = 0;
     double t_cost = 0.0;
-    const int n_li = n * NL;
-    for (int base = warp * GPW; base < n_li; base += nwarps * GPW) {
-        const int li = base + sub;
-        const bool live = (li < n_li) && (pl < P);
-        const int lic = li < n_li ? li : n_li - 1;
-        const int i = lic / NL, j = lic - i * NL;
-        const double *F = s_frames + (size_t)lic * 12;
+    for (int base = warp * GPW; base < n_act; base += nwarps * GPW) {
+        const int idx = base + sub;
+        const bool have = idx < n_act;
+        const int li = s_act[have ? idx : n_act - 1];
+        const bool live = have && (pl < P);
+        const int i = li / NL, j = li - i * NL;
+        const double *F = s_frames + (size_t)li * 12;
         const double *bp = s_pts + ((size_t)j * P + (pl < P ? pl : 0)) * 3;
         double X, Y, Z;
         xform(F, bp[0], bp[1], bp[2], X, Y, Z);
         const float x = (float)X, y = (float)Y, z = (float)Z;   // omg/cost.py:136 .float()
-        unsigned long long m = live ? s_mask[lic] : 0ull;
+        unsigned long long m = live ? s_mask[li] : 0ull;
         float pot = 0.0f, col = 0.0f, gx = 0.0f, gy = 0.0f, gz = 0.0f;
         while (m) {
             const int o = __ffsll((long long)m) - 1;
             m &= m - 1;
             float po, co;
             bool inb;
+            if (use_dil && far_pair(s_objs[o], a.dil, o, x, y, z)) {   // exact: contributes nothing, in bounds
+                t_pin += 1;
+                continue;
+            }
             if (topk_mode) {
                 inb = pair_potential(s_objs[o], a.grids, x, y, z, po, co);
             } else {
@@ -402,17 +545,16 @@ __global__ void __launch_bounds__(512, 1) chomp_step_kernel(const StepArgs a) {
             }
         }
         if (topk_mode) {
-            if (li < n_li) s_pot[(size_t)li * LPI + pl] = live ? pot : 0.0f;
-            // argmax over the body points of this link instance; ties -> highest point index
-            float bv = live ? pot : -1.0f;
-            int bi = pl;
-#pragma unroll
-            for (int off = LPI / 2; off > 0; off >>= 1) {
-                const float ov = __shfl_xor_sync(0xffffffffu, bv, off, LPI);
-                const int oi = __shfl_xor_sync(0xffffffffu, bi, off, LPI);
-                if (ov > bv || (ov == bv && oi > bi)) { bv = ov; bi = oi; }
+            if (live) s_pot[(size_t)li * LPI + pl] = pot;
+            // argmax over the body points of this link instance (potentials are >= 0, so their bit patterns
+            // order like the values); ties -> highest point index
+            const unsigned bits = live ? __float_as_uint(pot) : 0u;
+            const unsigned mx = __reduce_max_sync(gmask, bits);
+            const unsigned bal = __ballot_sync(gmask, live && bits == mx) & gmask;
+            if (have && pl == 0 && mx != 0u) {
+                s_best[li] = __uint_as_float(mx);
+                s_bestp[li] = (31 - __clz(bal)) - sub * LPI;
             }
-            if (li < n_li && pl == 0) { s_best[li] = bv; s_bestp[li] = bi; }
         } else {
             // full-sum mode: functional gradient of every point with non-zero potential, reduced over
             // the link instance's body points with warp shuffles
@@ -420,32 +562,36 @@ __global__ void __launch_bounds__(512, 1) chomp_step_kernel(const StepArgs a) {
             double cst = 0.0;
 #pragma unroll
             for (int s = 0; s < NS; ++s) g[s] = 0.0;
-            if (live && (pot != 0.0f || gx != 0.0f || gy != 0.0f || gz != 0.0f)) {
+            const bool nz = live && (pot != 0.0f || gx != 0.0f || gy != 0.0f || gz != 0.0f);
+            if (nz) {
                 const double *Fp = (i > 0) ? (F - NL * 12) : (s_frames + ((size_t)n * NL + j) * 12);
                 const double *Fn = (i < n - 1) ? (F + NL * 12) : (s_frames + ((size_t)(n + 1) * NL + j) * 12);
                 double xp, yp, zp, xn, yn, zn;
                 xform(Fp, bp[0], bp[1], bp[2], xp, yp, zp);
                 xform(Fn, bp[0], bp[1], bp[2], xn, yn, zn);
-                cst = functional_grad(s_jinfo + (size_t)i * NJ * 6, j, X, Y, Z, xp, yp, zp, xn, yn, zn,
+                cst = functional_grad(rc, s_frames + (size_t)i * NL * 12, j, X, Y, Z, xp, yp, zp, xn, yn, zn,
                                       (double)pot, (double)gx, (double)gy, (double)gz, dt, g);
             }
+            if (__ballot_sync(gmask, nz) & gmask) {   // uniform per link instance
 #pragma unroll
-            for (int off = LPI / 2; off > 0; off >>= 1) {
+                for (int off = LPI / 2; off > 0; off >>= 1) {
 #pragma unroll
-                for (int s = 0; s < NS; ++s) g[s] += __shfl_xor_sync(0xffffffffu, g[s], off, LPI);
-                cst += __shfl_xor_sync(0xffffffffu, cst, off, LPI);
-            }
-            if (li < n_li && pl == 0) {
+                    for (int s = 0; s < NS; ++s) g[s] += __shfl_xor_sync(gmask, g[s], off, LPI);
+                    cst += __shfl_xor_sync(gmask, cst, off, LPI);
+                }
+                if (have && pl == 0) {
 #pragma unroll
-                for (int s = 0; s < NS; ++s) s_lg[(size_t)li * NS + s] = g[s];
-                t_cost += cst;
-                if (a.row_obs) atomicAdd(a.row_obs + (size_t)b * n + i, cst);
+                    for (int s = 0; s < NS; ++s) s_lg[(size_t)li * NS + s] = g[s];
+                    t_cost += cst;
+                    if (a.row_obs) atomicAdd(a.row_obs + (size_t)b * n + i, cst);
+                }
             }
         }
     }
-    const int nnz = (int)(block_sum((double)t_nnz, s_red) + 0.5);
-    const int p_in = (int)(block_sum((double)t_pin, s_red) + 0.5);
-    const int collide = (int)(block_sum((double)t_col, s_red) + 0.5);
+    OMGB_PROF(5);
+    double red4[4] = {(double)t_nnz, (double)t_pin, (double)t_col, t_cost};
+    block_sum_n<4>(red4, s_red);
+    const int nnz = (int)(red4[0] + 0.5), p_in = (int)(red4[1] + 0.5), collide = (int)(red4[2] + 0.5);
 
     double obs_sum = 0.0;
     if (topk_mode) {
@@ -461,7 +607,7 @@ __global__ void __launch_bounds__(512, 1) chomp_step_kernel(const StepArgs a) {
                 __syncthreads();
                 for (int k = tid; k < n_slots; k += nthr) {
                     const uint32_t u = __float_as_uint(s_pot[k]);
-                    if ((u & pmask) == prefix) atomicAdd(&s_hist[(u >> shift) & 255u], 1);
+                    if (u != 0u && (u & pmask) == prefix) atomicAdd(&s_hist[(u >> shift) & 255u], 1);
                 }
                 __syncthreads();
                 if (tid == 0) {
@@ -481,32 +627,37 @@ __global__ void __launch_bounds__(512, 1) chomp_step_kernel(const StepArgs a) {
             }
             tau = prefix;   // ties at tau are all kept (reference: unstable argsort, order undefined)
         }
+        OMGB_PROF(6);
         // ---- phase 4a: obstacle cost = sum over members of c*|v| (cost.py:30,416), links 0..7 ---------
         const int jmax = prm.consider_finger ? NL : NL - 2;
         double acc = 0.0;
-        for (int k = tid; k < n_slots; k += nthr) {
-            const float pv = s_pot[k];
-            const int li = k / LPI, p = k - li * LPI;
-            const int i = li / NL, j = li - i * NL;
-            if (p < P && j < jmax && pv > 0.0f && __float_as_uint(pv) >= tau) {
-                const double *F = s_frames + (size_t)li * 12;
-                const double *Fp = (i > 0) ? (F - NL * 12) : (s_frames + ((size_t)n * NL + j) * 12);
-                const double *bp = s_pts + ((size_t)j * P + p) * 3;
-                double X, Y, Z, xp, yp, zp;
-                xform(F, bp[0], bp[1], bp[2], X, Y, Z);
-                xform(Fp, bp[0], bp[1], bp[2], xp, yp, zp);
-                const double vx = (X - xp) / dt, vy = (Y - yp) / dt, vz = (Z - zp) / dt;
-                acc += (double)pv * sqrt(vx * vx + vy * vy + vz * vz);
+        if (nnz > 0) {
+            for (int k = tid; k < n_act * LPI; k += nthr) {
+                const int li = s_act[k / LPI], p = k % LPI;
+                const float pv = s_pot[(size_t)li * LPI + p];
+                const int i = li / NL, j = li - i * NL;
+                if (p < P && j < jmax && pv > 0.0f && __float_as_uint(pv) >= tau) {
+                    const double *F = s_frames + (size_t)li * 12;
+                    const double *Fp = (i > 0) ? (F - NL * 12) : (s_frames + ((size_t)n * NL + j) * 12);
+                    const double *bp = s_pts + ((size_t)j * P + p) * 3;
+                    double X, Y, Z, xp, yp, zp;
+                    xform(F, bp[0], bp[1], bp[2], X, Y, Z);
+                    xform(Fp, bp[0], bp[1], bp[2], xp, yp, zp);
+                    const double vx = (X - xp) / dt, vy = (Y - yp) / dt, vz = (Z - zp) / dt;
+                    acc += (double)pv * sqrt(vx * vx + vy * vy + vz * vz);
+                }
             }
         }
-        obs_sum = block_sum(acc, s_red) * (double)n;   // added to every waypoint row (SURVEY A-3)
-        __syncthreads();   // s_pot is dead from here on; s_lg (same storage) is written next
+        double red1[1] = {acc};
+        block_sum_n<1>(red1, s_red);   // (also the barrier after which s_pot is dead and s_lg may be written)
+        obs_sum = red1[0] * (double)n;   // added to every waypoint row (SURVEY A-3)
+        for (int k = tid; k < n_li * NS; k += nthr) s_lg[k] = 0.0;
+        __syncthreads();
+        OMGB_PROF(7);
         // ---- phase 4b: one winner per (waypoint, link) (SURVEY A-1) ----------------------------------
-        for (int li = tid; li < n_li; li += nthr) {
+        for (int idx = tid; idx < n_act; idx += nthr) {
+            const int li = s_act[idx];
             const int i = li / NL, j = li - i * NL;
-            double g[NS];
-#pragma unroll
-            for (int s = 0; s < NS; ++s) g[s] = 0.0;
             const float bv = s_best[li];
             if (j < jmax && bv > 0.0f && __float_as_uint(bv) >= tau) {
                 const int p = s_bestp[li];
@@ -525,6 +676,7 @@ __global__ void __launch_bounds__(512, 1) chomp_step_kernel(const StepArgs a) {
                     const int o = __ffsll((long long)m) - 1;
                     m &= m - 1;
                     float po, ax, ay, az, co;
+                    if (use_dil && far_pair(s_objs[o], a.dil, o, x, y, z)) continue;
                     pair_full(s_objs[o], a.grids, x, y, z, po, ax, ay, az, co);
                     pot = __fadd_rn(pot, po);
                     gx = __fadd_rn(gx, ax); gy = __fadd_rn(gy, ay); gz = __fadd_rn(gz, az);
@@ -533,20 +685,22 @@ __global__ void __launch_bounds__(512, 1) chomp_step_kernel(const StepArgs a) {
                     pot = __fmul_rn(pot, 0.1f); gx = __fmul_rn(gx, 0.1f); gy = __fmul_rn(gy, 0.1f);
                     gz = __fmul_rn(gz, 0.1f);
                 }
-                functional_grad(s_jinfo + (size_t)i * NJ * 6, j, X, Y, Z, xp, yp, zp, xn, yn, zn, (double)pot,
+                double g[NS];
+                functional_grad(rc, s_frames + (size_t)i * NL * 12, j, X, Y, Z, xp, yp, zp, xn, yn, zn, (double)pot,
                                 (double)gx, (double)gy, (double)gz, dt, g);
-            }
 #pragma unroll
-            for (int s = 0; s < NS; ++s) s_lg[(size_t)li * NS + s] = g[s];
+                for (int s = 0; s < NS; ++s) s_lg[(size_t)li * NS + s] = g[s];
+            }
         }
     } else {
-        obs_sum = block_sum(t_cost, s_red);
+        obs_sum = red4[3];
     }
     __syncthreads();
 
+    OMGB_PROF(8);
     // ---- phase 5: assemble gradient (cost.py:386-388/417-421, 425-449, 467-476) ----------------------
     const int jlast = (topk_mode && !prm.consider_finger) ? 7 : 9;
-    double t_so = 0.0, t_ss = 0.0, t_sg = 0.0;
+    double red7[7] = {0, 0, 0, 0, 0, 0, 0};   // |w_obs g|^2, |w_smooth g|^2, |g|^2, smooth rows, goal^2, low, high
     for (int k = tid; k < n * ND; k += nthr) {
         const int i = k / ND, d = k - i * ND;
         double og = 0.0;
@@ -566,39 +720,26 @@ __global__ void __launch_bounds__(512, 1) chomp_step_kernel(const StepArgs a) {
         const double ws = prm.smoothness_weight * sg;
         const double gt = wo + ws;
         s_grad[k] = gt;
-        t_so += wo * wo; t_ss += ws * ws; t_sg += gt * gt;
+        red7[0] += wo * wo; red7[1] += ws * ws; red7[2] += gt * gt;
+        // check_joint_limit (optimizer.py:166-174, sic: scalar "any below" times elementwise "above")
+        if (xc < rc->lower[d] - 5e-3) red7[5] = 1.0;
+        if (xc > rc->upper[d] + 5e-3) red7[6] = 1.0;
+        if (goal_set && i == n - 1) { const double dg = xc - s_end[d]; red7[4] += dg * dg; }
     }
-    // smoothness loss rows 0..n (cost.py:443-445)
-    double t_sl = 0.0;
-    for (int k = tid; k < (n + 1) * ND; k += nthr) {
+    for (int k = tid; k < (n + 1) * ND; k += nthr) {   // smoothness loss rows 0..n (cost.py:443-445)
         const int r = k / ND, d = k - r * ND;
         double v;
         if (r == 0) v = (s_xi[d] - s_start[d]) / dt;
         else if (r < n) v = (s_xi[k] - s_xi[k - ND]) / dt;
         else v = goal_set ? 0.0 : (s_end[d] - s_xi[(n - 1) * ND + d]) / dt;
         v *= prm.link_smooth_weight[d];
-        t_sl += v * v;
+        red7[3] += v * v;
     }
-    const double norm_wo = sqrt(block_sum(t_so, s_red));
-    const double norm_ws = sqrt(block_sum(t_ss, s_red));
-    const double norm_g = sqrt(block_sum(t_sg, s_red));
-    const double smooth_sum = 0.5 * block_sum(t_sl, s_red);
-    double goal_dist = 0.0;
-    if (goal_set) {
-        double t = 0.0;
-        if (tid < ND) { const double d = s_xi[(n - 1) * ND + tid] - s_end[tid]; t = d * d; }
-        goal_dist = sqrt(block_sum(t, s_red));
-    }
-    // check_joint_limit (optimizer.py:166-174, sic: scalar "any below" times elementwise "above")
-    double t_low = 0.0, t_high = 0.0;
-    for (int k = tid; k < n * ND; k += nthr) {
-        const int d = k % ND;
-        if (s_xi[k] < rc->lower[d] - 5e-3) t_low = 1.0;
-        if (s_xi[k] > rc->upper[d] + 5e-3) t_high = 1.0;
-    }
-    const bool any_low = block_sum(t_low, s_red) > 0.0;
-    const bool any_high = block_sum(t_high, s_red) > 0.0;
-    const bool violate = any_low && any_high;
+    block_sum_n<7>(red7, s_red);
+    const double norm_wo = sqrt(red7[0]), norm_ws = sqrt(red7[1]), norm_g = sqrt(red7[2]);
+    const double smooth_sum = 0.5 * red7[3];
+    const double goal_dist = goal_set ? sqrt(red7[4]) : 0.0;
+    const bool violate = (red7[5] > 0.0) && (red7[6] > 0.0);
     const bool terminate = (collide <= prm.allow_collision_point) && prm.pre_terminate && (goal_dist < 0.01) &&
                            (smooth_sum < prm.terminate_smooth_loss) && !violate;
     if (a.grad_out)
@@ -610,6 +751,7 @@ __global__ void __launch_bounds__(512, 1) chomp_step_kernel(const StepArgs a) {
     // update: 0 = info only, 1 = always (force_update), 2 = unless this iteration reports terminate
     // (omg/optimizer.py:124-125)
     if (prm.update == 1 || (prm.update == 2 && !terminate)) {
+        OMGB_PROF(9);
         // ---- phase 6: covariant update -----------------------------------------------------------
         for (int k = tid; k < n * ND; k += nthr) {
             const int i = k / ND, d = k - i * ND;
@@ -619,32 +761,35 @@ __global__ void __launch_bounds__(512, 1) chomp_step_kernel(const StepArgs a) {
             s_u[k] = acc;
         }
         __syncthreads();
-        for (int k = tid; k < n * ND; k += nthr) {
+        for (int k = tid; k < n * ND; k += nthr) {   // + Trajectory.update (core.py:43-51)
             const int i = k / ND, d = k - i * ND;
-            double up = -prm.step_size * s_u[k];
-            if (goal_set) {
-                double t1 = 0.0, t2 = 0.0;
-                for (int r = 0; r < c; ++r) {
-                    const double m = __ldg(a.proj + (size_t)i * c + r);
-                    t1 = fma(m, s_u[(n - c + r) * ND + d], t1);
-                    t2 = fma(m, s_xi[(n - c + r) * ND + d] - s_goal[r * ND + d], t2);
-                }
-                up = up + prm.step_size * t1 - t2;
-            }
-            s_viol[k] = up;
-        }
-        __syncthreads();
-        for (int k = tid; k < n * ND; k += nthr) {   // Trajectory.update (core.py:43-51)
-            const int d = k % ND;
             double v = s_xi[k];
-            if (d < 7) v += s_viol[k];
-            else v = fmin(fmax(v, 0.0), 0.04);
-            s_xi[k] = v;
+            if (d < 7) {
+                double up = -prm.step_size * s_u[k];
+                if (goal_set) {
+                    double t1 = 0.0, t2 = 0.0;
+                    for (int r = 0; r < c; ++r) {
+                        const double m = __ldg(a.proj + (size_t)i * c + r);
+                        t1 = fma(m, s_u[(n - c + r) * ND + d], t1);
+                        t2 = fma(m, s_xi[(n - c + r) * ND + d] - s_goal[r * ND + d], t2);
+                    }
+                    up = up + prm.step_size * t1 - t2;
+                }
+                v += up;
+            } else {
+                v = fmin(fmax(v, 0.0), 0.04);
+            }
+            s_viol[k] = v;   // staged: other threads still read s_xi rows n-c..n-1
         }
         __syncthreads();
+        for (int k = tid; k < n * ND; k += nthr) s_xi[k] = s_viol[k];
+        __syncthreads();
+        OMGB_PROF(10);
         // ---- phase 7: smooth joint-limit projection (optimizer.py:148-164) ------------------------
         for (int round = 0; round <= prm.joint_limit_max_steps; ++round) {
-            double t = 0.0;
+            double t[1] = {0.0};
+            double bm = -1.0;
+            int bk = 0x7fffffff;
             for (int k = tid; k < n * ND; k += nthr) {
                 const int d = k % ND;
                 const double v = s_xi[k];
@@ -652,17 +797,13 @@ __global__ void __launch_bounds__(512, 1) chomp_step_kernel(const StepArgs a) {
                 if (v < rc->lower[d]) viol = rc->lower[d] - v;
                 else if (v > rc->upper[d]) viol = rc->upper[d] - v;
                 s_viol[k] = viol;
-                t += viol * viol;
+                t[0] += viol * viol;
+                const double m = fabs(viol);
+                if (m > bm) { bm = m; bk = k; }   // first occurrence of the max in flat order (np.argmax)
             }
-            const double vn = sqrt(block_sum(t, s_red));
+            block_sum_n<1>(t, s_red);
+            const double vn = sqrt(t[0]);
             if (!(vn > 1e-2) || round == prm.joint_limit_max_steps) break;
-            // argmax |viol|, first occurrence in flat order (np.argmax)
-            double bm = -1.0;
-            int bk = 0x7fffffff;
-            for (int k = tid; k < n * ND; k += nthr) {
-                const double m = fabs(s_viol[k]);
-                if (m > bm) { bm = m; bk = k; }
-            }
 #pragma unroll
             for (int off = 16; off > 0; off >>= 1) {
                 const double om = __shfl_xor_sync(0xffffffffu, bm, off);
@@ -676,11 +817,11 @@ __global__ void __launch_bounds__(512, 1) chomp_step_kernel(const StepArgs a) {
                 int fk = s_hist[0];
                 for (int w = 1; w < nwarps; ++w)
                     if (s_red[w] > fm || (s_red[w] == fm && s_hist[w] < fk)) { fm = s_red[w]; fk = s_hist[w]; }
-                s_red[34] = fm;
+                s_red[40] = fm;
                 s_hist[260] = fk;
             }
             __syncthreads();
-            const double vmax = s_red[34];
+            const double vmax = s_red[40];
             const int kmax = s_hist[260];
             for (int k = tid; k < n * ND; k += nthr) {
                 const int i = k / ND, d = k - i * ND;
@@ -698,6 +839,7 @@ __global__ void __launch_bounds__(512, 1) chomp_step_kernel(const StepArgs a) {
         // ---- phase 8: write back ---------------------------------------------------------------
         for (int k = tid; k < n * ND; k += nthr) g_xi[k] = s_xi[k];
     }
+    OMGB_PROF(11);
     if (tid == 0) {
         double *inf = a.info + (size_t)b * OMGB_INFO_STRIDE;
         inf[OMGB_INFO_OBS] = obs_sum;
@@ -717,7 +859,7 @@ __global__ void __launch_bounds__(512, 1) chomp_step_kernel(const StepArgs a) {
         inf[OMGB_INFO_P_IN] = (double)p_in;
         inf[OMGB_INFO_NONZERO] = (double)nnz;
         inf[OMGB_INFO_LIMIT_ROUNDS] = (double)limit_rounds;
-        inf[OMGB_INFO_RESERVED] = 0.0;
+        inf[OMGB_INFO_RESERVED] = (double)n_act;   // link instances that survived the cull (diagnostic)
         if (a.done && a.stop_on_terminate && terminate && a.iteration > 0) a.done[b] = 1;
     }
 }

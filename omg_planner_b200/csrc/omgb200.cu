@@ -2,6 +2,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <string>
@@ -87,8 +88,86 @@ __global__ void prep_objects_kernel(const float *__restrict__ pose, const float 
     // An out-of-bounds sample reads 1.0 (kernel.cu:47-48): it contributes nothing iff eps < 1 and
     // clearance <= 1.  Otherwise the cull must never reject.
     r.cull_pad = (r.eps < 1.0f && r.clr <= 1.0f) ? (1e-3f + fmaxf(sx, fmaxf(sy, sz))) : 1e30f;
+    r.isx = 1.0f / sx; r.isy = 1.0f / sy; r.isz = 1.0f / sz;
+    r.alox = r.aloy = r.aloz = -1e30f; r.ahix = r.ahiy = r.ahiz = 1e30f; r.pad0_ = 0.0f;   // (no active box yet)
     r.grid_offset = (long long)o * r.d0 * r.d1 * r.d2;
     out[o] = r;
+}
+
+// ----------------------------------------------------------------------------------------------------
+// lower-bound grid (DilDesc): 2^3-voxel brick minima, then the minimum over each brick's 3^3 neighbourhood.
+// Built once per omgb_scene_set_sdf.
+// ----------------------------------------------------------------------------------------------------
+__global__ void brick_min_kernel(const float *__restrict__ grids, int num_objects, int d0, int d1, int d2,
+                                 float *__restrict__ out, int b0, int b1, int b2) {
+    const long long total = (long long)num_objects * b0 * b1 * b2;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
+         t += (long long)gridDim.x * blockDim.x) {
+        const int bz = (int)(t % b2);
+        const int by = (int)((t / b2) % b1);
+        const int bx = (int)((t / ((long long)b2 * b1)) % b0);
+        const int o = (int)(t / ((long long)b2 * b1 * b0));
+        const float *g = grids + (size_t)o * d0 * d1 * d2;
+        float m = 3.0e38f;
+        for (int x = bx * 2; x < min(bx * 2 + 2, d0); ++x)
+            for (int y = by * 2; y < min(by * 2 + 2, d1); ++y)
+                for (int z = bz * 2; z < min(bz * 2 + 2, d2); ++z) m = fminf(m, g[((size_t)x * d1 + y) * d2 + z]);
+        out[t] = m;
+    }
+}
+
+__global__ void brick_dilate_kernel(const float *__restrict__ in, int num_objects, int b0, int b1, int b2,
+                                    float *__restrict__ out) {
+    const long long total = (long long)num_objects * b0 * b1 * b2;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
+         t += (long long)gridDim.x * blockDim.x) {
+        const int bz = (int)(t % b2);
+        const int by = (int)((t / b2) % b1);
+        const int bx = (int)((t / ((long long)b2 * b1)) % b0);
+        const int o = (int)(t / ((long long)b2 * b1 * b0));
+        const float *g = in + (size_t)o * b0 * b1 * b2;
+        float m = 3.0e38f;
+        for (int x = max(bx - 1, 0); x <= min(bx + 1, b0 - 1); ++x)
+            for (int y = max(by - 1, 0); y <= min(by + 1, b1 - 1); ++y)
+                for (int z = max(bz - 1, 0); z <= min(bz + 1, b2 - 1); ++z) m = fminf(m, g[((size_t)x * b1 + y) * b2 + z]);
+        out[t] = m;
+    }
+}
+
+// Active box per object: AABB (object frame) of the bricks whose lower bound allows value <= eps or < clearance.
+__global__ void active_bounds_init_kernel(int *__restrict__ bounds, int num_objects) {
+    const int o = blockIdx.x * blockDim.x + threadIdx.x;
+    if (o >= num_objects) return;
+    bounds[6 * o + 0] = bounds[6 * o + 1] = bounds[6 * o + 2] = 0x7fffffff;
+    bounds[6 * o + 3] = bounds[6 * o + 4] = bounds[6 * o + 5] = -1;
+}
+
+__global__ void active_bounds_kernel(const float *__restrict__ dil, const ObjRec *__restrict__ objs, int num_objects,
+                                     int b0, int b1, int b2, int *__restrict__ bounds) {
+    const long long per = (long long)b0 * b1 * b2, total = per * num_objects;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
+         t += (long long)gridDim.x * blockDim.x) {
+        const int o = (int)(t / per);
+        const float v = dil[t];
+        const float slack = 1e-4f + 1e-5f * fabsf(v);
+        if ((v > objs[o].eps + slack) && (v > objs[o].clr + slack)) continue;   // provably inactive brick
+        const long long r = t - (long long)o * per;
+        const int bz = (int)(r % b2), by = (int)((r / b2) % b1), bx = (int)(r / ((long long)b2 * b1));
+        atomicMin(bounds + 6 * o + 0, bx); atomicMin(bounds + 6 * o + 1, by); atomicMin(bounds + 6 * o + 2, bz);
+        atomicMax(bounds + 6 * o + 3, bx); atomicMax(bounds + 6 * o + 4, by); atomicMax(bounds + 6 * o + 5, bz);
+    }
+}
+
+__global__ void active_bounds_final_kernel(const int *__restrict__ bounds, ObjRec *__restrict__ objs, int num_objects) {
+    const int o = blockIdx.x * blockDim.x + threadIdx.x;
+    if (o >= num_objects) return;
+    ObjRec &r = objs[o];
+    const float sx = r.ex / r.fd0, sy = r.ey / r.fd1, sz = r.ez / r.fd2;
+    // a sample whose grid coordinate g has floor(g) in brick b lies in [2b, 2b+2) voxel units
+    r.alox = r.minx + (2.0f * bounds[6 * o + 0] - 0.01f) * sx; r.ahix = r.minx + (2.0f * bounds[6 * o + 3] + 2.01f) * sx;
+    r.aloy = r.miny + (2.0f * bounds[6 * o + 1] - 0.01f) * sy; r.ahiy = r.miny + (2.0f * bounds[6 * o + 4] + 2.01f) * sy;
+    r.aloz = r.minz + (2.0f * bounds[6 * o + 2] - 0.01f) * sz; r.ahiz = r.minz + (2.0f * bounds[6 * o + 5] + 2.01f) * sz;
+    if (bounds[6 * o + 3] < 0) { r.alox = r.aloy = r.aloz = 1e30f; r.ahix = r.ahiy = r.ahiz = -1e30f; }
 }
 
 // ----------------------------------------------------------------------------------------------------
@@ -163,7 +242,7 @@ __global__ void __launch_bounds__(256) batch_obstacle_cost_kernel(
             double ql[ND];
 #pragma unroll
             for (int d = 0; d < ND; ++d) ql[d] = q[d];
-            panda_fk(rc, ql, s_frames + (size_t)threadIdx.x * NL * 12, nullptr);
+            panda_fk(rc, ql, s_frames + (size_t)threadIdx.x * NL * 12);
         }
     }
     __syncthreads();
@@ -231,6 +310,10 @@ struct omgb_scene {
     int n = 0, c = 0;
     bool metric_set = false;
     // staging for the host-buffer entry point
+    float *d_dil = nullptr;
+    DilDesc dil;
+    int *d_bounds = nullptr;
+    long long *d_prof = nullptr;   // diagnostic: per-CTA phase clocks (omgb_scene_set_profile)
     double *d_stage = nullptr;
     size_t stage_bytes = 0;
     int smem_optin = 0;
@@ -244,6 +327,7 @@ extern "C" int omgb_scene_create(omgb_scene_t **out, int device) {
     OMGB_CUDA(cudaSetDevice(device));
     omgb_scene *s = new omgb_scene();
     s->device = device;
+    memset(&s->dil, 0, sizeof(s->dil));
     cudaError_t e = cudaMalloc(&s->d_robot, sizeof(RobotConst));
     if (e != cudaSuccess) { delete s; return fail(OMGB_ERR_CUDA, cudaGetErrorString(e)); }
     cudaDeviceGetAttribute(&s->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
@@ -255,7 +339,7 @@ extern "C" int omgb_scene_destroy(omgb_scene_t *s) {
     if (!s) return OMGB_OK;
     cudaSetDevice(s->device);
     cudaFree(s->d_robot); cudaFree(s->d_limits); cudaFree(s->d_objparams); cudaFree(s->d_objs);
-    cudaFree(s->d_Ainv); cudaFree(s->d_proj); cudaFree(s->d_stage);
+    cudaFree(s->d_Ainv); cudaFree(s->d_proj); cudaFree(s->d_stage); cudaFree(s->d_dil); cudaFree(s->d_bounds);
     delete s;
     return OMGB_OK;
 }
@@ -285,9 +369,18 @@ extern "C" int omgb_scene_set_robot(omgb_scene_t *s, const double *pose_0, const
         const double *t2j = tip2joint + 16 * i;
         const double *ax = joint_axis + 3 * i;
         const double *og = use_true_origin ? joint_origin + 3 * i : ax;   // robot_pykdl.py:104 aliasing
+        // joint axis / "origin" in the joint's link frame (joint_pose = T * tip2joint, robot_pykdl.py:193-202),
+        // then re-expressed in the body-point frame F = T * center_offset the kernel stores:
+        //   axis_world = F.R * (CO_R^T a),  origin_world = F.R * (CO_R^T (o - CO_t)) + F.t
+        double ja[3], jo[3];
         for (int r = 0; r < 3; ++r) {
-            h.ja[i][r] = t2j[4 * r] * ax[0] + t2j[4 * r + 1] * ax[1] + t2j[4 * r + 2] * ax[2];
-            h.jo[i][r] = t2j[4 * r] * og[0] + t2j[4 * r + 1] * og[1] + t2j[4 * r + 2] * og[2] + t2j[4 * r + 3];
+            ja[r] = t2j[4 * r] * ax[0] + t2j[4 * r + 1] * ax[1] + t2j[4 * r + 2] * ax[2];
+            jo[r] = t2j[4 * r] * og[0] + t2j[4 * r + 1] * og[1] + t2j[4 * r + 2] * og[2] + t2j[4 * r + 3];
+        }
+        for (int r = 0; r < 3; ++r) {
+            const double *co = h.CO[i];
+            h.jab[i][r] = co[r] * ja[0] + co[3 + r] * ja[1] + co[6 + r] * ja[2];
+            h.job[i][r] = co[r] * (jo[0] - co[9]) + co[3 + r] * (jo[1] - co[10]) + co[6 + r] * (jo[2] - co[11]);
         }
         // bounding sphere of the link's body points (centre = midpoint of the AABB)
         double lo[3] = {1e30, 1e30, 1e30}, hi[3] = {-1e30, -1e30, -1e30};
@@ -315,6 +408,12 @@ extern "C" int omgb_scene_set_robot(omgb_scene_t *s, const double *pose_0, const
     return OMGB_OK;
 }
 
+extern "C" int omgb_scene_set_profile(omgb_scene_t *s, long long *d_phase_clocks) {
+    if (!s) return fail(OMGB_ERR_INVALID, "omgb_scene_set_profile: null scene");
+    s->d_prof = d_phase_clocks;
+    return OMGB_OK;
+}
+
 extern "C" int omgb_scene_set_sdf(omgb_scene_t *s, const float *d_sdf_grids, const float *h_sdf_limits,
                                   int num_objects, int dx, int dy, int dz) {
     if (!s || !d_sdf_grids || !h_sdf_limits) return fail(OMGB_ERR_INVALID, "omgb_scene_set_sdf: null argument");
@@ -336,6 +435,28 @@ extern "C" int omgb_scene_set_sdf(omgb_scene_t *s, const float *d_sdf_grids, con
     OMGB_CUDA(cudaMemcpy(s->d_limits, h_sdf_limits, sizeof(float) * 10 * num_objects, cudaMemcpyHostToDevice));
     s->d_grids = d_sdf_grids;
     s->num_objects = num_objects; s->gx = dx; s->gy = dy; s->gz = dz;
+    {   // lower-bound grid (see DilDesc)
+        DilDesc &dd = s->dil;
+        memset(&dd, 0, sizeof(dd));
+        dd.bx = (dx + 1) / 2; dd.by = (dy + 1) / 2; dd.bz = (dz + 1) / 2;
+        dd.obj_stride = (long long)dd.bx * dd.by * dd.bz;
+        const long long total = dd.obj_stride * num_objects;
+        cudaFree(s->d_dil);
+        s->d_dil = nullptr;
+        float *tmp = nullptr;
+        OMGB_CUDA(cudaMalloc(&s->d_dil, sizeof(float) * (size_t)total));
+        OMGB_CUDA(cudaMalloc(&tmp, sizeof(float) * (size_t)total));
+        const int blocks = (int)((total + 255) / 256 > 148 * 64 ? 148 * 64 : (total + 255) / 256);
+        brick_min_kernel<<<blocks, 256>>>(d_sdf_grids, num_objects, dx, dy, dz, tmp, dd.bx, dd.by, dd.bz);
+        brick_dilate_kernel<<<blocks, 256>>>(tmp, num_objects, dd.bx, dd.by, dd.bz, s->d_dil);
+        cudaError_t e1 = cudaGetLastError(), e2 = cudaDeviceSynchronize();
+        cudaFree(tmp);
+        if (e1 != cudaSuccess || e2 != cudaSuccess)
+            return fail(OMGB_ERR_CUDA, std::string("lower-bound grid build: ") + cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
+        dd.data = s->d_dil;
+        const char *env = getenv("OMGB_NO_LOWER_BOUND");
+        dd.enabled = (env && atoi(env)) ? 0 : 1;
+    }
     s->sdf_set = true;
     s->objs_set = false;
     return OMGB_OK;
@@ -361,6 +482,15 @@ extern "C" int omgb_scene_set_objects(omgb_scene_t *s, const float *pose_inv, co
                                                       s->d_objparams + 17 * O, s->d_objparams + 18 * O,
                                                       s->d_objparams + 19 * O, O, s->d_objs);
     OMGB_CUDA(cudaGetLastError());
+    if (s->dil.enabled) {   // active boxes depend on eps / clearance
+        if (!s->d_bounds) OMGB_CUDA(cudaMalloc(&s->d_bounds, sizeof(int) * 6 * OMGB_MAX_OBJECTS));
+        const long long total = s->dil.obj_stride * O;
+        const int blocks = (int)((total + 255) / 256 > 148 * 16 ? 148 * 16 : (total + 255) / 256);
+        active_bounds_init_kernel<<<1, 64, 0, st>>>(s->d_bounds, O);
+        active_bounds_kernel<<<blocks, 256, 0, st>>>(s->d_dil, s->d_objs, O, s->dil.bx, s->dil.by, s->dil.bz, s->d_bounds);
+        active_bounds_final_kernel<<<1, 64, 0, st>>>(s->d_bounds, s->d_objs, O);
+        OMGB_CUDA(cudaGetLastError());
+    }
     s->objs_set = true;
     return OMGB_OK;
 }
@@ -437,21 +567,45 @@ static int check_step(const omgb_scene *s, const omgb_step_params_t *prm, int ba
     return OMGB_OK;
 }
 
+template <int LPI, int THREADS, int MINB>
+static int launch_cfg(const StepArgs &a, size_t smem, cudaStream_t st) {
+    OMGB_CUDA(cudaFuncSetAttribute(chomp_step_kernel<LPI, THREADS, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)smem));
+    chomp_step_kernel<LPI, THREADS, MINB><<<a.batch, THREADS, smem, st>>>(a);
+    OMGB_CUDA(cudaGetLastError());
+    return OMGB_OK;
+}
+
+static int step_config() {   // 0: 256 threads x 3 CTAs/SM, 1: 512 x 2, 2: 512 x 1, 3: 256 x 2
+    static int cfg = -1;
+    if (cfg < 0) {
+        const char *e = getenv("OMGB_STEP_CONFIG");
+        cfg = e ? atoi(e) : 0;
+    }
+    return cfg;
+}
+
 static int launch_step(omgb_scene *s, const StepArgs &a, cudaStream_t st) {
     const int lpi = s->p <= 16 ? 16 : 32;
     const SmemLayout L = make_layout(a.prm.n_waypoints, a.prm.constraint_rows, lpi, s->num_objects, s->p);
     if (L.total > (size_t)s->smem_optin)
         return fail(OMGB_ERR_UNSUPPORTED, "trajectory too long for one CTA's shared memory");
     if (a.batch == 0) return OMGB_OK;
+    const int cfg = step_config();
     if (lpi == 16) {
-        OMGB_CUDA(cudaFuncSetAttribute(chomp_step_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
-        chomp_step_kernel<16><<<a.batch, 512, L.total, st>>>(a);
-    } else {
-        OMGB_CUDA(cudaFuncSetAttribute(chomp_step_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
-        chomp_step_kernel<32><<<a.batch, 512, L.total, st>>>(a);
+        switch (cfg) {
+            case 1: return launch_cfg<16, 512, 2>(a, L.total, st);
+            case 2: return launch_cfg<16, 512, 1>(a, L.total, st);
+            case 3: return launch_cfg<16, 256, 2>(a, L.total, st);
+            default: return launch_cfg<16, 256, 3>(a, L.total, st);
+        }
     }
-    OMGB_CUDA(cudaGetLastError());
-    return OMGB_OK;
+    switch (cfg) {
+        case 1: return launch_cfg<32, 512, 2>(a, L.total, st);
+        case 2: return launch_cfg<32, 512, 1>(a, L.total, st);
+        case 3: return launch_cfg<32, 256, 2>(a, L.total, st);
+        default: return launch_cfg<32, 256, 3>(a, L.total, st);
+    }
 }
 
 static StepArgs make_args(const omgb_scene *s, const omgb_step_params_t *prm, int batch, double *xi,
@@ -462,6 +616,8 @@ static StepArgs make_args(const omgb_scene *s, const omgb_step_params_t *prm, in
     a.objs = s->d_objs; a.grids = s->d_grids; a.robot = s->d_robot; a.Ainv = s->d_Ainv; a.proj = s->d_proj;
     a.xi = xi; a.start = start; a.end = end; a.goal_rows = goal_rows; a.active = active; a.done = nullptr;
     a.grad_out = grad_out; a.info = info; a.dbg_pot = dbg_pot; a.dbg_pts = dbg_pts; a.row_obs = row_obs;
+    a.dil = s->dil;
+    a.prof = s->d_prof;
     a.num_objects = s->num_objects; a.batch = batch; a.iteration = 0; a.stop_on_terminate = 0;
     a.prm = *prm;
     if (!a.prm.goal_set_proj) a.prm.constraint_rows = 0;

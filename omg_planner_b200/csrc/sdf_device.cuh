@@ -28,6 +28,10 @@ struct __align__(16) ObjRec {
     float lox, loy, loz;         // object-frame interval inside which a point's 8-tap cell is in bounds
     float hix, hiy, hiz;
     float cull_pad;              // conservative slack for the sphere cull
+    float isx, isy, isz;         // 1 / grid spacing per axis (cull only)
+    float alox, aloy, aloz;      // object-frame AABB of the region where a sample can be <= eps or < clearance
+    float ahix, ahiy, ahiz;      // (from the lower-bound grid; empty when alo > ahi)
+    float pad0_;
     long long grid_offset;       // o * d0*d1*d2
 };
 

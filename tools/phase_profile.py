@@ -1,0 +1,57 @@
+#!/usr/bin/env python
+"""Per-phase clock breakdown of the fused CHOMP kernel (diagnostic; run on the GPU box).
+Writes gpurun_out/phase_profile.txt."""
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from omg_planner_b200 import _lib, scene as S  # noqa: E402
+from omg_planner_b200.config import ChompConfig  # noqa: E402
+from omg_planner_b200.engine import ChompEngine, _dp  # noqa: E402
+from omg_planner_b200.robot import PandaConstants  # noqa: E402
+
+NAMES = ["stage", "fk", "cull", "compact", "points", "reduce+select", "cost", "winners", "assemble", "update",
+         "limits"]
+
+
+def main():
+    mode = dict(goal_set_proj=True, use_standoff=True, top_k_collision=0 if "fullsum" in sys.argv else 1000)
+    B = 1024
+    sc = S.make_scene(num_objects=10, grid=128, seed=0)
+    cfg = ChompConfig(**mode)
+    robot = PandaConstants()
+    eng = ChompEngine(robot=robot).load_scene(sc, cfg)
+    xi, st, en, tails = S.make_trajectories(B, 30, robot.joint_lower_limit, robot.joint_upper_limit, seed=0)
+    dev = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    x, s, e, t = dev(xi), dev(st), dev(en), dev(tails)
+    prof = torch.zeros((B, 12), dtype=torch.int64, device="cuda")
+    for it in range(8):
+        cfg.obstacle_weight, cfg.smoothness_weight, cfg.step_size = cfg.schedule(it + 1)
+        if it == 7:
+            _lib.check(eng.L.omgb_scene_set_profile(eng._h, _dp(prof)))
+        out = eng.step(cfg, x, s, e, t)
+    torch.cuda.synchronize()
+    p = prof.cpu().numpy().astype(np.float64)
+    d = np.diff(p, axis=1)
+    info = out["info"].cpu().numpy()
+    lines = ["mode %s; per-CTA cycles (mean / median / max over %d CTAs)" % (mode, B)]
+    tot = (p[:, 11] - p[:, 0])
+    for k, name in enumerate(NAMES):
+        lines.append("%-14s mean %9.0f  median %9.0f  max %9.0f  share %.3f" % (
+            name, d[:, k].mean(), np.median(d[:, k]), d[:, k].max(), d[:, k].sum() / tot.sum()))
+    lines.append("total          mean %9.0f  median %9.0f  max %9.0f" % (tot.mean(), np.median(tot), tot.max()))
+    lines.append("P_in mean %.1f  nnz mean %.1f  active link instances mean %.1f / 300  limit rounds mean %.2f" % (
+        info[:, 12].mean(), info[:, 13].mean(), info[:, 15].mean(), info[:, 14].mean()))
+    txt = "\n".join(lines)
+    print(txt)
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    with open(os.path.join(ROOT, "gpurun_out", "phase_profile.txt"), "a") as f:
+        f.write(txt + "\n\n")
+
+
+if __name__ == "__main__":
+    main()
