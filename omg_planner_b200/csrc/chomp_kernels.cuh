@@ -231,14 +231,12 @@ __device__ __forceinline__ void panda_fk_row(const RobotConst *__restrict__ rc, 
 // number of gradient slots of link j
 __device__ __forceinline__ int link_slots(int j) { return j < 7 ? j + 1 : (j == 7 ? 7 : 8); }
 
-// CHOMP functional gradient of one body point (omg/cost.py:24-43) pulled back through the point Jacobian
-// (omg/cost.py:92-110).  frames_i: the 10 body-point frames of waypoint i (joint axes and the reference's
-// "origins" are rebuilt from them: axis_k = R_k * jab[k], origin_k = R_k * job[k] + t_k).
-// x, xp, xn: the point at waypoint i, i-1, i+1.  Writes g[0..8) and returns c * |v|.
-__device__ __forceinline__ double functional_grad(const RobotConst *__restrict__ rc, const double *frames_i, int j,
-                                                  double x, double y, double z, double xpx, double xpy, double xpz,
-                                                  double xnx, double xny, double xnz, double c, double gcx,
-                                                  double gcy, double gcz, double dt, double *g) {
+// CHOMP functional gradient of one body point (omg/cost.py:24-43): the workspace vector w that the point
+// Jacobian pulls back, w = |v| P grad_c - c P a / |v|^2 with P = I - v^ v^T.  x, xp, xn: the point at waypoint
+// i, i-1, i+1.  Returns c * |v| (the point's obstacle cost).
+__device__ __forceinline__ double fg_weight(double x, double y, double z, double xpx, double xpy, double xpz,
+                                            double xnx, double xny, double xnz, double c, double gcx, double gcy,
+                                            double gcz, double dt, double &wx, double &wy, double &wz) {
     const double idt = 1.0 / dt;
     const double vx = (x - xpx) * idt, vy = (y - xpy) * idt, vz = (z - xpz) * idt;
     const double idt2 = idt * idt;
@@ -250,33 +248,43 @@ __device__ __forceinline__ double functional_grad(const RobotConst *__restrict__
     const double ha = hx * ax + hy * ay + hz * az;
     const double hg = hx * gcx + hy * gcy + hz * gcz;
     const double ks = c / (speed * speed + 1e-8);
-    const double wx = speed * (gcx - hx * hg) - ks * (ax - hx * ha);
-    const double wy = speed * (gcy - hy * hg) - ks * (ay - hy * ha);
-    const double wz = speed * (gcz - hz * hg) - ks * (az - hz * ha);
-    const int ns = link_slots(j);
-#pragma unroll 1
-    for (int s = 0; s < NS; ++s) {
-        double val = 0.0;
-        if (s < ns) {
-            const int k = (s < 7) ? s : j;            // joint id: arm joint s, or the finger's own joint
-            const double *F = frames_i + 12 * k;
-            const double a0 = rc->jab[k][0], a1 = rc->jab[k][1], a2 = rc->jab[k][2];
-            const double ux = fma(F[0], a0, fma(F[1], a1, F[2] * a2));
-            const double uy = fma(F[3], a0, fma(F[4], a1, F[5] * a2));
-            const double uz = fma(F[6], a0, fma(F[7], a1, F[8] * a2));
-            if (s < 7) {
-                const double o0 = rc->job[k][0], o1 = rc->job[k][1], o2 = rc->job[k][2];
-                const double rx = x - fma(F[0], o0, fma(F[1], o1, fma(F[2], o2, F[9])));
-                const double ry = y - fma(F[3], o0, fma(F[4], o1, fma(F[5], o2, F[10])));
-                const double rz = z - fma(F[6], o0, fma(F[7], o1, fma(F[8], o2, F[11])));
-                val = (uy * rz - uz * ry) * wx + (uz * rx - ux * rz) * wy + (ux * ry - uy * rx) * wz;
-            } else {   // prismatic finger joint: the column is the axis itself (cost.py:106-108)
-                val = ux * wx + uy * wy + uz * wz;
-            }
-        }
-        g[s] = val;
-    }
+    wx = speed * (gcx - hx * hg) - ks * (ax - hx * ha);
+    wy = speed * (gcy - hy * hg) - ks * (ay - hy * ha);
+    wz = speed * (gcz - hz * hg) - ks * (az - hz * ha);
     return c * speed;
+}
+
+// Gradient slot s of link j: (point Jacobian column)^T w (omg/cost.py:92-110).  frames_i: the 10 body-point
+// frames of waypoint i; joint axes and the reference's "origins" are rebuilt from them:
+// axis_k = R_k * jab[k], origin_k = R_k * job[k] + t_k.
+__device__ __forceinline__ double fg_slot(const RobotConst *__restrict__ rc, const double *frames_i, int j, int s,
+                                          double x, double y, double z, double wx, double wy, double wz) {
+    if (s >= link_slots(j)) return 0.0;
+    const int k = (s < 7) ? s : j;            // joint id: arm joint s, or the finger's own joint
+    const double *F = frames_i + 12 * k;
+    const double a0 = rc->jab[k][0], a1 = rc->jab[k][1], a2 = rc->jab[k][2];
+    const double ux = fma(F[0], a0, fma(F[1], a1, F[2] * a2));
+    const double uy = fma(F[3], a0, fma(F[4], a1, F[5] * a2));
+    const double uz = fma(F[6], a0, fma(F[7], a1, F[8] * a2));
+    if (s < 7) {
+        const double o0 = rc->job[k][0], o1 = rc->job[k][1], o2 = rc->job[k][2];
+        const double rx = x - fma(F[0], o0, fma(F[1], o1, fma(F[2], o2, F[9])));
+        const double ry = y - fma(F[3], o0, fma(F[4], o1, fma(F[5], o2, F[10])));
+        const double rz = z - fma(F[6], o0, fma(F[7], o1, fma(F[8], o2, F[11])));
+        return (uy * rz - uz * ry) * wx + (uz * rx - ux * rz) * wy + (ux * ry - uy * rx) * wz;
+    }
+    return ux * wx + uy * wy + uz * wz;   // prismatic finger joint: the column is the axis itself (cost.py:106-108)
+}
+
+__device__ __forceinline__ double functional_grad(const RobotConst *__restrict__ rc, const double *frames_i, int j,
+                                                  double x, double y, double z, double xpx, double xpy, double xpz,
+                                                  double xnx, double xny, double xnz, double c, double gcx,
+                                                  double gcy, double gcz, double dt, double *g) {
+    double wx, wy, wz;
+    const double cost = fg_weight(x, y, z, xpx, xpy, xpz, xnx, xny, xnz, c, gcx, gcy, gcz, dt, wx, wy, wz);
+#pragma unroll 1
+    for (int s = 0; s < NS; ++s) g[s] = fg_slot(rc, frames_i, j, s, x, y, z, wx, wy, wz);
+    return cost;
 }
 
 struct SmemLayout {
@@ -610,14 +618,29 @@ __global__ void __launch_bounds__(THREADS, MINB) chomp_step_kernel(const StepArg
                     if (u != 0u && (u & pmask) == prefix) atomicAdd(&s_hist[(u >> shift) & 255u], 1);
                 }
                 __syncthreads();
-                if (tid == 0) {
-                    int acc = 0, bsel = 0;
-                    for (int bkt = 255; bkt >= 0; --bkt) {
-                        if (acc + s_hist[bkt] >= remaining) { bsel = bkt; break; }
-                        acc += s_hist[bkt];
+                if (warp == 0) {   // descending scan of the 256 buckets: 8 per lane
+                    int loc[8], sum = 0;
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) { loc[q] = s_hist[255 - (lane * 8 + q)]; sum += loc[q]; }
+                    int incl = sum;
+#pragma unroll
+                    for (int off = 1; off < 32; off <<= 1) {
+                        const int t = __shfl_up_sync(0xffffffffu, incl, off);
+                        if (lane >= off) incl += t;
                     }
-                    s_hist[256] = bsel;
-                    s_hist[257] = remaining - acc;
+                    const int excl = incl - sum;
+                    if (excl < remaining && incl >= remaining) {
+                        int acc = excl;
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) {
+                            if (acc + loc[q] >= remaining) {
+                                s_hist[256] = 255 - (lane * 8 + q);
+                                s_hist[257] = remaining - acc;
+                                break;
+                            }
+                            acc += loc[q];
+                        }
+                    }
                 }
                 __syncthreads();
                 prefix |= ((uint32_t)s_hist[256]) << shift;
@@ -654,12 +677,18 @@ __global__ void __launch_bounds__(THREADS, MINB) chomp_step_kernel(const StepArg
         for (int k = tid; k < n_li * NS; k += nthr) s_lg[k] = 0.0;
         __syncthreads();
         OMGB_PROF(7);
-        // ---- phase 4b: one winner per (waypoint, link) (SURVEY A-1) ----------------------------------
-        for (int idx = tid; idx < n_act; idx += nthr) {
-            const int li = s_act[idx];
-            const int i = li / NL, j = li - i * NL;
-            const float bv = s_best[li];
-            if (j < jmax && bv > 0.0f && __float_as_uint(bv) >= tau) {
+        // ---- phase 4b: one winner per (waypoint, link) (SURVEY A-1); 8 lanes per winner: the 7 trilinear samples
+        // of the operator and the 8 gradient slots are spread over the group ------------------------------------
+        {
+            const int grp = lane >> 3, l8 = lane & 7;
+            const unsigned gm8 = 0xffu << (grp * 8);
+            for (int base = warp * 4; base < n_act; base += nwarps * 4) {
+                const int idx = base + grp;
+                const int li = s_act[idx < n_act ? idx : n_act - 1];
+                const int i = li / NL, j = li - i * NL;
+                const float bv = s_best[li];
+                const bool win = (idx < n_act) && (j < jmax) && (bv > 0.0f) && (__float_as_uint(bv) >= tau);
+                if (!win) continue;   // uniform within the 8-lane group
                 const int p = s_bestp[li];
                 const double *F = s_frames + (size_t)li * 12;
                 const double *Fp = (i > 0) ? (F - NL * 12) : (s_frames + ((size_t)n * NL + j) * 12);
@@ -675,9 +704,9 @@ __global__ void __launch_bounds__(THREADS, MINB) chomp_step_kernel(const StepArg
                 while (m) {
                     const int o = __ffsll((long long)m) - 1;
                     m &= m - 1;
-                    float po, ax, ay, az, co;
                     if (use_dil && far_pair(s_objs[o], a.dil, o, x, y, z)) continue;
-                    pair_full(s_objs[o], a.grids, x, y, z, po, ax, ay, az, co);
+                    float po, ax, ay, az, co;
+                    pair_full_group8(s_objs[o], a.grids, gm8, l8, x, y, z, po, ax, ay, az, co);
                     pot = __fadd_rn(pot, po);
                     gx = __fadd_rn(gx, ax); gy = __fadd_rn(gy, ay); gz = __fadd_rn(gz, az);
                 }
@@ -685,11 +714,9 @@ __global__ void __launch_bounds__(THREADS, MINB) chomp_step_kernel(const StepArg
                     pot = __fmul_rn(pot, 0.1f); gx = __fmul_rn(gx, 0.1f); gy = __fmul_rn(gy, 0.1f);
                     gz = __fmul_rn(gz, 0.1f);
                 }
-                double g[NS];
-                functional_grad(rc, s_frames + (size_t)i * NL * 12, j, X, Y, Z, xp, yp, zp, xn, yn, zn, (double)pot,
-                                (double)gx, (double)gy, (double)gz, dt, g);
-#pragma unroll
-                for (int s = 0; s < NS; ++s) s_lg[(size_t)li * NS + s] = g[s];
+                double wx, wy, wz;
+                fg_weight(X, Y, Z, xp, yp, zp, xn, yn, zn, (double)pot, (double)gx, (double)gy, (double)gz, dt, wx, wy, wz);
+                s_lg[(size_t)li * NS + l8] = fg_slot(rc, s_frames + (size_t)i * NL * 12, j, l8, X, Y, Z, wx, wy, wz);
             }
         }
     } else {

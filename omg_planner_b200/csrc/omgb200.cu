@@ -576,11 +576,11 @@ static int launch_cfg(const StepArgs &a, size_t smem, cudaStream_t st) {
     return OMGB_OK;
 }
 
-static int step_config() {   // 0: 256 threads x 3 CTAs/SM, 1: 512 x 2, 2: 512 x 1, 3: 256 x 2
+static int step_config() {   // 0: 256 threads x 3 CTAs/SM, 1 (default): 512 x 2, 2: 512 x 1, 3: 256 x 2
     static int cfg = -1;
     if (cfg < 0) {
         const char *e = getenv("OMGB_STEP_CONFIG");
-        cfg = e ? atoi(e) : 0;
+        cfg = e ? atoi(e) : 1;
     }
     return cfg;
 }

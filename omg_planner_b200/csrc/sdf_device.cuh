@@ -114,25 +114,15 @@ __device__ __forceinline__ bool pair_potential(const ObjRec &o, const float *__r
     return inb;
 }
 
-// Full evaluation: potential, world-frame potential gradient, collide flag (kernel.cu:147-180).
-__device__ __forceinline__ bool pair_full(const ObjRec &o, const float *__restrict__ grids, float x, float y,
-                                          float z, float &pot, float &gx, float &gy, float &gz, float &col) {
-    float px, py, pz;
-    to_grid(o, x, y, z, px, py, pz);
-    const float *g = grids + o.grid_offset;
-    bool inb, dummy;
-    const float v = value_interp(g, o.d0, o.d1, o.d2, px, py, pz, inb);
+// Potential, world-frame potential gradient and collide flag of one pair from its seven trilinear samples
+// (value, then +x +y +z -x -y -z shifted by one voxel): kernel.cu:150-180.
+__device__ __forceinline__ void finish_pair(const ObjRec &o, float v, float fpx, float fpy, float fpz, float fmx,
+                                            float fmy, float fmz, float &pot, float &gx, float &gy, float &gz,
+                                            float &col) {
     col = (v < o.clr) ? 1.0f : 0.0f;
     pot = 0.0f; gx = gy = gz = 0.0f;
-    if (!(v <= o.eps)) return inb;    // value > eps (including the OOB 1.0 when eps < 1): kernel.cu:172-173
-    // kernel.cu:67-86: six re-interpolations, 0.5*(f+ - f-)/delta
-    const float fpx = value_interp(g, o.d0, o.d1, o.d2, __fadd_rn(px, 1.0f), py, pz, dummy);
-    const float fpy = value_interp(g, o.d0, o.d1, o.d2, px, __fadd_rn(py, 1.0f), pz, dummy);
-    const float fpz = value_interp(g, o.d0, o.d1, o.d2, px, py, __fadd_rn(pz, 1.0f), dummy);
-    const float fmx = value_interp(g, o.d0, o.d1, o.d2, __fsub_rn(px, 1.0f), py, pz, dummy);
-    const float fmy = value_interp(g, o.d0, o.d1, o.d2, px, __fsub_rn(py, 1.0f), pz, dummy);
-    const float fmz = value_interp(g, o.d0, o.d1, o.d2, px, py, __fsub_rn(pz, 1.0f), dummy);
-    const float dgx = __fdiv_rn(__fmul_rn(0.5f, __fsub_rn(fpx, fmx)), o.delta);
+    if (!(v <= o.eps)) return;        // value > eps (including the OOB 1.0 when eps < 1): kernel.cu:172-173
+    const float dgx = __fdiv_rn(__fmul_rn(0.5f, __fsub_rn(fpx, fmx)), o.delta);   // kernel.cu:82-84
     const float dgy = __fdiv_rn(__fmul_rn(0.5f, __fsub_rn(fpy, fmy)), o.delta);
     const float dgz = __fdiv_rn(__fmul_rn(0.5f, __fsub_rn(fpz, fmz)), o.delta);
     float vx, vy, vz;
@@ -150,7 +140,47 @@ __device__ __forceinline__ bool pair_full(const ObjRec &o, const float *__restri
     gx = __fmaf_rn(o.r[6], vz, __fmaf_rn(o.r[3], vy, __fmul_rn(o.r[0], vx)));
     gy = __fmaf_rn(o.r[7], vz, __fmaf_rn(o.r[4], vy, __fmul_rn(o.r[1], vx)));
     gz = __fmaf_rn(o.r[8], vz, __fmaf_rn(o.r[5], vy, __fmul_rn(o.r[2], vx)));
+}
+
+// Full evaluation by one thread: potential, world-frame potential gradient, collide flag (kernel.cu:147-180).
+__device__ __forceinline__ bool pair_full(const ObjRec &o, const float *__restrict__ grids, float x, float y,
+                                          float z, float &pot, float &gx, float &gy, float &gz, float &col) {
+    float px, py, pz;
+    to_grid(o, x, y, z, px, py, pz);
+    const float *g = grids + o.grid_offset;
+    bool inb, dummy;
+    const float v = value_interp(g, o.d0, o.d1, o.d2, px, py, pz, inb);
+    float fpx = 0.f, fpy = 0.f, fpz = 0.f, fmx = 0.f, fmy = 0.f, fmz = 0.f;
+    if (v <= o.eps) {   // kernel.cu:67-86: six re-interpolations (their result is unused when value > eps)
+        fpx = value_interp(g, o.d0, o.d1, o.d2, __fadd_rn(px, 1.0f), py, pz, dummy);
+        fpy = value_interp(g, o.d0, o.d1, o.d2, px, __fadd_rn(py, 1.0f), pz, dummy);
+        fpz = value_interp(g, o.d0, o.d1, o.d2, px, py, __fadd_rn(pz, 1.0f), dummy);
+        fmx = value_interp(g, o.d0, o.d1, o.d2, __fsub_rn(px, 1.0f), py, pz, dummy);
+        fmy = value_interp(g, o.d0, o.d1, o.d2, px, __fsub_rn(py, 1.0f), pz, dummy);
+        fmz = value_interp(g, o.d0, o.d1, o.d2, px, py, __fsub_rn(pz, 1.0f), dummy);
+    }
+    finish_pair(o, v, fpx, fpy, fpz, fmx, fmy, fmz, pot, gx, gy, gz, col);
     return inb;
+}
+
+// The same evaluation spread over a group of 8 lanes (gm = the group's lane mask, l = lane within the group):
+// lane l < 7 takes sample l, the values are exchanged with shuffles and every lane finishes redundantly.
+__device__ __forceinline__ void pair_full_group8(const ObjRec &o, const float *__restrict__ grids, unsigned gm, int l,
+                                                 float x, float y, float z, float &pot, float &gx, float &gy,
+                                                 float &gz, float &col) {
+    float px, py, pz;
+    to_grid(o, x, y, z, px, py, pz);
+    const float sx = (l == 1) ? 1.0f : ((l == 4) ? -1.0f : 0.0f);
+    const float sy = (l == 2) ? 1.0f : ((l == 5) ? -1.0f : 0.0f);
+    const float sz = (l == 3) ? 1.0f : ((l == 6) ? -1.0f : 0.0f);
+    bool inb;
+    // p + 1 and p - 1 are single roundings either way (float3 operator+/- of kernel.cu:20-28)
+    const float v = value_interp(grids + o.grid_offset, o.d0, o.d1, o.d2, __fadd_rn(px, sx), __fadd_rn(py, sy),
+                                 __fadd_rn(pz, sz), inb);
+    const float v0 = __shfl_sync(gm, v, 0, 8), fpx = __shfl_sync(gm, v, 1, 8), fpy = __shfl_sync(gm, v, 2, 8),
+                fpz = __shfl_sync(gm, v, 3, 8), fmx = __shfl_sync(gm, v, 4, 8), fmy = __shfl_sync(gm, v, 5, 8),
+                fmz = __shfl_sync(gm, v, 6, 8);
+    finish_pair(o, v0, fpx, fpy, fpz, fmx, fmy, fmz, pot, gx, gy, gz, col);
 }
 
 }  // namespace omgb
