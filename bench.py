@@ -64,6 +64,7 @@ def run_cpu(a, scene, mode, sample, steps, warmup):
     from omg_planner_b200.robot import PandaConstants
 
     cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    sample = max(sample, cores)   # every host core gets at least one trajectory
     cores = max(1, min(cores, sample))
     robot = PandaConstants()
     xi, st, en, tails = S.make_trajectories(sample, a.waypoints, robot.joint_lower_limit, robot.joint_upper_limit, seed=0)
