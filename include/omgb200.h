@@ -123,7 +123,7 @@ int omgb_scene_set_objects(omgb_scene_t *scene, const float *pose_inv, const flo
 int omgb_scene_set_metric(omgb_scene_t *scene, int n_waypoints, const double *h_Ainv, int constraint_rows,
                           const double *h_proj);
 
-/* Diagnostic: when d_phase_clocks (DEVICE int64 [B,12]) is non-NULL every CTA of the fused step writes clock64()
+/* Diagnostic: when d_phase_clocks (DEVICE int64 [B,16]) is non-NULL every CTA of the fused step writes clock64()
  * at its phase boundaries (profiles/ phase breakdowns); NULL (default) disables it. */
 int omgb_scene_set_profile(omgb_scene_t *scene, long long *d_phase_clocks);
 

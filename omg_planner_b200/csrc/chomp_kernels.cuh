@@ -68,7 +68,9 @@ struct StepArgs {
     float *dbg_pot;          // [B,n,10,p] or null
     float *dbg_pts;          // [B,n,10,p,3] or null
     double *row_obs;         // [B,n] or null: obstacle cost per waypoint row (obs_cost.sum(-1)); zeroed by the caller
-    long long *prof;         // [B,12] or null: clock64() at phase boundaries (diagnostic)
+    const int *order;        // [B] or null: CTA -> trajectory map (longest-first scheduling hint; never changes results)
+    int *cta_cost;           // [B] or null: clocks this trajectory's CTA took (feeds the next launch's order)
+    long long *prof;         // [B,16] or null: clock64() at phase boundaries (diagnostic)
     DilDesc dil;
     int num_objects;
     int batch;
@@ -349,10 +351,13 @@ __device__ __forceinline__ bool far_pair(const ObjRec &ob, const DilDesc &dd, in
 template <int LPI, int THREADS, int MINB>
 __global__ void __launch_bounds__(THREADS, MINB) chomp_step_kernel(const StepArgs a) {
     extern __shared__ __align__(16) unsigned char smem[];
-    const int b = blockIdx.x;
-    if (b >= a.batch) return;
-    if (a.active && !a.active[b]) return;
-    if (a.done && a.done[b]) return;
+    if ((int)blockIdx.x >= a.batch) return;
+    const int b = a.order ? a.order[blockIdx.x] : (int)blockIdx.x;
+    if ((a.active && !a.active[b]) || (a.done && a.done[b])) {
+        if (a.cta_cost && threadIdx.x == 0) a.cta_cost[b] = 0;
+        return;
+    }
+    const long long t_begin = clock64();
 
     const omgb_step_params_t &prm = a.prm;
     const int n = prm.n_waypoints, c = prm.constraint_rows;
@@ -387,7 +392,7 @@ __global__ void __launch_bounds__(THREADS, MINB) chomp_step_kernel(const StepArg
     const bool goal_set = prm.goal_set_proj != 0;
     const int n_li = n * NL;
 
-#define OMGB_PROF(slot) do { if (a.prof && tid == 0) a.prof[(size_t)b * 12 + (slot)] = clock64(); } while (0)
+#define OMGB_PROF(slot) do { if (a.prof && tid == 0) a.prof[(size_t)b * 16 + (slot)] = clock64(); } while (0)
     OMGB_PROF(0);
     // ---- phase 0: stage ---------------------------------------------------------------------------
     double *g_xi = a.xi + (size_t)b * n * ND;
@@ -504,7 +509,7 @@ __global__ void __launch_bounds__(THREADS, MINB) chomp_step_kernel(const StepArg
     const int sub = lane / LPI, pl = lane % LPI;  // which instance of the warp, which body point
     const unsigned gmask = (LPI == 32) ? 0xffffffffu : (0xffffu << (sub * 16));
     const bool finger_soft = (prm.uncheck_finger_collision == -1);
-    int t_nnz = 0, t_col = 0;
+    int t_nnz = 0, t_col = 0, t_exact = 0;
     double t_cost = 0.0;
     for (int base = warp * GPW; base < n_act; base += nwarps * GPW) {
         const int idx = base + sub;
@@ -528,6 +533,7 @@ __global__ void __launch_bounds__(THREADS, MINB) chomp_step_kernel(const StepArg
                 t_pin += 1;
                 continue;
             }
+            t_exact += 1;
             if (topk_mode) {
                 inb = pair_potential(s_objs[o], a.grids, x, y, z, po, co);
             } else {
@@ -599,6 +605,11 @@ __global__ void __launch_bounds__(THREADS, MINB) chomp_step_kernel(const StepArg
     OMGB_PROF(5);
     double red4[4] = {(double)t_nnz, (double)t_pin, (double)t_col, t_cost};
     block_sum_n<4>(red4, s_red);
+    if (a.prof) {   // diagnostic: exact operator evaluations in the points phase
+        double ex[1] = {(double)t_exact};
+        block_sum_n<1>(ex, s_red);
+        if (tid == 0) a.prof[(size_t)b * 16 + 12] = (long long)(ex[0] + 0.5);
+    }
     const int nnz = (int)(red4[0] + 0.5), p_in = (int)(red4[1] + 0.5), collide = (int)(red4[2] + 0.5);
 
     double obs_sum = 0.0;
@@ -888,6 +899,7 @@ __global__ void __launch_bounds__(THREADS, MINB) chomp_step_kernel(const StepArg
         inf[OMGB_INFO_LIMIT_ROUNDS] = (double)limit_rounds;
         inf[OMGB_INFO_RESERVED] = (double)n_act;   // link instances that survived the cull (diagnostic)
         if (a.done && a.stop_on_terminate && terminate && a.iteration > 0) a.done[b] = 1;
+        if (a.cta_cost) a.cta_cost[b] = (int)min((long long)0x7fffffff, clock64() - t_begin);
     }
 }
 

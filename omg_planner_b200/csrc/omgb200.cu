@@ -170,6 +170,28 @@ __global__ void active_bounds_final_kernel(const int *__restrict__ bounds, ObjRe
     if (bounds[6 * o + 3] < 0) { r.alox = r.aloy = r.aloz = 1e30f; r.ahix = r.ahiy = r.ahiz = -1e30f; }
 }
 
+// Longest-processing-time-first CTA order for the next launch: 64-bucket counting sort of the per-trajectory
+// CTA clocks of the previous launch, descending.  A scheduling hint only (trajectories are independent).
+__global__ void lpt_order_kernel(const int *__restrict__ cost, int *__restrict__ order, int batch) {
+    __shared__ int hist[64], base[64], cmax;
+    if (threadIdx.x < 64) hist[threadIdx.x] = 0;
+    if (threadIdx.x == 0) cmax = 1;
+    __syncthreads();
+    int m = 1;
+    for (int b = threadIdx.x; b < batch; b += blockDim.x) m = max(m, cost[b]);
+    atomicMax(&cmax, m);
+    __syncthreads();
+    const float scale = 63.999f / (float)cmax;
+    for (int b = threadIdx.x; b < batch; b += blockDim.x) atomicAdd(&hist[63 - (int)(cost[b] * scale)], 1);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int acc = 0;
+        for (int k = 0; k < 64; ++k) { base[k] = acc; acc += hist[k]; }
+    }
+    __syncthreads();
+    for (int b = threadIdx.x; b < batch; b += blockDim.x) order[atomicAdd(&base[63 - (int)(cost[b] * scale)], 1)] = b;
+}
+
 // ----------------------------------------------------------------------------------------------------
 // raw operator: drop-in for omg_cuda.sdf_loss_forward (one thread per point, objects in ascending order)
 // ----------------------------------------------------------------------------------------------------
@@ -313,6 +335,11 @@ struct omgb_scene {
     float *d_dil = nullptr;
     DilDesc dil;
     int *d_bounds = nullptr;
+    // longest-first CTA scheduling state (hint only)
+    int *d_order = nullptr, *d_cost = nullptr;
+    int order_cap = 0, order_batch = -1;
+    const void *order_key = nullptr;
+    bool order_valid = false;
     long long *d_prof = nullptr;   // diagnostic: per-CTA phase clocks (omgb_scene_set_profile)
     double *d_stage = nullptr;
     size_t stage_bytes = 0;
@@ -339,7 +366,7 @@ extern "C" int omgb_scene_destroy(omgb_scene_t *s) {
     if (!s) return OMGB_OK;
     cudaSetDevice(s->device);
     cudaFree(s->d_robot); cudaFree(s->d_limits); cudaFree(s->d_objparams); cudaFree(s->d_objs);
-    cudaFree(s->d_Ainv); cudaFree(s->d_proj); cudaFree(s->d_stage); cudaFree(s->d_dil); cudaFree(s->d_bounds);
+    cudaFree(s->d_Ainv); cudaFree(s->d_proj); cudaFree(s->d_stage); cudaFree(s->d_dil); cudaFree(s->d_bounds); cudaFree(s->d_order); cudaFree(s->d_cost);
     delete s;
     return OMGB_OK;
 }
@@ -576,7 +603,7 @@ static int launch_cfg(const StepArgs &a, size_t smem, cudaStream_t st) {
     return OMGB_OK;
 }
 
-static int step_config() {   // 0: 256 threads x 3 CTAs/SM, 1 (default): 512 x 2, 2: 512 x 1, 3: 256 x 2
+static int step_config() {   // 0: 256 threads x 3 CTAs/SM, 1 (default): 512 x 2, 2: 512 x 1, 3: 256 x 2, 4: 384 x 2, 5: 320 x 3
     static int cfg = -1;
     if (cfg < 0) {
         const char *e = getenv("OMGB_STEP_CONFIG");
@@ -585,27 +612,58 @@ static int step_config() {   // 0: 256 threads x 3 CTAs/SM, 1 (default): 512 x 2
     return cfg;
 }
 
-static int launch_step(omgb_scene *s, const StepArgs &a, cudaStream_t st) {
+static int launch_step(omgb_scene *s, const StepArgs &a_in, cudaStream_t st) {
+    const StepArgs &a0 = a_in;
     const int lpi = s->p <= 16 ? 16 : 32;
-    const SmemLayout L = make_layout(a.prm.n_waypoints, a.prm.constraint_rows, lpi, s->num_objects, s->p);
+    const SmemLayout L = make_layout(a0.prm.n_waypoints, a0.prm.constraint_rows, lpi, s->num_objects, s->p);
     if (L.total > (size_t)s->smem_optin)
         return fail(OMGB_ERR_UNSUPPORTED, "trajectory too long for one CTA's shared memory");
-    if (a.batch == 0) return OMGB_OK;
+    if (a0.batch == 0) return OMGB_OK;
+    // longest-first order from the previous launch on the same batch (same xi buffer and size)
+    StepArgs a = a_in;
+    static int use_lpt = -1;
+    if (use_lpt < 0) { const char *e = getenv("OMGB_NO_LPT"); use_lpt = (e && atoi(e)) ? 0 : 1; }
+    if (use_lpt && a.batch >= 2 * 148) {
+        if (a.batch > s->order_cap) {
+            cudaFree(s->d_order); cudaFree(s->d_cost);
+            s->d_order = s->d_cost = nullptr; s->order_cap = 0;
+            OMGB_CUDA(cudaMalloc(&s->d_order, sizeof(int) * a.batch));
+            OMGB_CUDA(cudaMalloc(&s->d_cost, sizeof(int) * a.batch));
+            s->order_cap = a.batch;
+            s->order_valid = false;
+        }
+        if (s->order_batch != a.batch || s->order_key != (const void *)a.xi) s->order_valid = false;
+        a.order = s->order_valid ? s->d_order : nullptr;
+        a.cta_cost = s->d_cost;
+    }
     const int cfg = step_config();
+    int rc_ = OMGB_OK;
     if (lpi == 16) {
         switch (cfg) {
-            case 1: return launch_cfg<16, 512, 2>(a, L.total, st);
-            case 2: return launch_cfg<16, 512, 1>(a, L.total, st);
-            case 3: return launch_cfg<16, 256, 2>(a, L.total, st);
-            default: return launch_cfg<16, 256, 3>(a, L.total, st);
+            case 0: rc_ = launch_cfg<16, 256, 3>(a, L.total, st); break;
+            case 2: rc_ = launch_cfg<16, 512, 1>(a, L.total, st); break;
+            case 3: rc_ = launch_cfg<16, 256, 2>(a, L.total, st); break;
+            case 4: rc_ = launch_cfg<16, 384, 2>(a, L.total, st); break;
+            case 5: rc_ = launch_cfg<16, 320, 3>(a, L.total, st); break;
+            default: rc_ = launch_cfg<16, 512, 2>(a, L.total, st); break;
+        }
+    } else {
+        switch (cfg) {
+            case 0: rc_ = launch_cfg<32, 256, 3>(a, L.total, st); break;
+            case 2: rc_ = launch_cfg<32, 512, 1>(a, L.total, st); break;
+            case 3: rc_ = launch_cfg<32, 256, 2>(a, L.total, st); break;
+            default: rc_ = launch_cfg<32, 512, 2>(a, L.total, st); break;
         }
     }
-    switch (cfg) {
-        case 1: return launch_cfg<32, 512, 2>(a, L.total, st);
-        case 2: return launch_cfg<32, 512, 1>(a, L.total, st);
-        case 3: return launch_cfg<32, 256, 2>(a, L.total, st);
-        default: return launch_cfg<32, 256, 3>(a, L.total, st);
+    if (rc_) return rc_;
+    if (a.cta_cost) {
+        lpt_order_kernel<<<1, 1024, 0, st>>>(s->d_cost, s->d_order, a.batch);
+        OMGB_CUDA(cudaGetLastError());
+        s->order_valid = true;
+        s->order_batch = a.batch;
+        s->order_key = (const void *)a.xi;
     }
+    return OMGB_OK;
 }
 
 static StepArgs make_args(const omgb_scene *s, const omgb_step_params_t *prm, int batch, double *xi,

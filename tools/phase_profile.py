@@ -28,7 +28,7 @@ def main():
     xi, st, en, tails = S.make_trajectories(B, 30, robot.joint_lower_limit, robot.joint_upper_limit, seed=0)
     dev = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
     x, s, e, t = dev(xi), dev(st), dev(en), dev(tails)
-    prof = torch.zeros((B, 12), dtype=torch.int64, device="cuda")
+    prof = torch.zeros((B, 16), dtype=torch.int64, device="cuda")
     for it in range(8):
         cfg.obstacle_weight, cfg.smoothness_weight, cfg.step_size = cfg.schedule(it + 1)
         if it == 7:
@@ -36,6 +36,8 @@ def main():
         out = eng.step(cfg, x, s, e, t)
     torch.cuda.synchronize()
     p = prof.cpu().numpy().astype(np.float64)
+    exact = p[:, 12].copy()
+    p = p[:, :12]
     d = np.diff(p, axis=1)
     info = out["info"].cpu().numpy()
     lines = ["mode %s; per-CTA cycles (mean / median / max over %d CTAs)" % (mode, B)]
@@ -44,6 +46,7 @@ def main():
         lines.append("%-14s mean %9.0f  median %9.0f  max %9.0f  share %.3f" % (
             name, d[:, k].mean(), np.median(d[:, k]), d[:, k].max(), d[:, k].sum() / tot.sum()))
     lines.append("total          mean %9.0f  median %9.0f  max %9.0f" % (tot.mean(), np.median(tot), tot.max()))
+    lines.append("exact operator evaluations in the points phase: mean %.1f max %.0f per trajectory" % (exact.mean(), exact.max()))
     lines.append("P_in mean %.1f  nnz mean %.1f  active link instances mean %.1f / 300  limit rounds mean %.2f" % (
         info[:, 12].mean(), info[:, 13].mean(), info[:, 15].mean(), info[:, 14].mean()))
     txt = "\n".join(lines)
