@@ -51,6 +51,45 @@ struct DilDesc {
     int enabled;
 };
 
+struct SmemLayout {
+    unsigned off_xi, off_start, off_end, off_goal, off_frames, off_lg, off_grad, off_u, off_viol, off_red, off_pts,
+        off_mask, off_best, off_bestp, off_act, off_objs, off_hist, total;
+};
+
+__host__ __device__ inline unsigned align_up(unsigned v, unsigned a) { return (v + a - 1) / a * a; }
+
+__host__ __device__ inline SmemLayout make_layout(int n, int c, int lpi, int nobj, int p) {
+    SmemLayout L;
+    unsigned o = 0;
+    L.off_xi = o; o += sizeof(double) * n * ND;
+    L.off_start = o; o += sizeof(double) * ND;
+    L.off_end = o; o += sizeof(double) * ND;
+    L.off_goal = o; o += sizeof(double) * (c > 0 ? c : 1) * ND;
+    L.off_frames = o; o += sizeof(double) * (n + 2) * NL * 12;
+    // link gradients [n*10][8] fp64; aliased with (a) the sin/cos table of the FK phase and (b) the fp32
+    // potential array [n*10][lpi] of the top-k path
+    unsigned lg = sizeof(double) * n * NL * NS, pot = sizeof(float) * n * NL * lpi, sc = sizeof(double2) * (n + 2) * 7;
+    unsigned u = lg > pot ? lg : pot;
+    u = u > sc ? u : sc;
+    o = align_up(o, 16);   // double2 sin/cos table
+    L.off_lg = o; o += align_up(u, 16);
+    L.off_grad = o; o += sizeof(double) * n * ND;
+    L.off_u = o; o += sizeof(double) * n * ND;
+    L.off_viol = o; o += sizeof(double) * n * ND;
+    L.off_red = o; o += sizeof(double) * (33 * 8);
+    L.off_pts = o;   // (body points are read from global memory)
+    L.off_mask = o; o += sizeof(unsigned long long) * n * NL;
+    L.off_best = o; o += sizeof(float) * n * NL;
+    L.off_bestp = o; o += sizeof(int) * n * NL;
+    L.off_act = o; o += sizeof(int) * (n * NL + 40);
+    o = align_up(o, 16);
+    L.off_objs = o; o += sizeof(ObjRec) * nobj;
+    L.off_hist = o; o += sizeof(int) * 264;
+    L.total = align_up(o, 16);
+    (void)p;
+    return L;
+}
+
 struct StepArgs {
     const ObjRec *objs;
     const float *grids;
@@ -72,6 +111,7 @@ struct StepArgs {
     int *cta_cost;           // [B] or null: clocks this trajectory's CTA took (feeds the next launch's order)
     long long *prof;         // [B,16] or null: clock64() at phase boundaries (diagnostic)
     DilDesc dil;
+    SmemLayout lay;          // computed on the host (make_layout)
     int num_objects;
     int batch;
     int iteration;           // index inside a plan (for the t > 0 rule of planner.py:627)
@@ -289,44 +329,6 @@ __device__ __forceinline__ double functional_grad(const RobotConst *__restrict__
     return cost;
 }
 
-struct SmemLayout {
-    size_t off_xi, off_start, off_end, off_goal, off_frames, off_lg, off_grad, off_u, off_viol, off_red, off_pts,
-        off_mask, off_best, off_bestp, off_act, off_objs, off_hist, total;
-};
-
-__host__ __device__ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
-
-__host__ __device__ inline SmemLayout make_layout(int n, int c, int lpi, int nobj, int p) {
-    SmemLayout L;
-    size_t o = 0;
-    L.off_xi = o; o += sizeof(double) * n * ND;
-    L.off_start = o; o += sizeof(double) * ND;
-    L.off_end = o; o += sizeof(double) * ND;
-    L.off_goal = o; o += sizeof(double) * (c > 0 ? c : 1) * ND;
-    L.off_frames = o; o += sizeof(double) * (n + 2) * NL * 12;
-    // link gradients [n*10][8] fp64; aliased with (a) the sin/cos table of the FK phase and (b) the fp32
-    // potential array [n*10][lpi] of the top-k path
-    size_t lg = sizeof(double) * n * NL * NS, pot = sizeof(float) * n * NL * lpi, sc = sizeof(double2) * (n + 2) * 7;
-    size_t u = lg > pot ? lg : pot;
-    u = u > sc ? u : sc;
-    o = align_up(o, 16);   // double2 sin/cos table
-    L.off_lg = o; o += align_up(u, 16);
-    L.off_grad = o; o += sizeof(double) * n * ND;
-    L.off_u = o; o += sizeof(double) * n * ND;
-    L.off_viol = o; o += sizeof(double) * n * ND;
-    L.off_red = o; o += sizeof(double) * (33 * 8);
-    L.off_pts = o; o += sizeof(double) * NL * p * 3;
-    L.off_mask = o; o += sizeof(unsigned long long) * n * NL;
-    L.off_best = o; o += sizeof(float) * n * NL;
-    L.off_bestp = o; o += sizeof(int) * n * NL;
-    L.off_act = o; o += sizeof(int) * (n * NL + 40);
-    o = align_up(o, 16);
-    L.off_objs = o; o += sizeof(ObjRec) * nobj;
-    L.off_hist = o; o += sizeof(int) * 264;
-    L.total = align_up(o, 16);
-    return L;
-}
-
 // True when the lower-bound grid proves that the sample of object `ob` at world point (x,y,z) is > eps and
 // >= clearance (so the pair contributes nothing) AND that its 8-tap cell is in bounds (so it counts in P_in).
 // Approximate (matrix-form, division-free) grid coordinates are enough: the 6^3 region and the 1.5-voxel
@@ -348,7 +350,7 @@ __device__ __forceinline__ bool far_pair(const ObjRec &ob, const DilDesc &dd, in
 // ----------------------------------------------------------------------------------------------------
 // the fused iteration
 // ----------------------------------------------------------------------------------------------------
-template <int LPI, int THREADS, int MINB>
+template <int LPI, int THREADS, int MINB, bool TOPK>
 __global__ void __launch_bounds__(THREADS, MINB) chomp_step_kernel(const StepArgs a) {
     extern __shared__ __align__(16) unsigned char smem[];
     if ((int)blockIdx.x >= a.batch) return;
@@ -364,7 +366,7 @@ __global__ void __launch_bounds__(THREADS, MINB) chomp_step_kernel(const StepArg
     const RobotConst *__restrict__ rc = a.robot;
     const int P = rc->p;
     const int O = a.num_objects;
-    const SmemLayout L = make_layout(n, c, LPI, O, P);
+    const SmemLayout &L = a.lay;
     double *s_xi = reinterpret_cast<double *>(smem + L.off_xi);
     double *s_start = reinterpret_cast<double *>(smem + L.off_start);
     double *s_end = reinterpret_cast<double *>(smem + L.off_end);
@@ -377,7 +379,6 @@ __global__ void __launch_bounds__(THREADS, MINB) chomp_step_kernel(const StepArg
     double *s_u = reinterpret_cast<double *>(smem + L.off_u);
     double *s_viol = reinterpret_cast<double *>(smem + L.off_viol);
     double *s_red = reinterpret_cast<double *>(smem + L.off_red);
-    double *s_pts = reinterpret_cast<double *>(smem + L.off_pts);
     unsigned long long *s_mask = reinterpret_cast<unsigned long long *>(smem + L.off_mask);
     float *s_best = reinterpret_cast<float *>(smem + L.off_best);
     int *s_bestp = reinterpret_cast<int *>(smem + L.off_bestp);
@@ -388,7 +389,7 @@ __global__ void __launch_bounds__(THREADS, MINB) chomp_step_kernel(const StepArg
     const int tid = threadIdx.x, nthr = blockDim.x;
     const int lane = tid & 31, warp = tid >> 5, nwarps = nthr >> 5;
     const double dt = prm.time_interval;
-    const bool topk_mode = prm.top_k_collision > 0;
+    constexpr bool topk_mode = TOPK;   // prm.top_k_collision > 0
     const bool goal_set = prm.goal_set_proj != 0;
     const int n_li = n * NL;
 
@@ -407,10 +408,6 @@ __global__ void __launch_bounds__(THREADS, MINB) chomp_step_kernel(const StepArg
         const uint32_t *src = reinterpret_cast<const uint32_t *>(a.objs);
         uint32_t *dst = reinterpret_cast<uint32_t *>(s_objs);
         for (int k = tid; k < words; k += nthr) dst[k] = src[k];
-    }
-    for (int k = tid; k < NL * P * 3; k += nthr) {
-        const int j = k / (P * 3), r = k - j * P * 3;
-        s_pts[k] = rc->pts[j][r / 3][r % 3];
     }
     for (int k = tid; k < n_li; k += nthr) { s_best[k] = 0.0f; s_bestp[k] = 0; }
     __syncthreads();
@@ -518,7 +515,7 @@ __global__ void __launch_bounds__(THREADS, MINB) chomp_step_kernel(const StepArg
         const bool live = have && (pl < P);
         const int i = li / NL, j = li - i * NL;
         const double *F = s_frames + (size_t)li * 12;
-        const double *bp = s_pts + ((size_t)j * P + (pl < P ? pl : 0)) * 3;
+        const double *bp = rc->pts[j][pl < P ? pl : 0];
         double X, Y, Z;
         xform(F, bp[0], bp[1], bp[2], X, Y, Z);
         const float x = (float)X, y = (float)Y, z = (float)Z;   // omg/cost.py:136 .float()
@@ -673,7 +670,7 @@ __global__ void __launch_bounds__(THREADS, MINB) chomp_step_kernel(const StepArg
                 if (p < P && j < jmax && pv > 0.0f && __float_as_uint(pv) >= tau) {
                     const double *F = s_frames + (size_t)li * 12;
                     const double *Fp = (i > 0) ? (F - NL * 12) : (s_frames + ((size_t)n * NL + j) * 12);
-                    const double *bp = s_pts + ((size_t)j * P + p) * 3;
+                    const double *bp = rc->pts[j][p];
                     double X, Y, Z, xp, yp, zp;
                     xform(F, bp[0], bp[1], bp[2], X, Y, Z);
                     xform(Fp, bp[0], bp[1], bp[2], xp, yp, zp);
@@ -704,7 +701,7 @@ __global__ void __launch_bounds__(THREADS, MINB) chomp_step_kernel(const StepArg
                 const double *F = s_frames + (size_t)li * 12;
                 const double *Fp = (i > 0) ? (F - NL * 12) : (s_frames + ((size_t)n * NL + j) * 12);
                 const double *Fn = (i < n - 1) ? (F + NL * 12) : (s_frames + ((size_t)(n + 1) * NL + j) * 12);
-                const double *bp = s_pts + ((size_t)j * P + p) * 3;
+                const double *bp = rc->pts[j][p];
                 double X, Y, Z, xp, yp, zp, xn, yn, zn;
                 xform(F, bp[0], bp[1], bp[2], X, Y, Z);
                 xform(Fp, bp[0], bp[1], bp[2], xp, yp, zp);

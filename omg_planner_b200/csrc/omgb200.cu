@@ -596,18 +596,24 @@ static int check_step(const omgb_scene *s, const omgb_step_params_t *prm, int ba
 
 template <int LPI, int THREADS, int MINB>
 static int launch_cfg(const StepArgs &a, size_t smem, cudaStream_t st) {
-    OMGB_CUDA(cudaFuncSetAttribute(chomp_step_kernel<LPI, THREADS, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   (int)smem));
-    chomp_step_kernel<LPI, THREADS, MINB><<<a.batch, THREADS, smem, st>>>(a);
+    if (a.prm.top_k_collision > 0) {
+        OMGB_CUDA(cudaFuncSetAttribute(chomp_step_kernel<LPI, THREADS, MINB, true>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        chomp_step_kernel<LPI, THREADS, MINB, true><<<a.batch, THREADS, smem, st>>>(a);
+    } else {
+        OMGB_CUDA(cudaFuncSetAttribute(chomp_step_kernel<LPI, THREADS, MINB, false>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        chomp_step_kernel<LPI, THREADS, MINB, false><<<a.batch, THREADS, smem, st>>>(a);
+    }
     OMGB_CUDA(cudaGetLastError());
     return OMGB_OK;
 }
 
-static int step_config() {   // 0: 256 threads x 3 CTAs/SM, 1 (default): 512 x 2, 2: 512 x 1, 3: 256 x 2, 4: 384 x 2, 5: 320 x 3
+static int step_config() {   // 0: 256 threads x 3 CTAs/SM, 1: 512 x 2, 2: 512 x 1, 3: 256 x 2, 4 (default): 384 x 2, 5: 320 x 3
     static int cfg = -1;
     if (cfg < 0) {
         const char *e = getenv("OMGB_STEP_CONFIG");
-        cfg = e ? atoi(e) : 1;
+        cfg = e ? atoi(e) : 4;
     }
     return cfg;
 }
@@ -621,6 +627,7 @@ static int launch_step(omgb_scene *s, const StepArgs &a_in, cudaStream_t st) {
     if (a0.batch == 0) return OMGB_OK;
     // longest-first order from the previous launch on the same batch (same xi buffer and size)
     StepArgs a = a_in;
+    a.lay = L;
     static int use_lpt = -1;
     if (use_lpt < 0) { const char *e = getenv("OMGB_NO_LPT"); use_lpt = (e && atoi(e)) ? 0 : 1; }
     if (use_lpt && a.batch >= 2 * 148) {
@@ -643,9 +650,9 @@ static int launch_step(omgb_scene *s, const StepArgs &a_in, cudaStream_t st) {
             case 0: rc_ = launch_cfg<16, 256, 3>(a, L.total, st); break;
             case 2: rc_ = launch_cfg<16, 512, 1>(a, L.total, st); break;
             case 3: rc_ = launch_cfg<16, 256, 2>(a, L.total, st); break;
-            case 4: rc_ = launch_cfg<16, 384, 2>(a, L.total, st); break;
             case 5: rc_ = launch_cfg<16, 320, 3>(a, L.total, st); break;
-            default: rc_ = launch_cfg<16, 512, 2>(a, L.total, st); break;
+            case 1: rc_ = launch_cfg<16, 512, 2>(a, L.total, st); break;
+            default: rc_ = launch_cfg<16, 384, 2>(a, L.total, st); break;
         }
     } else {
         switch (cfg) {
