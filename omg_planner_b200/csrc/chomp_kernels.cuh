@@ -73,9 +73,10 @@ __host__ __device__ inline SmemLayout make_layout(int n, int c, int lpi, int nob
     u = u > sc ? u : sc;
     o = align_up(o, 16);   // double2 sin/cos table
     L.off_lg = o; o += align_up(u, 16);
-    L.off_grad = o; o += sizeof(double) * n * ND;
-    L.off_u = o; o += sizeof(double) * n * ND;
-    L.off_viol = o; o += sizeof(double) * n * ND;
+    // grad / u / viol live in the frames region: the link frames are dead once the obstacle gradient is assembled
+    L.off_grad = L.off_frames;
+    L.off_u = L.off_grad + sizeof(double) * n * ND;
+    L.off_viol = L.off_u + sizeof(double) * n * ND;
     L.off_red = o; o += sizeof(double) * (33 * 8);
     L.off_pts = o;   // (body points are read from global memory)
     L.off_mask = o; o += sizeof(unsigned long long) * n * NL;

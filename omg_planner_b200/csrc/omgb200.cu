@@ -594,26 +594,38 @@ static int check_step(const omgb_scene *s, const omgb_step_params_t *prm, int ba
     return OMGB_OK;
 }
 
+// Shared-memory carveout (percent of 228 KB) that lets `ctas` CTAs of `smem` dynamic bytes (+1 KB reserved each)
+// be resident; whatever is left of the 256 KB array stays L1.
+static int carveout_percent(size_t smem, int ctas) {
+    const double need = (double)ctas * (double)(smem + 1024);
+    int pct = (int)(need / (228.0 * 1024.0) * 100.0) + 1;
+    return pct > 100 ? 100 : pct;
+}
+
 template <int LPI, int THREADS, int MINB>
 static int launch_cfg(const StepArgs &a, size_t smem, cudaStream_t st) {
     if (a.prm.top_k_collision > 0) {
         OMGB_CUDA(cudaFuncSetAttribute(chomp_step_kernel<LPI, THREADS, MINB, true>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        OMGB_CUDA(cudaFuncSetAttribute(chomp_step_kernel<LPI, THREADS, MINB, true>,
+                                       cudaFuncAttributePreferredSharedMemoryCarveout, carveout_percent(smem, MINB)));
         chomp_step_kernel<LPI, THREADS, MINB, true><<<a.batch, THREADS, smem, st>>>(a);
     } else {
         OMGB_CUDA(cudaFuncSetAttribute(chomp_step_kernel<LPI, THREADS, MINB, false>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        OMGB_CUDA(cudaFuncSetAttribute(chomp_step_kernel<LPI, THREADS, MINB, false>,
+                                       cudaFuncAttributePreferredSharedMemoryCarveout, carveout_percent(smem, MINB)));
         chomp_step_kernel<LPI, THREADS, MINB, false><<<a.batch, THREADS, smem, st>>>(a);
     }
     OMGB_CUDA(cudaGetLastError());
     return OMGB_OK;
 }
 
-static int step_config() {   // 0: 256 threads x 3 CTAs/SM, 1: 512 x 2, 2: 512 x 1, 3: 256 x 2, 4 (default): 384 x 2, 5: 320 x 3
+static int step_config() {   // 0: 256 threads x 3 CTAs/SM, 1: 512 x 2, 2: 512 x 1, 3: 256 x 2, 4: 384 x 2, 5 (default): 320 x 3
     static int cfg = -1;
     if (cfg < 0) {
         const char *e = getenv("OMGB_STEP_CONFIG");
-        cfg = e ? atoi(e) : 4;
+        cfg = e ? atoi(e) : 5;
     }
     return cfg;
 }
@@ -650,9 +662,9 @@ static int launch_step(omgb_scene *s, const StepArgs &a_in, cudaStream_t st) {
             case 0: rc_ = launch_cfg<16, 256, 3>(a, L.total, st); break;
             case 2: rc_ = launch_cfg<16, 512, 1>(a, L.total, st); break;
             case 3: rc_ = launch_cfg<16, 256, 2>(a, L.total, st); break;
-            case 5: rc_ = launch_cfg<16, 320, 3>(a, L.total, st); break;
             case 1: rc_ = launch_cfg<16, 512, 2>(a, L.total, st); break;
-            default: rc_ = launch_cfg<16, 384, 2>(a, L.total, st); break;
+            case 4: rc_ = launch_cfg<16, 384, 2>(a, L.total, st); break;
+            default: rc_ = launch_cfg<16, 320, 3>(a, L.total, st); break;
         }
     } else {
         switch (cfg) {
