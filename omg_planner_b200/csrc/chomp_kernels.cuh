@@ -279,8 +279,7 @@ __device__ __forceinline__ int link_slots(int j) { return j < 7 ? j + 1 : (j == 
 // i, i-1, i+1.  Returns c * |v| (the point's obstacle cost).
 __device__ __forceinline__ double fg_weight(double x, double y, double z, double xpx, double xpy, double xpz,
                                             double xnx, double xny, double xnz, double c, double gcx, double gcy,
-                                            double gcz, double dt, double &wx, double &wy, double &wz) {
-    const double idt = 1.0 / dt;
+                                            double gcz, double idt, double &wx, double &wy, double &wz) {
     const double vx = (x - xpx) * idt, vy = (y - xpy) * idt, vz = (z - xpz) * idt;
     const double idt2 = idt * idt;
     const double ax = (xpx - 2.0 * x + xnx) * idt2, ay = (xpy - 2.0 * y + xny) * idt2,
@@ -322,9 +321,9 @@ __device__ __forceinline__ double fg_slot(const RobotConst *__restrict__ rc, con
 __device__ __forceinline__ double functional_grad(const RobotConst *__restrict__ rc, const double *frames_i, int j,
                                                   double x, double y, double z, double xpx, double xpy, double xpz,
                                                   double xnx, double xny, double xnz, double c, double gcx,
-                                                  double gcy, double gcz, double dt, double *g) {
+                                                  double gcy, double gcz, double idt, double *g) {
     double wx, wy, wz;
-    const double cost = fg_weight(x, y, z, xpx, xpy, xpz, xnx, xny, xnz, c, gcx, gcy, gcz, dt, wx, wy, wz);
+    const double cost = fg_weight(x, y, z, xpx, xpy, xpz, xnx, xny, xnz, c, gcx, gcy, gcz, idt, wx, wy, wz);
 #pragma unroll 1
     for (int s = 0; s < NS; ++s) g[s] = fg_slot(rc, frames_i, j, s, x, y, z, wx, wy, wz);
     return cost;
@@ -390,6 +389,7 @@ __global__ void __launch_bounds__(THREADS, MINB) chomp_step_kernel(const StepArg
     const int tid = threadIdx.x, nthr = blockDim.x;
     const int lane = tid & 31, warp = tid >> 5, nwarps = nthr >> 5;
     const double dt = prm.time_interval;
+    const double inv_dt = 1.0 / dt, inv_dt2 = inv_dt * inv_dt;   // fp64 divisions are ~50 instructions each
     constexpr bool topk_mode = TOPK;   // prm.top_k_collision > 0
     const bool goal_set = prm.goal_set_proj != 0;
     const int n_li = n * NL;
@@ -582,7 +582,7 @@ __global__ void __launch_bounds__(THREADS, MINB) chomp_step_kernel(const StepArg
                 xform(Fp, bp[0], bp[1], bp[2], xp, yp, zp);
                 xform(Fn, bp[0], bp[1], bp[2], xn, yn, zn);
                 cst = functional_grad(rc, s_frames + (size_t)i * NL * 12, j, X, Y, Z, xp, yp, zp, xn, yn, zn,
-                                      (double)pot, (double)gx, (double)gy, (double)gz, dt, g);
+                                      (double)pot, (double)gx, (double)gy, (double)gz, inv_dt, g);
             }
             if (__ballot_sync(gmask, nz) & gmask) {   // uniform per link instance
 #pragma unroll
@@ -614,7 +614,6 @@ __global__ void __launch_bounds__(THREADS, MINB) chomp_step_kernel(const StepArg
     if (topk_mode) {
         // ---- phase 3: membership threshold = k-th largest potential (bit pattern; potentials >= 0) ----
         const int K = prm.top_k_collision;
-        const int n_slots = n_li * LPI;
         uint32_t tau = 1u;   // "pot >= tau" <=> pot > 0
         if (nnz > K) {
             uint32_t prefix = 0u, pmask = 0u;
@@ -622,8 +621,8 @@ __global__ void __launch_bounds__(THREADS, MINB) chomp_step_kernel(const StepArg
             for (int shift = 24; shift >= 0; shift -= 8) {
                 for (int k = tid; k < 256; k += nthr) s_hist[k] = 0;
                 __syncthreads();
-                for (int k = tid; k < n_slots; k += nthr) {
-                    const uint32_t u = __float_as_uint(s_pot[k]);
+                for (int k = tid; k < n_act * LPI; k += nthr) {   // inactive link instances hold zeros
+                    const uint32_t u = __float_as_uint(s_pot[(size_t)s_act[k / LPI] * LPI + (k % LPI)]);
                     if (u != 0u && (u & pmask) == prefix) atomicAdd(&s_hist[(u >> shift) & 255u], 1);
                 }
                 __syncthreads();
@@ -675,7 +674,7 @@ __global__ void __launch_bounds__(THREADS, MINB) chomp_step_kernel(const StepArg
                     double X, Y, Z, xp, yp, zp;
                     xform(F, bp[0], bp[1], bp[2], X, Y, Z);
                     xform(Fp, bp[0], bp[1], bp[2], xp, yp, zp);
-                    const double vx = (X - xp) / dt, vy = (Y - yp) / dt, vz = (Z - zp) / dt;
+                    const double vx = (X - xp) * inv_dt, vy = (Y - yp) * inv_dt, vz = (Z - zp) * inv_dt;
                     acc += (double)pv * sqrt(vx * vx + vy * vy + vz * vz);
                 }
             }
@@ -724,7 +723,7 @@ __global__ void __launch_bounds__(THREADS, MINB) chomp_step_kernel(const StepArg
                     gz = __fmul_rn(gz, 0.1f);
                 }
                 double wx, wy, wz;
-                fg_weight(X, Y, Z, xp, yp, zp, xn, yn, zn, (double)pot, (double)gx, (double)gy, (double)gz, dt, wx, wy, wz);
+                fg_weight(X, Y, Z, xp, yp, zp, xn, yn, zn, (double)pot, (double)gx, (double)gy, (double)gz, inv_dt, wx, wy, wz);
                 s_lg[(size_t)li * NS + l8] = fg_slot(rc, s_frames + (size_t)i * NL * 12, j, l8, X, Y, Z, wx, wy, wz);
             }
         }
@@ -748,8 +747,8 @@ __global__ void __launch_bounds__(THREADS, MINB) chomp_step_kernel(const StepArg
         const double xc = s_xi[k];
         const double xprev = (i > 0) ? s_xi[k - ND] : s_start[d];
         double sg;
-        if (i < n - 1) sg = (2.0 * xc - xprev - s_xi[k + ND]) / (dt * dt);
-        else sg = goal_set ? (xc - xprev) / (dt * dt) : (2.0 * xc - xprev - s_end[d]) / (dt * dt);
+        if (i < n - 1) sg = (2.0 * xc - xprev - s_xi[k + ND]) * inv_dt2;
+        else sg = goal_set ? (xc - xprev) * inv_dt2 : (2.0 * xc - xprev - s_end[d]) * inv_dt2;
         sg *= prm.link_smooth_weight[d];
         double wo = prm.obstacle_weight * og;
         wo = fmin(fmax(wo, -prm.clip_grad_scale), prm.clip_grad_scale);
@@ -765,9 +764,9 @@ __global__ void __launch_bounds__(THREADS, MINB) chomp_step_kernel(const StepArg
     for (int k = tid; k < (n + 1) * ND; k += nthr) {   // smoothness loss rows 0..n (cost.py:443-445)
         const int r = k / ND, d = k - r * ND;
         double v;
-        if (r == 0) v = (s_xi[d] - s_start[d]) / dt;
-        else if (r < n) v = (s_xi[k] - s_xi[k - ND]) / dt;
-        else v = goal_set ? 0.0 : (s_end[d] - s_xi[(n - 1) * ND + d]) / dt;
+        if (r == 0) v = (s_xi[d] - s_start[d]) * inv_dt;
+        else if (r < n) v = (s_xi[k] - s_xi[k - ND]) * inv_dt;
+        else v = goal_set ? 0.0 : (s_end[d] - s_xi[(n - 1) * ND + d]) * inv_dt;
         v *= prm.link_smooth_weight[d];
         red7[3] += v * v;
     }

@@ -49,6 +49,14 @@ def main():
     lines.append("exact operator evaluations in the points phase: mean %.1f max %.0f per trajectory" % (exact.mean(), exact.max()))
     lines.append("P_in mean %.1f  nnz mean %.1f  active link instances mean %.1f / 300  limit rounds mean %.2f" % (
         info[:, 12].mean(), info[:, 13].mean(), info[:, 15].mean(), info[:, 14].mean()))
+    order = np.argsort(-tot)[:6]
+    lines.append("heaviest CTAs (cycles per phase):")
+    for bidx in order:
+        lines.append("  traj %4d total %7.0f | %s | nnz %4.0f exact %5.0f active %3.0f rounds %2.0f" % (
+            bidx, tot[bidx], " ".join("%s=%d" % (nm[:4], d[bidx, k]) for k, nm in enumerate(NAMES)),
+            info[bidx, 13], exact[bidx], info[bidx, 15], info[bidx, 14]))
+    pct = np.percentile(tot, [50, 90, 99, 100])
+    lines.append("total percentiles 50/90/99/100: %s" % np.round(pct))
     txt = "\n".join(lines)
     print(txt)
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
