@@ -53,7 +53,7 @@ struct DilDesc {
 
 struct SmemLayout {
     unsigned off_xi, off_start, off_end, off_goal, off_frames, off_lg, off_grad, off_u, off_viol, off_red, off_pts,
-        off_mask, off_best, off_bestp, off_act, off_objs, off_hist, total;
+        off_mask, off_best, off_bestp, off_act, off_win, off_objs, off_hist, total;
 };
 
 __host__ __device__ inline unsigned align_up(unsigned v, unsigned a) { return (v + a - 1) / a * a; }
@@ -83,6 +83,7 @@ __host__ __device__ inline SmemLayout make_layout(int n, int c, int lpi, int nob
     L.off_best = o; o += sizeof(float) * n * NL;
     L.off_bestp = o; o += sizeof(int) * n * NL;
     L.off_act = o; o += sizeof(int) * (n * NL + 40);
+    L.off_win = o; o += sizeof(unsigned short) * (n * NL + 8);
     o = align_up(o, 16);
     L.off_objs = o; o += sizeof(ObjRec) * nobj;
     L.off_hist = o; o += sizeof(int) * 264;
@@ -347,6 +348,67 @@ __device__ __forceinline__ bool far_pair(const ObjRec &ob, const DilDesc &dd, in
     return (v > ob.eps + slack) & (v > ob.clr + slack);
 }
 
+// Phase 4b body: the winners of the top-k branch, G lanes per winner (the operator's 7 trilinear samples and the
+// 8 gradient slots are spread over the group).
+struct WinCtx {
+    const RobotConst *rc;
+    const double *frames;
+    const unsigned long long *mask;
+    const int *bestp;
+    const unsigned short *win;
+    const ObjRec *objs;
+    const float *grids;
+    const DilDesc *dil;
+    double *lg;
+    double inv_dt;
+    int n, n_win;
+    bool finger_soft, use_dil;
+};
+
+template <int G>
+__device__ __forceinline__ void winners_pass(const WinCtx &c) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    constexpr int GPWW = 32 / G;
+    const int grp = lane / G, l = lane % G;
+    const unsigned gm = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (grp * G));
+    for (int base = warp * GPWW; base < c.n_win; base += nwarps * GPWW) {
+        const int idx = base + grp;
+        if (idx >= c.n_win) continue;   // uniform within the group
+        const int li = c.win[idx];
+        const int i = li / NL, j = li - i * NL;
+        const int p = c.bestp[li];
+        const double *F = c.frames + (size_t)li * 12;
+        const double *Fp = (i > 0) ? (F - NL * 12) : (c.frames + ((size_t)c.n * NL + j) * 12);
+        const double *Fn = (i < c.n - 1) ? (F + NL * 12) : (c.frames + ((size_t)(c.n + 1) * NL + j) * 12);
+        const double *bp = c.rc->pts[j][p];
+        const double b0 = bp[0], b1 = bp[1], b2 = bp[2];
+        double X, Y, Z, xp, yp, zp, xn, yn, zn;
+        xform(F, b0, b1, b2, X, Y, Z);
+        xform(Fp, b0, b1, b2, xp, yp, zp);
+        xform(Fn, b0, b1, b2, xn, yn, zn);
+        const float x = (float)X, y = (float)Y, z = (float)Z;
+        float pot = 0.0f, gx = 0.0f, gy = 0.0f, gz = 0.0f;
+        unsigned long long m = c.mask[li];
+        while (m) {
+            const int o = __ffsll((long long)m) - 1;
+            m &= m - 1;
+            if (c.use_dil && far_pair(c.objs[o], *c.dil, o, x, y, z)) continue;
+            float po, ax, ay, az, co;
+            pair_full_group<G>(c.objs[o], c.grids, gm, l, x, y, z, po, ax, ay, az, co);
+            pot = __fadd_rn(pot, po);
+            gx = __fadd_rn(gx, ax); gy = __fadd_rn(gy, ay); gz = __fadd_rn(gz, az);
+        }
+        if (c.finger_soft && j >= 8) {
+            pot = __fmul_rn(pot, 0.1f); gx = __fmul_rn(gx, 0.1f); gy = __fmul_rn(gy, 0.1f); gz = __fmul_rn(gz, 0.1f);
+        }
+        double wx, wy, wz;
+        fg_weight(X, Y, Z, xp, yp, zp, xn, yn, zn, (double)pot, (double)gx, (double)gy, (double)gz, c.inv_dt, wx, wy, wz);
+#pragma unroll 1
+        for (int s = l; s < NS; s += G)
+            c.lg[(size_t)li * NS + s] = fg_slot(c.rc, c.frames + (size_t)i * NL * 12, j, s, X, Y, Z, wx, wy, wz);
+    }
+}
+
 // ----------------------------------------------------------------------------------------------------
 // the fused iteration
 // ----------------------------------------------------------------------------------------------------
@@ -383,6 +445,7 @@ __global__ void __launch_bounds__(THREADS, MINB) chomp_step_kernel(const StepArg
     float *s_best = reinterpret_cast<float *>(smem + L.off_best);
     int *s_bestp = reinterpret_cast<int *>(smem + L.off_bestp);
     int *s_act = reinterpret_cast<int *>(smem + L.off_act);
+    unsigned short *s_win = reinterpret_cast<unsigned short *>(smem + L.off_win);
     ObjRec *s_objs = reinterpret_cast<ObjRec *>(smem + L.off_objs);
     int *s_hist = reinterpret_cast<int *>(smem + L.off_hist);
 
@@ -618,10 +681,24 @@ __global__ void __launch_bounds__(THREADS, MINB) chomp_step_kernel(const StepArg
         if (nnz > K) {
             uint32_t prefix = 0u, pmask = 0u;
             int remaining = K;
+            // each thread keeps its share of the active slots' bit patterns in registers across the four passes
+            constexpr int RC = 16;
+            uint32_t cache[RC];
+            const int n_as = n_act * LPI;
+#pragma unroll
+            for (int q = 0; q < RC; ++q) {
+                const int k = tid + q * nthr;
+                cache[q] = (k < n_as) ? __float_as_uint(s_pot[(size_t)s_act[k / LPI] * LPI + (k % LPI)]) : 0u;
+            }
             for (int shift = 24; shift >= 0; shift -= 8) {
                 for (int k = tid; k < 256; k += nthr) s_hist[k] = 0;
                 __syncthreads();
-                for (int k = tid; k < n_act * LPI; k += nthr) {   // inactive link instances hold zeros
+#pragma unroll
+                for (int q = 0; q < RC; ++q) {
+                    const uint32_t u = cache[q];
+                    if (u != 0u && (u & pmask) == prefix) atomicAdd(&s_hist[(u >> shift) & 255u], 1);
+                }
+                for (int k = tid + RC * nthr; k < n_as; k += nthr) {   // (only when n_as > 16 * blockDim)
                     const uint32_t u = __float_as_uint(s_pot[(size_t)s_act[k / LPI] * LPI + (k % LPI)]);
                     if (u != 0u && (u & pmask) == prefix) atomicAdd(&s_hist[(u >> shift) & 255u], 1);
                 }
@@ -679,53 +756,42 @@ __global__ void __launch_bounds__(THREADS, MINB) chomp_step_kernel(const StepArg
                 }
             }
         }
+        // winner list: active link instances whose best point is a top-k member (unordered; each winner writes
+        // only its own gradient rows)
+        if (tid == 0) s_hist[261] = 0;
+        __syncthreads();
+        for (int base = 0; base < n_act; base += nthr) {
+            const int idx = base + tid;
+            bool win = false;
+            int li = 0;
+            if (idx < n_act) {
+                li = s_act[idx];
+                const float bv = s_best[li];
+                win = ((li % NL) < jmax) && (bv > 0.0f) && (__float_as_uint(bv) >= tau);
+            }
+            const unsigned bal = __ballot_sync(0xffffffffu, win);
+            int wbase = 0;
+            if (lane == 0 && bal) wbase = atomicAdd(&s_hist[261], __popc(bal));
+            wbase = __shfl_sync(0xffffffffu, wbase, 0);
+            if (win) s_win[wbase + __popc(bal & ((1u << lane) - 1u))] = (unsigned short)li;
+        }
         double red1[1] = {acc};
         block_sum_n<1>(red1, s_red);   // (also the barrier after which s_pot is dead and s_lg may be written)
         obs_sum = red1[0] * (double)n;   // added to every waypoint row (SURVEY A-3)
         for (int k = tid; k < n_li * NS; k += nthr) s_lg[k] = 0.0;
         __syncthreads();
         OMGB_PROF(7);
-        // ---- phase 4b: one winner per (waypoint, link) (SURVEY A-1); 8 lanes per winner: the 7 trilinear samples
-        // of the operator and the 8 gradient slots are spread over the group ------------------------------------
+        // ---- phase 4b: one winner per (waypoint, link) (SURVEY A-1).  The winner list was compacted in phase 4a;
+        // the lanes per winner adapt to how many there are (few winners: low latency; many: no redundancy) ----
         {
-            const int grp = lane >> 3, l8 = lane & 7;
-            const unsigned gm8 = 0xffu << (grp * 8);
-            for (int base = warp * 4; base < n_act; base += nwarps * 4) {
-                const int idx = base + grp;
-                const int li = s_act[idx < n_act ? idx : n_act - 1];
-                const int i = li / NL, j = li - i * NL;
-                const float bv = s_best[li];
-                const bool win = (idx < n_act) && (j < jmax) && (bv > 0.0f) && (__float_as_uint(bv) >= tau);
-                if (!win) continue;   // uniform within the 8-lane group
-                const int p = s_bestp[li];
-                const double *F = s_frames + (size_t)li * 12;
-                const double *Fp = (i > 0) ? (F - NL * 12) : (s_frames + ((size_t)n * NL + j) * 12);
-                const double *Fn = (i < n - 1) ? (F + NL * 12) : (s_frames + ((size_t)(n + 1) * NL + j) * 12);
-                const double *bp = rc->pts[j][p];
-                double X, Y, Z, xp, yp, zp, xn, yn, zn;
-                xform(F, bp[0], bp[1], bp[2], X, Y, Z);
-                xform(Fp, bp[0], bp[1], bp[2], xp, yp, zp);
-                xform(Fn, bp[0], bp[1], bp[2], xn, yn, zn);
-                const float x = (float)X, y = (float)Y, z = (float)Z;
-                float pot = 0.0f, gx = 0.0f, gy = 0.0f, gz = 0.0f;
-                unsigned long long m = s_mask[li];
-                while (m) {
-                    const int o = __ffsll((long long)m) - 1;
-                    m &= m - 1;
-                    if (use_dil && far_pair(s_objs[o], a.dil, o, x, y, z)) continue;
-                    float po, ax, ay, az, co;
-                    pair_full_group8(s_objs[o], a.grids, gm8, l8, x, y, z, po, ax, ay, az, co);
-                    pot = __fadd_rn(pot, po);
-                    gx = __fadd_rn(gx, ax); gy = __fadd_rn(gy, ay); gz = __fadd_rn(gz, az);
-                }
-                if (finger_soft && j >= 8) {
-                    pot = __fmul_rn(pot, 0.1f); gx = __fmul_rn(gx, 0.1f); gy = __fmul_rn(gy, 0.1f);
-                    gz = __fmul_rn(gz, 0.1f);
-                }
-                double wx, wy, wz;
-                fg_weight(X, Y, Z, xp, yp, zp, xn, yn, zn, (double)pot, (double)gx, (double)gy, (double)gz, inv_dt, wx, wy, wz);
-                s_lg[(size_t)li * NS + l8] = fg_slot(rc, s_frames + (size_t)i * NL * 12, j, l8, X, Y, Z, wx, wy, wz);
-            }
+            WinCtx wc;
+            wc.rc = rc; wc.frames = s_frames; wc.mask = s_mask; wc.bestp = s_bestp; wc.win = s_win; wc.objs = s_objs;
+            wc.grids = a.grids; wc.dil = &a.dil; wc.lg = s_lg; wc.inv_dt = inv_dt; wc.n = n; wc.n_win = s_hist[261];
+            wc.finger_soft = finger_soft; wc.use_dil = use_dil;
+            if (wc.n_win * 8 <= nthr) winners_pass<8>(wc);
+            else if (wc.n_win * 4 <= nthr) winners_pass<4>(wc);
+            else if (wc.n_win * 2 <= nthr) winners_pass<2>(wc);
+            else winners_pass<1>(wc);
         }
     } else {
         obs_sum = red4[3];

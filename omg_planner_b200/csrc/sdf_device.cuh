@@ -163,24 +163,39 @@ __device__ __forceinline__ bool pair_full(const ObjRec &o, const float *__restri
     return inb;
 }
 
-// The same evaluation spread over a group of 8 lanes (gm = the group's lane mask, l = lane within the group):
-// lane l < 7 takes sample l, the values are exchanged with shuffles and every lane finishes redundantly.
-__device__ __forceinline__ void pair_full_group8(const ObjRec &o, const float *__restrict__ grids, unsigned gm, int l,
-                                                 float x, float y, float z, float &pot, float &gx, float &gy,
-                                                 float &gz, float &col) {
+// The same evaluation spread over a group of G lanes (G = 1, 2, 4 or 8; gm = the group's lane mask, l = lane
+// within the group): lane l takes samples l, l+G, ... of the seven, the values are exchanged with shuffles and
+// every lane finishes redundantly.  G == 1 evaluates the six gradient samples only when value <= eps.
+template <int G>
+__device__ __forceinline__ void pair_full_group(const ObjRec &o, const float *__restrict__ grids, unsigned gm, int l,
+                                                float x, float y, float z, float &pot, float &gx, float &gy,
+                                                float &gz, float &col) {
+    if (G == 1) {
+        pair_full(o, grids, x, y, z, pot, gx, gy, gz, col);
+        return;
+    }
     float px, py, pz;
     to_grid(o, x, y, z, px, py, pz);
-    const float sx = (l == 1) ? 1.0f : ((l == 4) ? -1.0f : 0.0f);
-    const float sy = (l == 2) ? 1.0f : ((l == 5) ? -1.0f : 0.0f);
-    const float sz = (l == 3) ? 1.0f : ((l == 6) ? -1.0f : 0.0f);
-    bool inb;
-    // p + 1 and p - 1 are single roundings either way (float3 operator+/- of kernel.cu:20-28)
-    const float v = value_interp(grids + o.grid_offset, o.d0, o.d1, o.d2, __fadd_rn(px, sx), __fadd_rn(py, sy),
-                                 __fadd_rn(pz, sz), inb);
-    const float v0 = __shfl_sync(gm, v, 0, 8), fpx = __shfl_sync(gm, v, 1, 8), fpy = __shfl_sync(gm, v, 2, 8),
-                fpz = __shfl_sync(gm, v, 3, 8), fmx = __shfl_sync(gm, v, 4, 8), fmy = __shfl_sync(gm, v, 5, 8),
-                fmz = __shfl_sync(gm, v, 6, 8);
-    finish_pair(o, v0, fpx, fpy, fpz, fmx, fmy, fmz, pot, gx, gy, gz, col);
+    constexpr int Q = (7 + G - 1) / G;
+    float v[Q];
+#pragma unroll
+    for (int q = 0; q < Q; ++q) {
+        const int k = l + q * G;
+        v[q] = 0.0f;
+        if (k < 7) {
+            // p + 1 and p - 1 are single roundings either way (float3 operator+/- of kernel.cu:20-28)
+            const float sx = (k == 1) ? 1.0f : ((k == 4) ? -1.0f : 0.0f);
+            const float sy = (k == 2) ? 1.0f : ((k == 5) ? -1.0f : 0.0f);
+            const float sz = (k == 3) ? 1.0f : ((k == 6) ? -1.0f : 0.0f);
+            bool inb;
+            v[q] = value_interp(grids + o.grid_offset, o.d0, o.d1, o.d2, __fadd_rn(px, sx), __fadd_rn(py, sy),
+                                __fadd_rn(pz, sz), inb);
+        }
+    }
+    float f[7];
+#pragma unroll
+    for (int k = 0; k < 7; ++k) f[k] = __shfl_sync(gm, v[k / G], k % G, G);
+    finish_pair(o, f[0], f[1], f[2], f[3], f[4], f[5], f[6], pot, gx, gy, gz, col);
 }
 
 }  // namespace omgb
