@@ -205,6 +205,8 @@ def run_b200(a):
     for _ in range(max(a.warmup, 3)):
         one_step()
     barrier()
+    from omg_planner_b200 import _lib
+    launches0 = int(_lib.lib().omgb_launch_count())
     sampler = ClockSampler(local)
     sampler.start()
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(a.steps)]
@@ -215,6 +217,7 @@ def run_b200(a):
         pins.append(out["info"][:, 12].sum())
     barrier()
     t_wall = time.perf_counter() - t_wall
+    launches = int(_lib.lib().omgb_launch_count()) - launches0
     clocks = sampler.stop()
     dev_ms = sum(s.elapsed_time(e) for s, e in evs)
     p_in_per_launch = float(torch.stack(pins).mean().item())
@@ -302,9 +305,9 @@ def run_b200(a):
         "e2e": {"value": total / (e2e_ms_max * 1e-3), "unit": "trajectory-iterations/s",
                 "h2d_bytes_per_step": 8 * (n_xi + 2 * n_se + n_goal), "d2h_bytes_per_step": 8 * (n_xi + n_info),
                 "ms_per_step": e2e_ms_max / a.steps, "api": "omgb_chomp_step_host (pinned host buffers)"},
-        "gpu_launches": a.steps,
+        "gpu_launches": launches,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": traffic, "peak_source": peak_src, "kernel": "chomp_step_kernel<16>",
+                     "traffic": traffic, "peak_source": peak_src, "kernel": "chomp_step_kernel<16,320,3,topk>" if a.mode == "default" else "chomp_step_kernel<16,320,3,fullsum>",
                      "algorithmic_bytes_per_launch": bytes_per_launch, "p_in_per_launch": p_in_per_launch,
                      "kernel_ms": kern_ms,
                      "note": "gather-bound: the 84 MB of SDFs stay in L2; see DESIGN.md for DRAM vs L2 traffic"},

@@ -123,6 +123,13 @@ int omgb_scene_set_objects(omgb_scene_t *scene, const float *pose_inv, const flo
 int omgb_scene_set_metric(omgb_scene_t *scene, int n_waypoints, const double *h_Ainv, int constraint_rows,
                           const double *h_proj);
 
+/* Exact accelerations that never change results (tests compare on/off bit for bit): the lower-bound grid
+ * culling and the longest-first CTA order.  -1 keeps the current value; both default to on. */
+int omgb_scene_set_options(omgb_scene_t *scene, int use_lower_bound, int use_longest_first);
+
+/* Number of kernels this library has launched so far in this process (bench.py reports the delta). */
+unsigned long long omgb_launch_count(void);
+
 /* Diagnostic: when d_phase_clocks (DEVICE int64 [B,16]) is non-NULL every CTA of the fused step writes clock64()
  * at its phase boundaries (profiles/ phase breakdowns); NULL (default) disables it. */
 int omgb_scene_set_profile(omgb_scene_t *scene, long long *d_phase_clocks);

@@ -330,22 +330,40 @@ __device__ __forceinline__ double functional_grad(const RobotConst *__restrict__
     return cost;
 }
 
-// True when the lower-bound grid proves that the sample of object `ob` at world point (x,y,z) is > eps and
-// >= clearance (so the pair contributes nothing) AND that its 8-tap cell is in bounds (so it counts in P_in).
-// Approximate (matrix-form, division-free) grid coordinates are enough: the 6^3 region and the 1.5-voxel
-// interior margin absorb their error.
-__device__ __forceinline__ bool far_pair(const ObjRec &ob, const DilDesc &dd, int oi, float x, float y, float z) {
+// Cheap classification of a (body point, object) pair from approximate (matrix-form, division-free) grid
+// coordinates; their error is far below the margins used.
+//   PAIR_FAR : the 8-tap cell is certainly in bounds AND the lower-bound grid proves value > eps and >= clearance
+//              -> contributes nothing, counts in P_in;
+//   PAIR_OUT : the 8-tap cell is certainly out of bounds -> the sample reads 1.0 (kernel.cu:47-48), contributes
+//              nothing (eps < 1, clearance <= 1 is checked when the record is built), not in P_in;
+//   PAIR_EXACT: anything else -> run the operator.
+enum { PAIR_EXACT = 0, PAIR_FAR = 1, PAIR_OUT = 2, PAIR_LOAD = 3 };
+// Stage 1: no memory access.  Returns PAIR_EXACT / PAIR_OUT, or PAIR_LOAD with the lower-bound entry to read.
+__device__ __forceinline__ int classify_prepare(const ObjRec &ob, const DilDesc &dd, int oi, float x, float y,
+                                                float z, const float *&addr) {
     const float qx = fmaf(ob.r[0], x, fmaf(ob.r[1], y, fmaf(ob.r[2], z, ob.tx)));
     const float qy = fmaf(ob.r[3], x, fmaf(ob.r[4], y, fmaf(ob.r[5], z, ob.ty)));
     const float qz = fmaf(ob.r[6], x, fmaf(ob.r[7], y, fmaf(ob.r[8], z, ob.tz)));
     const float gx = (qx - ob.minx) * ob.isx, gy = (qy - ob.miny) * ob.isy, gz = (qz - ob.minz) * ob.isz;
+    // in bounds <=> g in (-0.5, d - 0.5) on every axis (cell_of + the x1 < dim test of kernel.cu:47)
+    const bool outside = (gx < -0.75f) | (gx > ob.fd0 - 0.25f) | (gy < -0.75f) | (gy > ob.fd1 - 0.25f) |
+                         (gz < -0.75f) | (gz > ob.fd2 - 0.25f);
     const bool interior = (gx >= 1.5f) & (gx <= ob.fd0 - 1.5f) & (gy >= 1.5f) & (gy <= ob.fd1 - 1.5f) &
                           (gz >= 1.5f) & (gz <= ob.fd2 - 1.5f);
-    if (!interior) return false;
-    const int ix = ((int)gx) >> 1, iy = ((int)gy) >> 1, iz = ((int)gz) >> 1;
-    const float v = __ldg(dd.data + (size_t)oi * dd.obj_stride + ((size_t)ix * dd.by + iy) * dd.bz + iz);
+    const int ix = interior ? ((int)gx) >> 1 : 0, iy = interior ? ((int)gy) >> 1 : 0, iz = interior ? ((int)gz) >> 1 : 0;
+    addr = dd.data + (size_t)oi * dd.obj_stride + ((size_t)ix * dd.by + iy) * dd.bz + iz;
+    if (outside) return (ob.cull_pad < 1e29f) ? PAIR_OUT : PAIR_EXACT;
+    return interior ? PAIR_LOAD : PAIR_EXACT;
+}
+// Stage 2: the lower bound v proves "farther than eps and not colliding"?
+__device__ __forceinline__ int classify_finish(const ObjRec &ob, float v) {
     const float slack = 1e-4f + 1e-5f * fabsf(v);   // an fp32 lerp may undershoot its taps by a few ulps
-    return (v > ob.eps + slack) & (v > ob.clr + slack);
+    return ((v > ob.eps + slack) & (v > ob.clr + slack)) ? PAIR_FAR : PAIR_EXACT;
+}
+__device__ __forceinline__ int classify_pair(const ObjRec &ob, const DilDesc &dd, int oi, float x, float y, float z) {
+    const float *addr;
+    const int st = classify_prepare(ob, dd, oi, x, y, z, addr);
+    return st == PAIR_LOAD ? classify_finish(ob, __ldg(addr)) : st;
 }
 
 // Phase 4b body: the winners of the top-k branch, G lanes per winner (the operator's 7 trilinear samples and the
@@ -392,7 +410,7 @@ __device__ __forceinline__ void winners_pass(const WinCtx &c) {
         while (m) {
             const int o = __ffsll((long long)m) - 1;
             m &= m - 1;
-            if (c.use_dil && far_pair(c.objs[o], *c.dil, o, x, y, z)) continue;
+            if (c.use_dil && classify_pair(c.objs[o], *c.dil, o, x, y, z) != PAIR_EXACT) continue;
             float po, ax, ay, az, co;
             pair_full_group<G>(c.objs[o], c.grids, gm, l, x, y, z, po, ax, ay, az, co);
             pot = __fadd_rn(pot, po);
@@ -590,9 +608,12 @@ __global__ void __launch_bounds__(THREADS, MINB) chomp_step_kernel(const StepArg
             m &= m - 1;
             float po, co;
             bool inb;
-            if (use_dil && far_pair(s_objs[o], a.dil, o, x, y, z)) {   // exact: contributes nothing, in bounds
-                t_pin += 1;
-                continue;
+            if (use_dil) {
+                const int cls = classify_pair(s_objs[o], a.dil, o, x, y, z);
+                if (cls != PAIR_EXACT) {   // provably contributes nothing
+                    t_pin += (cls == PAIR_FAR) ? 1 : 0;
+                    continue;
+                }
             }
             t_exact += 1;
             if (topk_mode) {

@@ -15,6 +15,7 @@
 namespace omgb {
 
 static thread_local std::string g_err;
+static unsigned long long g_launches = 0;   // kernels launched by this library (bench.py's gpu_launches)
 
 static int fail(int code, const std::string &msg) {
     g_err = msg;
@@ -340,6 +341,7 @@ struct omgb_scene {
     int order_cap = 0, order_batch = -1;
     const void *order_key = nullptr;
     bool order_valid = false;
+    int use_lpt = 1;
     long long *d_prof = nullptr;   // diagnostic: per-CTA phase clocks (omgb_scene_set_profile)
     double *d_stage = nullptr;
     size_t stage_bytes = 0;
@@ -432,6 +434,15 @@ extern "C" int omgb_scene_set_robot(omgb_scene_t *s, const double *pose_0, const
     OMGB_CUDA(cudaMemcpy(s->d_robot, &h, sizeof(h), cudaMemcpyHostToDevice));
     s->p = p;
     s->robot_set = true;
+    return OMGB_OK;
+}
+
+extern "C" unsigned long long omgb_launch_count(void) { return g_launches; }
+
+extern "C" int omgb_scene_set_options(omgb_scene_t *s, int use_lower_bound, int use_longest_first) {
+    if (!s) return fail(OMGB_ERR_INVALID, "omgb_scene_set_options: null scene");
+    if (use_lower_bound >= 0) s->dil.enabled = (use_lower_bound != 0 && s->d_dil != nullptr) ? 1 : 0;
+    if (use_longest_first >= 0) { s->use_lpt = use_longest_first != 0; s->order_valid = false; }
     return OMGB_OK;
 }
 
@@ -571,6 +582,7 @@ extern "C" int omgb_sdf_loss(const float *pose_init, const float *sdf_grids, con
     if (blocks > 148 * 16) blocks = 148 * 16;
     sdf_loss_kernel<<<blocks, 256, smem, st>>>(recs, num_objects, sdf_grids, points, num_points, potentials,
                                                potential_grads, collides);
+    g_launches += 2;
     OMGB_CUDA(cudaGetLastError());
     return OMGB_OK;
 }
@@ -610,12 +622,14 @@ static int launch_cfg(const StepArgs &a, size_t smem, cudaStream_t st) {
         OMGB_CUDA(cudaFuncSetAttribute(chomp_step_kernel<LPI, THREADS, MINB, true>,
                                        cudaFuncAttributePreferredSharedMemoryCarveout, carveout_percent(smem, MINB)));
         chomp_step_kernel<LPI, THREADS, MINB, true><<<a.batch, THREADS, smem, st>>>(a);
+        ++g_launches;
     } else {
         OMGB_CUDA(cudaFuncSetAttribute(chomp_step_kernel<LPI, THREADS, MINB, false>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         OMGB_CUDA(cudaFuncSetAttribute(chomp_step_kernel<LPI, THREADS, MINB, false>,
                                        cudaFuncAttributePreferredSharedMemoryCarveout, carveout_percent(smem, MINB)));
         chomp_step_kernel<LPI, THREADS, MINB, false><<<a.batch, THREADS, smem, st>>>(a);
+        ++g_launches;
     }
     OMGB_CUDA(cudaGetLastError());
     return OMGB_OK;
@@ -640,9 +654,9 @@ static int launch_step(omgb_scene *s, const StepArgs &a_in, cudaStream_t st) {
     // longest-first order from the previous launch on the same batch (same xi buffer and size)
     StepArgs a = a_in;
     a.lay = L;
-    static int use_lpt = -1;
-    if (use_lpt < 0) { const char *e = getenv("OMGB_NO_LPT"); use_lpt = (e && atoi(e)) ? 0 : 1; }
-    if (use_lpt && a.batch >= 2 * 148) {
+    static int env_lpt = -1;
+    if (env_lpt < 0) { const char *e = getenv("OMGB_NO_LPT"); env_lpt = (e && atoi(e)) ? 0 : 1; }
+    if (env_lpt && s->use_lpt && a.batch >= 2 * 148) {
         if (a.batch > s->order_cap) {
             cudaFree(s->d_order); cudaFree(s->d_cost);
             s->d_order = s->d_cost = nullptr; s->order_cap = 0;
@@ -677,6 +691,7 @@ static int launch_step(omgb_scene *s, const StepArgs &a_in, cudaStream_t st) {
     if (rc_) return rc_;
     if (a.cta_cost) {
         lpt_order_kernel<<<1, 1024, 0, st>>>(s->d_cost, s->d_order, a.batch);
+        ++g_launches;
         OMGB_CUDA(cudaGetLastError());
         s->order_valid = true;
         s->order_batch = a.batch;

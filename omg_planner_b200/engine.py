@@ -92,6 +92,11 @@ class ChompEngine(object):
         _lib.check(self.L.omgb_scene_set_metric(self._h, cfg.timesteps, _hp(ainv), c, _hp(proj)), "omgb_scene_set_metric")
         self._metric_key = key
 
+    def set_options(self, use_lower_bound=-1, use_longest_first=-1):
+        """Toggle the exact accelerations (results are bit-identical either way)."""
+        _lib.check(self.L.omgb_scene_set_options(self._h, int(use_lower_bound), int(use_longest_first)),
+                   "omgb_scene_set_options")
+
     def load_scene(self, scene, cfg):
         """Upload a scene dict (omg_planner_b200.scene.make_scene layout) with the per-object parameters
         Cost.compute_obstacle_cost_layer would build (omg/cost.py:303-328)."""

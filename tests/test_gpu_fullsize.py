@@ -88,3 +88,27 @@ def test_long_trajectories_and_many_objects():
             eng.step(cfg, x, _dev(st), _dev(en), _dev(tails))
         torch.cuda.synchronize()
         assert np.abs(x.cpu().numpy() - ref_hist[:, 2])[..., :7].max() <= 1e-7
+
+
+def test_exact_accelerations_do_not_change_results(big):
+    """Lower-bound culling and longest-first CTA order are exact: outputs (including P_in) are bit-identical with
+    them off."""
+    sc, robot, xi, st, en, tails = big
+    outs = []
+    for lb, lpt in ((1, 1), (0, 0)):
+        mode = H.MODES["goalset_standoff_topk"]
+        cfg = ChompConfig(**mode)
+        eng = H.engine_for(sc, cfg, robot)
+        eng.set_options(use_lower_bound=lb, use_longest_first=lpt)
+        x = _dev(xi[:400])
+        infos = []
+        for it in range(3):
+            cfg.obstacle_weight, cfg.smoothness_weight, cfg.step_size = cfg.schedule(it + 1)
+            infos.append(eng.step(cfg, x, _dev(st[:400]), _dev(en[:400]), _dev(tails[:400]))["info"][:, :15].clone())
+        torch.cuda.synchronize()
+        outs.append((x.clone(), torch.stack(infos)))
+    assert torch.equal(outs[0][0], outs[1][0])                       # trajectories: bit-identical
+    a, b = outs[0][1], outs[1][1]
+    assert torch.equal(a[..., 3:], b[..., 3:]) and torch.equal(a[..., 1], b[..., 1])   # collide, P_in, flags, norms
+    # obstacle cost / total cost are block sums whose fp64 summation order follows the active set: last-ulp only
+    assert torch.allclose(a[..., [0, 2]], b[..., [0, 2]], rtol=1e-12, atol=0)
