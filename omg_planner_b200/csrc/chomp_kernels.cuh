@@ -92,6 +92,15 @@ __host__ __device__ inline SmemLayout make_layout(int n, int c, int lpi, int nob
     return L;
 }
 
+// Small robot constants passed as kernel parameters: they are read with warp-uniform indices inside dependent
+// chains (FK, joint limits), where the constant bank avoids the L1/L2 round trip of a global load.
+struct RobotParams {
+    double P0[10][12];
+    double CO[10][12];
+    double lower[ND], upper[ND];
+    float sph[10][4];
+};
+
 struct StepArgs {
     const ObjRec *objs;
     const float *grids;
@@ -114,6 +123,7 @@ struct StepArgs {
     long long *prof;         // [B,16] or null: clock64() at phase boundaries (diagnostic)
     DilDesc dil;
     SmemLayout lay;          // computed on the host (make_layout)
+    RobotParams rp;
     int num_objects;
     int batch;
     int iteration;           // index inside a plan (for the t > 0 rule of planner.py:627)
@@ -235,38 +245,38 @@ __device__ __forceinline__ Row row_mul(const Row &r, const double *B) {
 }
 
 // frames: this configuration's [10][12]; row index r in 0..2; sc: sin/cos pairs of the 7 arm joints.
-__device__ __forceinline__ void panda_fk_row(const RobotConst *__restrict__ rc, const double *q, const double2 *sc,
-                                             int r, double *frames) {
+__device__ __forceinline__ void panda_fk_row(const RobotParams &rc, const double *q, const double2 *sc, int r,
+                                             double *frames) {
     Row T;
     T.a = (r == 0) ? 1.0 : 0.0; T.b = (r == 1) ? 1.0 : 0.0; T.c = (r == 2) ? 1.0 : 0.0; T.t = 0.0;
 #pragma unroll 1
     for (int i = 0; i < 7; ++i) {
-        const Row N = row_mul(T, rc->P0[i]);
+        const Row N = row_mul(T, rc.P0[i]);
         const double s = sc[i].x, c = sc[i].y;
         T.a = fma(N.a, c, N.b * s);
         T.b = fma(N.b, c, -(N.a * s));
         T.c = N.c;
         T.t = N.t;
-        const Row F = row_mul(T, rc->CO[i]);
+        const Row F = row_mul(T, rc.CO[i]);
         double *f = frames + 12 * i;
         f[3 * r] = F.a; f[3 * r + 1] = F.b; f[3 * r + 2] = F.c; f[9 + r] = F.t;
     }
-    const Row H = row_mul(T, rc->P0[7]);
+    const Row H = row_mul(T, rc.P0[7]);
     {
-        const Row F = row_mul(H, rc->CO[7]);
+        const Row F = row_mul(H, rc.CO[7]);
         double *f = frames + 12 * 7;
         f[3 * r] = F.a; f[3 * r + 1] = F.b; f[3 * r + 2] = F.c; f[9 + r] = F.t;
     }
 #pragma unroll 1
     for (int k = 0; k < 2; ++k) {
-        const double *B = rc->P0[8 + k];
+        const double *B = rc.P0[8 + k];
         const double ty = B[10] + ((k == 0) ? q[7] : -q[8]);   // robot_pykdl.py:181-184
         Row G;
         G.a = fma(H.a, B[0], fma(H.b, B[3], H.c * B[6]));
         G.b = fma(H.a, B[1], fma(H.b, B[4], H.c * B[7]));
         G.c = fma(H.a, B[2], fma(H.b, B[5], H.c * B[8]));
         G.t = fma(H.a, B[9], fma(H.b, ty, fma(H.c, B[11], H.t)));
-        const Row F = row_mul(G, rc->CO[8 + k]);
+        const Row F = row_mul(G, rc.CO[8 + k]);
         double *f = frames + 12 * (8 + k);
         f[3 * r] = F.a; f[3 * r + 1] = F.b; f[3 * r + 2] = F.c; f[9 + r] = F.t;
     }
@@ -509,7 +519,7 @@ __global__ void __launch_bounds__(THREADS, MINB) chomp_step_kernel(const StepArg
     for (int k = tid; k < (n + 2) * 3; k += nthr) {
         const int cfg = k / 3, r = k - cfg * 3;
         const double *q = (cfg < n) ? (s_xi + cfg * ND) : (cfg == n ? s_start : s_end);
-        panda_fk_row(rc, q, s_sc + cfg * 7, r, s_frames + (size_t)cfg * NL * 12);
+        panda_fk_row(a.rp, q, s_sc + cfg * 7, r, s_frames + (size_t)cfg * NL * 12);
     }
     __syncthreads();
 
@@ -524,8 +534,8 @@ __global__ void __launch_bounds__(THREADS, MINB) chomp_step_kernel(const StepArg
     for (int li = tid; li < n_li; li += nthr) {
         const int j = li % NL;
         double cx, cy, cz;
-        xform(s_frames + (size_t)li * 12, (double)rc->sph[j][0], (double)rc->sph[j][1], (double)rc->sph[j][2], cx, cy, cz);
-        const float fx = (float)cx, fy = (float)cy, fz = (float)cz, rad = rc->sph[j][3];
+        xform(s_frames + (size_t)li * 12, (double)a.rp.sph[j][0], (double)a.rp.sph[j][1], (double)a.rp.sph[j][2], cx, cy, cz);
+        const float fx = (float)cx, fy = (float)cy, fz = (float)cz, rad = a.rp.sph[j][3];
         unsigned long long m = 0ull;
         for (int o = 0; o < O; ++o) {
             const ObjRec &ob = s_objs[o];
@@ -844,8 +854,8 @@ __global__ void __launch_bounds__(THREADS, MINB) chomp_step_kernel(const StepArg
         s_grad[k] = gt;
         red7[0] += wo * wo; red7[1] += ws * ws; red7[2] += gt * gt;
         // check_joint_limit (optimizer.py:166-174, sic: scalar "any below" times elementwise "above")
-        if (xc < rc->lower[d] - 5e-3) red7[5] = 1.0;
-        if (xc > rc->upper[d] + 5e-3) red7[6] = 1.0;
+        if (xc < a.rp.lower[d] - 5e-3) red7[5] = 1.0;
+        if (xc > a.rp.upper[d] + 5e-3) red7[6] = 1.0;
         if (goal_set && i == n - 1) { const double dg = xc - s_end[d]; red7[4] += dg * dg; }
     }
     for (int k = tid; k < (n + 1) * ND; k += nthr) {   // smoothness loss rows 0..n (cost.py:443-445)
@@ -916,8 +926,8 @@ __global__ void __launch_bounds__(THREADS, MINB) chomp_step_kernel(const StepArg
                 const int d = k % ND;
                 const double v = s_xi[k];
                 double viol = 0.0;
-                if (v < rc->lower[d]) viol = rc->lower[d] - v;
-                else if (v > rc->upper[d]) viol = rc->upper[d] - v;
+                if (v < a.rp.lower[d]) viol = a.rp.lower[d] - v;
+                else if (v > a.rp.upper[d]) viol = a.rp.upper[d] - v;
                 s_viol[k] = viol;
                 t[0] += viol * viol;
                 const double m = fabs(viol);

@@ -320,6 +320,7 @@ using namespace omgb;
 struct omgb_scene {
     int device = 0;
     RobotConst *d_robot = nullptr;
+    RobotParams rp;
     bool robot_set = false;
     int p = 0;
     const float *d_grids = nullptr;
@@ -432,6 +433,11 @@ extern "C" int omgb_scene_set_robot(omgb_scene_t *s, const double *pose_0, const
     for (int d = 0; d < ND; ++d) { h.lower[d] = lower[d]; h.upper[d] = upper[d]; }
     h.p = p;
     OMGB_CUDA(cudaMemcpy(s->d_robot, &h, sizeof(h), cudaMemcpyHostToDevice));
+    memcpy(s->rp.P0, h.P0, sizeof(h.P0));
+    memcpy(s->rp.CO, h.CO, sizeof(h.CO));
+    memcpy(s->rp.lower, h.lower, sizeof(h.lower));
+    memcpy(s->rp.upper, h.upper, sizeof(h.upper));
+    memcpy(s->rp.sph, h.sph, sizeof(h.sph));
     s->p = p;
     s->robot_set = true;
     return OMGB_OK;
@@ -654,6 +660,7 @@ static int launch_step(omgb_scene *s, const StepArgs &a_in, cudaStream_t st) {
     // longest-first order from the previous launch on the same batch (same xi buffer and size)
     StepArgs a = a_in;
     a.lay = L;
+    a.rp = s->rp;
     static int env_lpt = -1;
     if (env_lpt < 0) { const char *e = getenv("OMGB_NO_LPT"); env_lpt = (e && atoi(e)) ? 0 : 1; }
     if (env_lpt && s->use_lpt && a.batch >= 2 * 148) {
