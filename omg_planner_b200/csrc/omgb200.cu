@@ -317,6 +317,15 @@ using namespace omgb;
 // ----------------------------------------------------------------------------------------------------
 // scene
 // ----------------------------------------------------------------------------------------------------
+constexpr int ORDER_SLOTS = 8;
+constexpr int PIPE_CHUNKS = 4;
+struct OrderSlot {
+    int *d_order = nullptr, *d_cost = nullptr;
+    int cap = 0, batch = -1;
+    const void *key = nullptr;
+    bool valid = false;
+};
+
 struct omgb_scene {
     int device = 0;
     RobotConst *d_robot = nullptr;
@@ -337,12 +346,16 @@ struct omgb_scene {
     float *d_dil = nullptr;
     DilDesc dil;
     int *d_bounds = nullptr;
-    // longest-first CTA scheduling state (hint only)
-    int *d_order = nullptr, *d_cost = nullptr;
-    int order_cap = 0, order_batch = -1;
-    const void *order_key = nullptr;
-    bool order_valid = false;
+    // longest-first CTA scheduling state (hint only), one slot per (xi buffer, batch) seen recently
+    OrderSlot order[ORDER_SLOTS];
+    int order_next = 0;
     int use_lpt = 1;
+    // host-buffer entry point: 0 auto (zero-copy when every buffer is mapped pinned memory, else pipelined staging),
+    // 1 staged in one piece, 2 staged + pipelined over chunks, 3 zero-copy required
+    int host_mode = 0;
+    cudaStream_t pipe_stream[PIPE_CHUNKS] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t pipe_done[PIPE_CHUNKS] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t pipe_begin = nullptr;
     long long *d_prof = nullptr;   // diagnostic: per-CTA phase clocks (omgb_scene_set_profile)
     double *d_stage = nullptr;
     size_t stage_bytes = 0;
@@ -369,7 +382,13 @@ extern "C" int omgb_scene_destroy(omgb_scene_t *s) {
     if (!s) return OMGB_OK;
     cudaSetDevice(s->device);
     cudaFree(s->d_robot); cudaFree(s->d_limits); cudaFree(s->d_objparams); cudaFree(s->d_objs);
-    cudaFree(s->d_Ainv); cudaFree(s->d_proj); cudaFree(s->d_stage); cudaFree(s->d_dil); cudaFree(s->d_bounds); cudaFree(s->d_order); cudaFree(s->d_cost);
+    cudaFree(s->d_Ainv); cudaFree(s->d_proj); cudaFree(s->d_stage); cudaFree(s->d_dil); cudaFree(s->d_bounds);
+    for (int k = 0; k < ORDER_SLOTS; ++k) { cudaFree(s->order[k].d_order); cudaFree(s->order[k].d_cost); }
+    for (int k = 0; k < PIPE_CHUNKS; ++k) {
+        if (s->pipe_stream[k]) cudaStreamDestroy(s->pipe_stream[k]);
+        if (s->pipe_done[k]) cudaEventDestroy(s->pipe_done[k]);
+    }
+    if (s->pipe_begin) cudaEventDestroy(s->pipe_begin);
     delete s;
     return OMGB_OK;
 }
@@ -448,7 +467,16 @@ extern "C" unsigned long long omgb_launch_count(void) { return g_launches; }
 extern "C" int omgb_scene_set_options(omgb_scene_t *s, int use_lower_bound, int use_longest_first) {
     if (!s) return fail(OMGB_ERR_INVALID, "omgb_scene_set_options: null scene");
     if (use_lower_bound >= 0) s->dil.enabled = (use_lower_bound != 0 && s->d_dil != nullptr) ? 1 : 0;
-    if (use_longest_first >= 0) { s->use_lpt = use_longest_first != 0; s->order_valid = false; }
+    if (use_longest_first >= 0) {
+        s->use_lpt = use_longest_first != 0;
+        for (int k = 0; k < ORDER_SLOTS; ++k) s->order[k].valid = false;
+    }
+    return OMGB_OK;
+}
+
+extern "C" int omgb_scene_set_host_mode(omgb_scene_t *s, int mode) {
+    if (!s || mode < 0 || mode > 3) return fail(OMGB_ERR_INVALID, "omgb_scene_set_host_mode: bad argument");
+    s->host_mode = mode;
     return OMGB_OK;
 }
 
@@ -620,25 +648,29 @@ static int carveout_percent(size_t smem, int ctas) {
     return pct > 100 ? 100 : pct;
 }
 
-template <int LPI, int THREADS, int MINB>
-static int launch_cfg(const StepArgs &a, size_t smem, cudaStream_t st) {
-    if (a.prm.top_k_collision > 0) {
-        OMGB_CUDA(cudaFuncSetAttribute(chomp_step_kernel<LPI, THREADS, MINB, true>,
+template <int LPI, int THREADS, int MINB, bool TOPK>
+static int launch_one(const StepArgs &a, size_t smem, cudaStream_t st) {
+    // function attributes are per (instantiation, device); set again only when the footprint changes
+    static size_t cached_smem[64] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64 || cached_smem[dev] != smem) {
+        OMGB_CUDA(cudaFuncSetAttribute(chomp_step_kernel<LPI, THREADS, MINB, TOPK>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        OMGB_CUDA(cudaFuncSetAttribute(chomp_step_kernel<LPI, THREADS, MINB, true>,
+        OMGB_CUDA(cudaFuncSetAttribute(chomp_step_kernel<LPI, THREADS, MINB, TOPK>,
                                        cudaFuncAttributePreferredSharedMemoryCarveout, carveout_percent(smem, MINB)));
-        chomp_step_kernel<LPI, THREADS, MINB, true><<<a.batch, THREADS, smem, st>>>(a);
-        ++g_launches;
-    } else {
-        OMGB_CUDA(cudaFuncSetAttribute(chomp_step_kernel<LPI, THREADS, MINB, false>,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        OMGB_CUDA(cudaFuncSetAttribute(chomp_step_kernel<LPI, THREADS, MINB, false>,
-                                       cudaFuncAttributePreferredSharedMemoryCarveout, carveout_percent(smem, MINB)));
-        chomp_step_kernel<LPI, THREADS, MINB, false><<<a.batch, THREADS, smem, st>>>(a);
-        ++g_launches;
+        if (dev >= 0 && dev < 64) cached_smem[dev] = smem;
     }
+    chomp_step_kernel<LPI, THREADS, MINB, TOPK><<<a.batch, THREADS, smem, st>>>(a);
+    ++g_launches;
     OMGB_CUDA(cudaGetLastError());
     return OMGB_OK;
+}
+
+template <int LPI, int THREADS, int MINB>
+static int launch_cfg(const StepArgs &a, size_t smem, cudaStream_t st) {
+    return a.prm.top_k_collision > 0 ? launch_one<LPI, THREADS, MINB, true>(a, smem, st)
+                                     : launch_one<LPI, THREADS, MINB, false>(a, smem, st);
 }
 
 static int step_config() {   // 0: 256 threads x 3 CTAs/SM, 1: 512 x 2, 2: 512 x 1, 3: 256 x 2, 4: 384 x 2, 5 (default): 320 x 3
@@ -663,18 +695,27 @@ static int launch_step(omgb_scene *s, const StepArgs &a_in, cudaStream_t st) {
     a.rp = s->rp;
     static int env_lpt = -1;
     if (env_lpt < 0) { const char *e = getenv("OMGB_NO_LPT"); env_lpt = (e && atoi(e)) ? 0 : 1; }
-    if (env_lpt && s->use_lpt && a.batch >= 2 * 148) {
-        if (a.batch > s->order_cap) {
-            cudaFree(s->d_order); cudaFree(s->d_cost);
-            s->d_order = s->d_cost = nullptr; s->order_cap = 0;
-            OMGB_CUDA(cudaMalloc(&s->d_order, sizeof(int) * a.batch));
-            OMGB_CUDA(cudaMalloc(&s->d_cost, sizeof(int) * a.batch));
-            s->order_cap = a.batch;
-            s->order_valid = false;
+    OrderSlot *os = nullptr;
+    if (env_lpt && s->use_lpt && a.batch >= 148) {
+        for (int k = 0; k < ORDER_SLOTS; ++k)
+            if (s->order[k].key == (const void *)a.xi && s->order[k].batch == a.batch) os = &s->order[k];
+        if (!os) {
+            os = &s->order[s->order_next];
+            s->order_next = (s->order_next + 1) % ORDER_SLOTS;
+            os->valid = false;
+            os->key = (const void *)a.xi;
+            os->batch = a.batch;
         }
-        if (s->order_batch != a.batch || s->order_key != (const void *)a.xi) s->order_valid = false;
-        a.order = s->order_valid ? s->d_order : nullptr;
-        a.cta_cost = s->d_cost;
+        if (a.batch > os->cap) {
+            cudaFree(os->d_order); cudaFree(os->d_cost);
+            os->d_order = os->d_cost = nullptr; os->cap = 0;
+            OMGB_CUDA(cudaMalloc(&os->d_order, sizeof(int) * a.batch));
+            OMGB_CUDA(cudaMalloc(&os->d_cost, sizeof(int) * a.batch));
+            os->cap = a.batch;
+            os->valid = false;
+        }
+        a.order = os->valid ? os->d_order : nullptr;
+        a.cta_cost = os->d_cost;
     }
     const int cfg = step_config();
     int rc_ = OMGB_OK;
@@ -696,13 +737,11 @@ static int launch_step(omgb_scene *s, const StepArgs &a_in, cudaStream_t st) {
         }
     }
     if (rc_) return rc_;
-    if (a.cta_cost) {
-        lpt_order_kernel<<<1, 1024, 0, st>>>(s->d_cost, s->d_order, a.batch);
+    if (os) {
+        lpt_order_kernel<<<1, 1024, 0, st>>>(os->d_cost, os->d_order, a.batch);
         ++g_launches;
         OMGB_CUDA(cudaGetLastError());
-        s->order_valid = true;
-        s->order_batch = a.batch;
-        s->order_key = (const void *)a.xi;
+        os->valid = true;
     }
     return OMGB_OK;
 }
@@ -763,6 +802,15 @@ extern "C" int omgb_chomp_plan(omgb_scene_t *s, const omgb_step_params_t *prm, i
     return OMGB_OK;
 }
 
+// Device alias of a host pointer when it lies in mapped pinned memory (cudaHostAlloc / cudaHostRegister under UVA).
+static void *mapped_alias(const void *h) {
+    if (!h) return nullptr;
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, h) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    if (at.type != cudaMemoryTypeHost) return nullptr;
+    return at.devicePointer;
+}
+
 extern "C" int omgb_chomp_step_host(omgb_scene_t *s, const omgb_step_params_t *prm, int batch, double *h_xi,
                                     const double *h_start, const double *h_end, const double *h_goal_rows,
                                     double *h_info, void *stream) {
@@ -774,6 +822,27 @@ extern "C" int omgb_chomp_step_host(omgb_scene_t *s, const omgb_step_params_t *p
     OMGB_CUDA(cudaSetDevice(s->device));
     cudaStream_t st = (cudaStream_t)stream;
     const int n = prm->n_waypoints, c = prm->goal_set_proj ? prm->constraint_rows : 0;
+
+    // (A) zero-copy: every buffer is mapped pinned host memory -> the fused kernel itself reads xi/start/end/goal rows
+    // over PCIe while staging them into shared memory and writes the new xi and the info row straight back; there
+    // is no separate copy to wait for.
+    if (s->host_mode == 0 || s->host_mode == 3) {
+        double *m_xi = (double *)mapped_alias(h_xi), *m_info = (double *)mapped_alias(h_info);
+        const double *m_start = (const double *)mapped_alias(h_start), *m_end = (const double *)mapped_alias(h_end);
+        const double *m_goal = c > 0 ? (const double *)mapped_alias(h_goal_rows) : nullptr;
+        const bool all = m_xi && m_info && m_start && m_end && (c == 0 || m_goal);
+        if (all) {
+            StepArgs a = make_args(s, prm, batch, m_xi, m_start, m_end, m_goal, nullptr, nullptr, m_info, nullptr, nullptr);
+            rc_ = launch_step(s, a, st);
+            if (rc_) return rc_;
+            OMGB_CUDA(cudaStreamSynchronize(st));
+            return OMGB_OK;
+        }
+        if (s->host_mode == 3) return fail(OMGB_ERR_INVALID, "omgb_chomp_step_host: buffers are not mapped pinned memory");
+    }
+
+    // (B) staged: H2D -> kernel -> D2H, pipelined over up to PIPE_CHUNKS chunks of trajectories on the scene's own
+    // streams so that chunk k's D2H overlaps chunk k+1's kernel and chunk k+2's H2D (separate copy engines).
     const size_t n_xi = (size_t)batch * n * ND, n_se = (size_t)batch * ND, n_goal = (size_t)batch * c * ND,
                  n_info = (size_t)batch * OMGB_INFO_STRIDE;
     const size_t need = sizeof(double) * (n_xi + 2 * n_se + n_goal + n_info);
@@ -785,16 +854,47 @@ extern "C" int omgb_chomp_step_host(omgb_scene_t *s, const omgb_step_params_t *p
     }
     double *d_xi = s->d_stage, *d_start = d_xi + n_xi, *d_end = d_start + n_se, *d_goal = d_end + n_se,
            *d_info = d_goal + n_goal;
-    OMGB_CUDA(cudaMemcpyAsync(d_xi, h_xi, sizeof(double) * n_xi, cudaMemcpyHostToDevice, st));
-    OMGB_CUDA(cudaMemcpyAsync(d_start, h_start, sizeof(double) * n_se, cudaMemcpyHostToDevice, st));
-    OMGB_CUDA(cudaMemcpyAsync(d_end, h_end, sizeof(double) * n_se, cudaMemcpyHostToDevice, st));
-    if (c > 0) OMGB_CUDA(cudaMemcpyAsync(d_goal, h_goal_rows, sizeof(double) * n_goal, cudaMemcpyHostToDevice, st));
-    StepArgs a = make_args(s, prm, batch, d_xi, d_start, d_end, c > 0 ? d_goal : nullptr, nullptr, nullptr, d_info,
-                           nullptr, nullptr);
-    rc_ = launch_step(s, a, st);
-    if (rc_) return rc_;
-    OMGB_CUDA(cudaMemcpyAsync(h_xi, d_xi, sizeof(double) * n_xi, cudaMemcpyDeviceToHost, st));
-    OMGB_CUDA(cudaMemcpyAsync(h_info, d_info, sizeof(double) * n_info, cudaMemcpyDeviceToHost, st));
+    int chunks = 1;
+    if (s->host_mode != 1) {
+        chunks = batch / 256;
+        chunks = chunks < 1 ? 1 : (chunks > PIPE_CHUNKS ? PIPE_CHUNKS : chunks);
+    }
+    if (chunks > 1 && !s->pipe_begin) {
+        for (int k = 0; k < PIPE_CHUNKS; ++k) {
+            OMGB_CUDA(cudaStreamCreateWithFlags(&s->pipe_stream[k], cudaStreamNonBlocking));
+            OMGB_CUDA(cudaEventCreateWithFlags(&s->pipe_done[k], cudaEventDisableTiming));
+        }
+        OMGB_CUDA(cudaEventCreateWithFlags(&s->pipe_begin, cudaEventDisableTiming));
+    }
+    if (chunks > 1) OMGB_CUDA(cudaEventRecord(s->pipe_begin, st));
+    for (int k = 0; k < chunks; ++k) {
+        const int b0 = (int)((long long)batch * k / chunks), b1 = (int)((long long)batch * (k + 1) / chunks);
+        const size_t nb = (size_t)(b1 - b0);
+        cudaStream_t cs = chunks > 1 ? s->pipe_stream[k] : st;
+        if (chunks > 1) OMGB_CUDA(cudaStreamWaitEvent(cs, s->pipe_begin, 0));
+        OMGB_CUDA(cudaMemcpyAsync(d_xi + (size_t)b0 * n * ND, h_xi + (size_t)b0 * n * ND, sizeof(double) * nb * n * ND,
+                                  cudaMemcpyHostToDevice, cs));
+        OMGB_CUDA(cudaMemcpyAsync(d_start + (size_t)b0 * ND, h_start + (size_t)b0 * ND, sizeof(double) * nb * ND,
+                                  cudaMemcpyHostToDevice, cs));
+        OMGB_CUDA(cudaMemcpyAsync(d_end + (size_t)b0 * ND, h_end + (size_t)b0 * ND, sizeof(double) * nb * ND,
+                                  cudaMemcpyHostToDevice, cs));
+        if (c > 0)
+            OMGB_CUDA(cudaMemcpyAsync(d_goal + (size_t)b0 * c * ND, h_goal_rows + (size_t)b0 * c * ND,
+                                      sizeof(double) * nb * c * ND, cudaMemcpyHostToDevice, cs));
+        StepArgs a = make_args(s, prm, (int)nb, d_xi + (size_t)b0 * n * ND, d_start + (size_t)b0 * ND,
+                               d_end + (size_t)b0 * ND, c > 0 ? d_goal + (size_t)b0 * c * ND : nullptr, nullptr, nullptr,
+                               d_info + (size_t)b0 * OMGB_INFO_STRIDE, nullptr, nullptr);
+        rc_ = launch_step(s, a, cs);
+        if (rc_) return rc_;
+        OMGB_CUDA(cudaMemcpyAsync(h_xi + (size_t)b0 * n * ND, d_xi + (size_t)b0 * n * ND, sizeof(double) * nb * n * ND,
+                                  cudaMemcpyDeviceToHost, cs));
+        OMGB_CUDA(cudaMemcpyAsync(h_info + (size_t)b0 * OMGB_INFO_STRIDE, d_info + (size_t)b0 * OMGB_INFO_STRIDE,
+                                  sizeof(double) * nb * OMGB_INFO_STRIDE, cudaMemcpyDeviceToHost, cs));
+        if (chunks > 1) {
+            OMGB_CUDA(cudaEventRecord(s->pipe_done[k], cs));
+            OMGB_CUDA(cudaStreamWaitEvent(st, s->pipe_done[k], 0));
+        }
+    }
     OMGB_CUDA(cudaStreamSynchronize(st));
     return OMGB_OK;
 }
