@@ -127,6 +127,12 @@ int omgb_scene_set_metric(omgb_scene_t *scene, int n_waypoints, const double *h_
  * culling and the longest-first CTA order.  -1 keeps the current value; both default to on. */
 int omgb_scene_set_options(omgb_scene_t *scene, int use_lower_bound, int use_longest_first);
 
+/* How omgb_chomp_step_host moves its HOST buffers: 0 (default) = zero-copy when every buffer lies in mapped pinned
+ * memory (cudaHostAlloc / cudaHostRegister: the fused kernel reads its inputs and writes its results over PCIe
+ * itself), otherwise staged copies pipelined over chunks of trajectories; 1 = staged, one piece; 2 = staged,
+ * pipelined; 3 = zero-copy or OMGB_ERR_INVALID.  Results are identical in every mode. */
+int omgb_scene_set_host_mode(omgb_scene_t *scene, int mode);
+
 /* Number of kernels this library has launched so far in this process (bench.py reports the delta). */
 unsigned long long omgb_launch_count(void);
 
@@ -162,8 +168,8 @@ int omgb_chomp_plan(omgb_scene_t *scene, const omgb_step_params_t *params, int i
                     int stop_on_terminate, int batch, double *xi, const double *start, const double *end,
                     const double *goal_rows, uint8_t *done, double *info, void *stream);
 
-/* Same as omgb_chomp_step with HOST buffers (pinned or pageable): copies xi/start/end/goal_rows to the
- * scene's staging buffers, runs the step, copies xi and info back, synchronises the stream. */
+/* Same as omgb_chomp_step with HOST buffers (pinned or pageable); xi and info are valid on return (the stream is
+ * synchronised).  Transfer strategy: omgb_scene_set_host_mode. */
 int omgb_chomp_step_host(omgb_scene_t *scene, const omgb_step_params_t *params, int batch, double *h_xi,
                          const double *h_start, const double *h_end, const double *h_goal_rows,
                          double *h_info, void *stream);

@@ -488,13 +488,21 @@ __global__ void __launch_bounds__(THREADS, MINB) chomp_step_kernel(const StepArg
 #define OMGB_PROF(slot) do { if (a.prof && tid == 0) a.prof[(size_t)b * 16 + (slot)] = clock64(); } while (0)
     OMGB_PROF(0);
     // ---- phase 0: stage ---------------------------------------------------------------------------
+    // xi, start, end and the goal rows may live in mapped pinned HOST memory (omgb_chomp_step_host, zero-copy): every
+    // load of them is a PCIe round trip, so all of a thread's loads are issued back to back into registers before
+    // the first dependent store (s_xi, s_start, s_end, s_goal are contiguous in shared memory, in this order), and
+    // the device-memory staging below runs while they are in flight.
     double *g_xi = a.xi + (size_t)b * n * ND;
-    for (int k = tid; k < n * ND; k += nthr) s_xi[k] = g_xi[k];
-    if (tid < ND) {
-        s_start[tid] = a.start[(size_t)b * ND + tid];
-        s_end[tid] = a.end[(size_t)b * ND + tid];
-    }
-    for (int k = tid; k < c * ND; k += nthr) s_goal[k] = a.goal_rows[(size_t)b * c * ND + k];
+    const int n_x = n * ND, n_in = n_x + 2 * ND + c * ND;
+    auto stage_src = [&](int k) -> const double * {
+        if (k < n_x) return g_xi + k;
+        if (k < n_x + ND) return a.start + (size_t)b * ND + (k - n_x);
+        if (k < n_x + 2 * ND) return a.end + (size_t)b * ND + (k - n_x - ND);
+        return a.goal_rows + (size_t)b * c * ND + (k - n_x - 2 * ND);
+    };
+    double stg0 = 0.0, stg1 = 0.0;
+    if (tid < n_in) stg0 = *stage_src(tid);
+    if (tid + nthr < n_in) stg1 = *stage_src(tid + nthr);
     {
         const int words = (int)(sizeof(ObjRec) / 4) * O;
         const uint32_t *src = reinterpret_cast<const uint32_t *>(a.objs);
@@ -502,6 +510,9 @@ __global__ void __launch_bounds__(THREADS, MINB) chomp_step_kernel(const StepArg
         for (int k = tid; k < words; k += nthr) dst[k] = src[k];
     }
     for (int k = tid; k < n_li; k += nthr) { s_best[k] = 0.0f; s_bestp[k] = 0; }
+    if (tid < n_in) s_xi[tid] = stg0;
+    if (tid + nthr < n_in) s_xi[tid + nthr] = stg1;
+    for (int k = tid + 2 * nthr; k < n_in; k += nthr) s_xi[k] = *stage_src(k);   // (long trajectories)
     __syncthreads();
 
     OMGB_PROF(1);
@@ -973,7 +984,7 @@ __global__ void __launch_bounds__(THREADS, MINB) chomp_step_kernel(const StepArg
     }
     OMGB_PROF(11);
     if (tid == 0) {
-        double *inf = a.info + (size_t)b * OMGB_INFO_STRIDE;
+        double *inf = s_red;   // staged in shared memory, written as one coalesced 128-byte row below
         inf[OMGB_INFO_OBS] = obs_sum;
         inf[OMGB_INFO_SMOOTH] = smooth_sum;
         inf[OMGB_INFO_COST] = prm.obstacle_weight * obs_sum + prm.smoothness_weight * smooth_sum;
@@ -995,6 +1006,8 @@ __global__ void __launch_bounds__(THREADS, MINB) chomp_step_kernel(const StepArg
         if (a.done && a.stop_on_terminate && terminate && a.iteration > 0) a.done[b] = 1;
         if (a.cta_cost) a.cta_cost[b] = (int)min((long long)0x7fffffff, clock64() - t_begin);
     }
+    __syncwarp();
+    if (tid < OMGB_INFO_STRIDE) a.info[(size_t)b * OMGB_INFO_STRIDE + tid] = s_red[tid];
 }
 
 }  // namespace omgb

@@ -121,8 +121,10 @@ class ChompEngine(object):
 
     # ---- parameters -------------------------------------------------------------------------------
     @staticmethod
-    def params_from(cfg, update=True):
-        p = _lib.StepParams()
+    def params_from(cfg, update=True, into=None, lsw_cache=None):
+        """omgb_step_params_t snapshot of cfg.  `into`/`lsw_cache`: reuse a struct across calls (the per-call
+        cost matters at ~0.1 ms per fused step)."""
+        p = _lib.StepParams() if into is None else into
         p.n_waypoints = int(cfg.timesteps)
         p.goal_set_proj = int(bool(cfg.goal_set_proj))
         p.constraint_rows = int(cfg.constraint_rows)
@@ -139,8 +141,14 @@ class ChompEngine(object):
         p.step_size = float(cfg.step_size)
         p.clip_grad_scale = float(cfg.clip_grad_scale)
         p.terminate_smooth_loss = float(cfg.terminate_smooth_loss)
+        lsw = cfg.link_smooth_weight
+        if lsw_cache is not None and lsw_cache.get("obj") is lsw and lsw_cache.get("bytes") == getattr(lsw, "tobytes", bytes)():
+            return p
+        flat = np.asarray(lsw, dtype=np.float64).reshape(-1)
         for d in range(9):
-            p.link_smooth_weight[d] = float(np.asarray(cfg.link_smooth_weight).reshape(-1)[d])
+            p.link_smooth_weight[d] = float(flat[d])
+        if lsw_cache is not None and isinstance(lsw, np.ndarray):
+            lsw_cache["obj"], lsw_cache["bytes"] = lsw, lsw.tobytes()
         return p
 
     # ---- hot path ---------------------------------------------------------------------------------
@@ -193,17 +201,35 @@ class ChompEngine(object):
                    "omgb_chomp_plan")
         return {"info": info, "done": done}
 
-    def step_host(self, cfg, xi, start, end, goal_rows=None):
-        """Reference-facing call with HOST numpy buffers: H2D + fused step + D2H inside (xi updated in place)."""
+    def set_host_mode(self, mode):
+        """0 auto (zero-copy on mapped pinned buffers, else pipelined staging), 1 staged, 2 staged + pipelined,
+        3 zero-copy required (omgb_scene_set_host_mode)."""
+        _lib.check(self.L.omgb_scene_set_host_mode(self._h, int(mode)), "omgb_scene_set_host_mode")
+
+    def step_host(self, cfg, xi, start, end, goal_rows=None, info=None):
+        """Reference-facing call with HOST numpy buffers (xi updated in place, info returned).  With pinned
+        buffers (torch .pin_memory() / cudaHostRegister) the fused kernel reads and writes them directly over PCIe;
+        pageable buffers go through pipelined staged copies.  `info`: optional [B,16] fp64 output buffer; by default
+        a pinned buffer owned by the engine is reused (valid until the next call)."""
         self.set_metric(cfg)
         B, n, c = xi.shape[0], cfg.timesteps, cfg.constraint_rows
         for a, shp in ((xi, (B, n, 9)), (start, (B, 9)), (end, (B, 9))):
             if not (a.dtype == np.float64 and a.flags["C_CONTIGUOUS"] and a.shape == shp):
                 raise RuntimeError("step_host buffers must be C-contiguous fp64 numpy arrays")
-        info = np.empty((B, _lib.INFO_STRIDE), dtype=np.float64)
-        prm = self.params_from(cfg, True)
-        _lib.check(self.L.omgb_chomp_step_host(self._h, ctypes.byref(prm), B, _hp(xi), _hp(start), _hp(end),
-                                               _hp(goal_rows) if c > 0 else None, _hp(info), _stream()),
+        if info is None:
+            buf = self._keep.get("host_info")
+            if buf is None or buf.shape[0] != B:
+                buf = torch.empty((B, _lib.INFO_STRIDE), dtype=torch.float64).pin_memory()
+                self._keep["host_info"] = buf
+                self._keep["host_info_np"] = buf.numpy()
+            info = self._keep["host_info_np"]
+        if "host_prm" not in self._keep:
+            self._keep["host_prm"], self._keep["host_lsw"] = _lib.StepParams(), {}
+        prm = self.params_from(cfg, True, into=self._keep["host_prm"], lsw_cache=self._keep["host_lsw"])
+        ptr = lambda a: a.__array_interface__["data"][0]
+        _lib.check(self.L.omgb_chomp_step_host(self._h, ctypes.byref(prm), B, ptr(xi), ptr(start), ptr(end),
+                                               ptr(goal_rows) if c > 0 else None, ptr(info),
+                                               torch.cuda.current_stream().cuda_stream),
                    "omgb_chomp_step_host")
         return info
 

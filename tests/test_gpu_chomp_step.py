@@ -160,3 +160,34 @@ def test_plan_equals_repeated_steps_and_host_entry_point():
     for b in range(7):
         expect = hist25[b, first[b] + 1] if first[b] >= 0 else hist25[b, -1]
         np.testing.assert_array_equal(x[b].cpu().numpy(), expect)
+
+
+def test_host_entry_transfer_modes_agree():
+    """omgb_chomp_step_host: zero-copy on mapped pinned buffers, staged, staged + pipelined over chunks and
+    pageable buffers all produce the device-resident step's numbers bit for bit."""
+    mode = H.MODES["goalset_standoff_topk"]
+    sc = S.make_scene(num_objects=6, grid=48, seed=11, grid_choices=[32, 40, 48])
+    cfg = ChompConfig(**mode)
+    robot = PandaConstants()
+    B = 600   # > 2 x 256: the pipelined path splits it into 2 chunks
+    xi, st, en, tails = S.make_trajectories(B, 30, robot.joint_lower_limit, robot.joint_upper_limit, seed=5)
+    eng = H.engine_for(sc, cfg, robot)
+    hist, infos, _ = _run_gpu(eng, cfg, xi, st, en, tails, 3)
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+    for host_mode, pinned in ((0, True), (3, True), (1, True), (2, True), (0, False), (2, False)):
+        eng.set_host_mode(host_mode)
+        if pinned:
+            keep = [pin(xi), pin(st), pin(en), pin(tails)]
+            xh, sh, eh, th = (k.numpy() for k in keep)
+        else:
+            xh, sh, eh, th = xi.copy(), np.ascontiguousarray(st), np.ascontiguousarray(en), np.ascontiguousarray(tails)
+        for it in range(3):
+            cfg.obstacle_weight, cfg.smoothness_weight, cfg.step_size = cfg.schedule(it + 1)
+            info = eng.step_host(cfg, xh, sh, eh, th)
+        np.testing.assert_array_equal(xh, hist[:, -1], err_msg="mode %d pinned %s" % (host_mode, pinned))
+        np.testing.assert_array_equal(np.array(info), infos[:, -1])
+    eng.set_host_mode(3)   # zero-copy required, pageable buffers -> error, never a silent fallback
+    with pytest.raises(RuntimeError):
+        eng.step_host(cfg, xi.copy(), np.ascontiguousarray(st), np.ascontiguousarray(en), np.ascontiguousarray(tails),
+                      info=np.empty((B, 16)))
+    eng.set_host_mode(0)
