@@ -29,7 +29,7 @@ class ChompConfig(object):
         use_standoff=True, pre_terminate=True, uncheck_finger_collision=0, allow_collision_point=5,
         soft_joint_limit_padding=0.2, clip_grad_scale=10.0, consider_finger=False, reach_tail_length=5,
         timesteps=30, time_interval=0.1, report_cost=False, report_time=False, timeout=-1.0,
-        base_link="panda_link0")
+        base_link="panda_link0", ol_alg="MD", dist_eps=0.1, normalize_cost=True, traj_init="grasp")
 
     def __init__(self, **kw):
         for k, v in self._DEFAULTS.items():

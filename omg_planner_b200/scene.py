@@ -150,3 +150,28 @@ def make_trajectories(batch, n, lower, upper, seed=0, tail=5):
         xi[b] = clamped_cubic(START_CONF, end, n)
     starts = np.tile(START_CONF, (batch, 1))
     return xi, starts, ends, tails
+
+
+def make_goal_sets(batch, num_goals, lower, upper, seed=0, tail=5, spread=0.6):
+    """Synthetic goal sets (stand-in for the IK solutions of the target's grasps, omg/planner.py:296-455):
+    per trajectory G goal configurations scattered around a seed goal inside the padded limits, plus for each the
+    `tail` standoff rows approaching it (reach_grasps[g], [c,9]).  Returns goals [B,G,9], reach [B,G,tail,9]."""
+    lower = np.asarray(lower, dtype=np.float64).reshape(-1)
+    upper = np.asarray(upper, dtype=np.float64).reshape(-1)
+    goals = np.zeros((batch, num_goals, 9)); reach = np.zeros((batch, num_goals, tail, 9))
+    for b in range(batch):
+        rng = np.random.RandomState(104729 * seed + b)
+        centre = rng.uniform(lower[:7] + 0.3, upper[:7] - 0.3)
+        for g in range(num_goals):
+            end = START_CONF.copy()
+            end[:7] = np.clip(centre + rng.uniform(-spread, spread, 7), lower[:7] + 0.05, upper[:7] - 0.05)
+            u = end - START_CONF
+            u = u / (np.linalg.norm(u) + 1e-12)
+            for k in range(tail):
+                row = end - (tail - 1 - k) / max(tail - 1, 1) * 0.15 * u
+                row[:7] = np.clip(row[:7], lower[:7] + 0.01, upper[:7] - 0.01)
+                row[7:] = 0.04
+                reach[b, g, k] = row
+            reach[b, g, -1] = end
+            goals[b, g] = end
+    return goals, reach

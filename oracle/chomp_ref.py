@@ -64,6 +64,11 @@ class RefConfig(object):
         self.reach_tail_length = 5
         self.timesteps = 30
         self.time_interval = 0.1
+        # goal selection (omg/config.py:39,67,68,79)
+        self.optim_steps = 50
+        self.ol_alg = "MD"
+        self.dist_eps = 0.1
+        self.normalize_cost = True
         for k, v in kw.items():
             if not hasattr(self, k):
                 raise AttributeError(k)

@@ -138,6 +138,7 @@ def load_reference(sdf_forward=None):
     ns.util = importlib.import_module("omg.util")
     ns.cost = importlib.import_module("omg.cost")
     ns.optimizer = importlib.import_module("omg.optimizer")
+    ns.online_learner = importlib.import_module("omg.online_learner")
     ns.robot_pykdl = importlib.import_module("ycb_render.robotPose.robot_pykdl")
     ns.cfg = ns.config.cfg
     _loaded["ns"] = ns
@@ -183,6 +184,10 @@ class RefTrajectory(object):
 
     def set(self, new_traj):  # omg/core.py:53-57
         self.data = new_traj
+
+    def interpolate_waypoints(self, waypoints=None, mode="cubic"):  # omg/core.py:59-78 (dynamic_timestep off)
+        self.data = self.ns.util.interpolate_waypoints(np.stack([self.start, self.end]), self.ns.cfg.timesteps,
+                                                       self.start.shape[0], mode=mode)
 
 
 def make_ref_env(ns, scene, body_points):
