@@ -18,6 +18,8 @@
  *   omgb_chomp_plan            the fixed-goal inner loop of plan()  omg/planner.py:612-627
  *   omgb_chomp_step_host       same as omgb_chomp_step, HOST buffers (H2D + D2H inside the call)
  *   omgb_batch_obstacle_cost   Cost.batch_obstacle_cost             omg/cost.py:192-286
+ *   omgb_goal_costs            Learner.cost_vector, device half     omg/online_learner.py:104-150 (omg/util.py:261-290,
+ *                                                                   omg/cost.py:192-286 with arc_length, the two sums)
  */
 #ifndef OMGB200_H_
 #define OMGB200_H_
@@ -181,6 +183,18 @@ int omgb_chomp_step_host(omgb_scene_t *scene, const omgb_step_params_t *params, 
 int omgb_batch_obstacle_cost(omgb_scene_t *scene, const double *joints, int num_configs, int arc_length,
                              const double *start, double time_interval, int uncheck_finger_collision,
                              float *potentials, float *grads, float *collides, void *stream);
+
+/* Goal scoring for the online learner (omg/online_learner.py:104-150), fused: for every trajectory b and goal g,
+ *   costs[b,g] = sum over i < arc_length, links, body points of  potential(x_i) * |x_i - x_{i-1}| / dt
+ * where the configurations q_i, i = 0..arc_length-1, are the interior points of the joint-space line from
+ * from[b] (= traj.data[start], q_{-1}) to goals[b,g] (multi_interpolate_waypoints, mode "linear") and x are the
+ * body points under forward kinematics.  from: DEVICE rows of 9 fp64, row b at from + b*from_stride (pass
+ * xi + start*9 with from_stride = n*9 to score from waypoint `start` of every trajectory in xi [B,n,9]);
+ * goals: DEVICE [B,G,9] fp64, or [G,9] shared by all trajectories when goals_shared != 0; costs: DEVICE [B,G] fp32.
+ * The Learner passes uncheck_finger_collision = 0 (online_learner.py:138). */
+int omgb_goal_costs(omgb_scene_t *scene, int batch, const double *from, long long from_stride, const double *goals,
+                    int num_goals, int goals_shared, int arc_length, double time_interval,
+                    int uncheck_finger_collision, float *costs, void *stream);
 
 #ifdef __cplusplus
 }

@@ -7,7 +7,8 @@ import subprocess
 _HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(_HERE)
 LIB_PATH = os.path.join(_HERE, "lib", "libomgb200.so")
-SOURCES = [os.path.join(_HERE, "csrc", f) for f in ("omgb200.cu", "chomp_kernels.cuh", "sdf_device.cuh")] + [
+SOURCES = [os.path.join(_HERE, "csrc", f) for f in ("omgb200.cu", "chomp_kernels.cuh", "goal_kernels.cuh",
+                                                     "sdf_device.cuh")] + [
     os.path.join(ROOT, "include", "omgb200.h")]
 
 INFO_STRIDE = 16
@@ -18,7 +19,7 @@ INFO_KEYS = ["obs", "smooth", "cost", "collide", "reach", "grad", "weighted_obs_
 EXPORTS = ["omgb_version", "omgb_last_error", "omgb_scene_create", "omgb_scene_destroy", "omgb_scene_set_robot",
            "omgb_scene_set_sdf", "omgb_scene_set_profile", "omgb_scene_set_options", "omgb_scene_set_host_mode", "omgb_launch_count", "omgb_scene_set_objects", "omgb_scene_set_metric",
            "omgb_sdf_loss_workspace_bytes", "omgb_sdf_loss", "omgb_chomp_step", "omgb_chomp_plan",
-           "omgb_chomp_step_host", "omgb_batch_obstacle_cost"]
+           "omgb_chomp_step_host", "omgb_batch_obstacle_cost", "omgb_goal_costs"]
 
 
 class StepParams(ctypes.Structure):
@@ -84,6 +85,7 @@ def lib():
     L.omgb_chomp_plan.argtypes = [vp, ctypes.POINTER(StepParams), ci, vp, vp, vp, ci, ci] + [vp] * 7
     L.omgb_chomp_step_host.argtypes = [vp, ctypes.POINTER(StepParams), ci] + [vp] * 6
     L.omgb_batch_obstacle_cost.argtypes = [vp, vp, ci, ci, vp, cd, ci, vp, vp, vp, vp]
+    L.omgb_goal_costs.argtypes = [vp, ci, vp, ctypes.c_longlong, vp, ci, ci, ci, cd, ci, vp, vp]
     for name in EXPORTS:
         fn = getattr(L, name)
         if name not in ("omgb_version", "omgb_last_error", "omgb_sdf_loss_workspace_bytes", "omgb_launch_count"):

@@ -93,18 +93,21 @@ class Cost(object):
         batched = data.ndim == 3
         xi = torch.from_numpy(np.ascontiguousarray(data if batched else data[None])).to(dev)
         B = xi.shape[0]
-        bc = lambda a: torch.from_numpy(np.ascontiguousarray(
+        bc = lambda a: torch.from_numpy(np.array(
             np.broadcast_to(np.asarray(a, dtype=np.float64).reshape((-1, 9))[-B:] if np.ndim(a) > 1
                             else np.asarray(a, dtype=np.float64)[None], (B, 9)))).to(dev)
         start, end = bc(traj.start), bc(traj.end)
         rows = None
         if self.cfg.goal_set_proj:
             c = self.engine_cfg().constraint_rows
-            if self.cfg.use_standoff:   # omg/optimizer.py:93-98
-                goal = np.asarray(self.target_obj.reach_grasps)[np.atleast_1d(traj.goal_idx).astype(int)]
+            idx = np.atleast_1d(traj.goal_idx).astype(int)
+            if self.cfg.use_standoff:   # omg/optimizer.py:93-98; batched: reach_grasps [B,G,c,9], goal_idx [B]
+                rg = np.asarray(self.target_obj.reach_grasps)
+                goal = rg[np.arange(B), idx] if rg.ndim == 4 else rg[idx]
             else:
-                goal = np.asarray(traj.goal_set)[np.atleast_1d(traj.goal_idx).astype(int)][:, None]
-            rows = torch.from_numpy(np.ascontiguousarray(np.broadcast_to(goal, (B, c, 9)), dtype=np.float64)).to(dev)
+                gs = np.asarray(traj.goal_set)
+                goal = (gs[np.arange(B), idx] if gs.ndim == 3 else gs[idx])[:, None]
+            rows = torch.from_numpy(np.array(np.broadcast_to(goal, (B, c, 9)), dtype=np.float64)).to(dev)
         return xi, start, end, rows, batched
 
     def engine_cfg(self):
@@ -211,6 +214,20 @@ class Cost(object):
             vis_pts[:, :m, :, 6] = pot.detach().cpu().numpy()
             vis_pts[:, :m, :, 9:] = grad.detach().cpu().numpy()
         return pot, grad, col
+
+    def goal_costs(self, data, first, goals, uncheck_finger_collision=0):
+        """The device half of Learner.cost_vector (omg/online_learner.py:123-150) in one fused launch:
+        data [B,n,9] (traj.data), `first` the waypoint the straight lines start from, goals [B,G,9] or [1,G,9] /
+        [G,9] (shared) -> numpy fp32 [B,G] = sum of potential x workspace speed along each line."""
+        self.sync()
+        dev = self.engine.device
+        xi = torch.from_numpy(np.ascontiguousarray(np.asarray(data, dtype=np.float64))).to(dev)
+        g = np.asarray(goals, dtype=np.float64)
+        if g.ndim == 3 and g.shape[0] == 1 and xi.shape[0] > 1:
+            g = g[0]
+        g = torch.from_numpy(np.ascontiguousarray(g)).to(dev)
+        return self.engine.goal_costs(xi, int(first), g, float(self.cfg.time_interval),
+                                      uncheck_finger_collision).cpu().numpy()
 
     def batch_obstacle_cost(self, joints, arc_length=-1, only_collide=False, special_check_id=0,
                             uncheck_finger_collision=-1, start=None, end=None):

@@ -10,6 +10,7 @@
 
 #include "../../include/omgb200.h"
 #include "chomp_kernels.cuh"
+#include "goal_kernels.cuh"
 #include "sdf_device.cuh"
 
 namespace omgb {
@@ -943,6 +944,49 @@ extern "C" int omgb_batch_obstacle_cost(omgb_scene_t *s, const double *joints, i
         s->d_objs, s->num_objects, s->d_grids, s->d_robot, joints, num_configs, arc_length, start,
         arc_length > 0 ? (float)(1.0 / time_interval) : 0.0f, uncheck_finger_collision == -1 ? 1 : 0, potentials,
         grads, collides);
+    OMGB_CUDA(cudaGetLastError());
+    return OMGB_OK;
+}
+
+// ----------------------------------------------------------------------------------------------------
+// goal scoring (device half of Learner.cost_vector)
+// ----------------------------------------------------------------------------------------------------
+extern "C" int omgb_goal_costs(omgb_scene_t *s, int batch, const double *from, long long from_stride,
+                               const double *goals, int num_goals, int goals_shared, int arc_length,
+                               double time_interval, int uncheck_finger_collision, float *costs, void *stream) {
+    if (!s) return fail(OMGB_ERR_INVALID, "omgb_goal_costs: null scene");
+    if (!s->robot_set || !s->sdf_set || !s->objs_set)
+        return fail(OMGB_ERR_STATE, "omgb_goal_costs: scene needs robot, sdf and objects");
+    if (batch < 0 || num_goals < 0) return fail(OMGB_ERR_INVALID, "omgb_goal_costs: negative size");
+    if (batch == 0 || num_goals == 0) return OMGB_OK;
+    if (!from || !goals || !costs) return fail(OMGB_ERR_INVALID, "omgb_goal_costs: null buffer");
+    if (arc_length < 1 || !(time_interval > 0) || from_stride < ND)
+        return fail(OMGB_ERR_INVALID, "omgb_goal_costs: arc_length >= 1, time_interval > 0 and from_stride >= 9 required");
+    if ((long long)batch * num_goals > 0x7fffffffLL) return fail(OMGB_ERR_INVALID, "omgb_goal_costs: batch x goals too large");
+    OMGB_CUDA(cudaSetDevice(s->device));
+    GoalArgs a;
+    memset(&a, 0, sizeof(a));
+    a.objs = s->d_objs; a.grids = s->d_grids; a.robot = s->d_robot;
+    a.from = from; a.from_stride = from_stride;
+    a.goals = goals; a.goal_stride_b = goals_shared ? 0 : (long long)num_goals * ND;
+    a.costs = costs;
+    a.dil = s->dil;
+    a.rp = s->rp;
+    a.num_objects = s->num_objects; a.num_goals = num_goals; a.arc = arc_length;
+    a.finger_soft = uncheck_finger_collision == -1 ? 1 : 0;
+    a.inv_dt = (float)(1.0 / time_interval);
+    goal_layout(a);
+    if (a.smem_total > (unsigned)s->smem_optin)
+        return fail(OMGB_ERR_UNSUPPORTED, "omgb_goal_costs: arc_length too long for one CTA's shared memory");
+    constexpr int THREADS = 256;
+    static unsigned cached[64] = {0};
+    if (s->device >= 64 || cached[s->device] < a.smem_total) {
+        OMGB_CUDA(cudaFuncSetAttribute(goal_cost_kernel<THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)a.smem_total));
+        if (s->device < 64) cached[s->device] = a.smem_total;
+    }
+    goal_cost_kernel<THREADS><<<batch * num_goals, THREADS, a.smem_total, (cudaStream_t)stream>>>(a);
+    ++g_launches;
     OMGB_CUDA(cudaGetLastError());
     return OMGB_OK;
 }

@@ -233,6 +233,22 @@ class ChompEngine(object):
                    "omgb_chomp_step_host")
         return info
 
+    def goal_costs(self, xi, first, goals, time_interval=0.1, uncheck_finger_collision=0):
+        """Device half of Learner.cost_vector (omg/online_learner.py:104-150) for a batch: xi [B,n,9] fp64 CUDA,
+        `first` = the waypoint the lines start from, goals [B,G,9] or [G,9] fp64 CUDA -> costs [B,G] fp32 CUDA."""
+        B, n = xi.shape[0], xi.shape[1]
+        self._check64(xi, (B, n, 9), "xi")
+        shared = goals.dim() == 2
+        G = goals.shape[-2]
+        self._check64(goals, (G, 9) if shared else (B, G, 9), "goals")
+        if not 0 <= first < n:
+            raise RuntimeError("first waypoint out of range")
+        costs = torch.empty((B, G), dtype=torch.float32, device=xi.device)
+        _lib.check(self.L.omgb_goal_costs(self._h, B, _vp(xi.data_ptr() + 8 * 9 * first), n * 9, _dp(goals), G,
+                                          int(shared), n - first, float(time_interval), int(uncheck_finger_collision),
+                                          _dp(costs), _stream()), "omgb_goal_costs")
+        return costs
+
     def batch_obstacle_cost(self, joints, arc_length=-1, start=None, time_interval=0.1,
                             uncheck_finger_collision=-1, want_grad=True):
         M = joints.shape[0]
