@@ -126,6 +126,8 @@ struct StepArgs {
     RobotParams rp;
     int num_objects;
     int batch;
+    int metric_kind;         // 0: dense Ainv; 1: Ainv = s*min(i,j) (goal-set, free end); 2: s*min(i,j)(n+1-max(i,j))/(n+1)
+    double metric_scale;     // s (= dt^2)
     int iteration;           // index inside a plan (for the t > 0 rule of planner.py:627)
     int stop_on_terminate;
     omgb_step_params_t prm;
@@ -249,6 +251,7 @@ __device__ __forceinline__ void panda_fk_row(const RobotParams &rc, const double
                                              double *frames) {
     Row T;
     T.a = (r == 0) ? 1.0 : 0.0; T.b = (r == 1) ? 1.0 : 0.0; T.c = (r == 2) ? 1.0 : 0.0; T.t = 0.0;
+    // (not unrolled: measured, the fully unrolled chain spills at the 64-register cap and the phase gets 40% slower)
 #pragma unroll 1
     for (int i = 0; i < 7; ++i) {
         const Row N = row_mul(T, rc.P0[i]);
@@ -351,17 +354,17 @@ enum { PAIR_EXACT = 0, PAIR_FAR = 1, PAIR_OUT = 2, PAIR_LOAD = 3 };
 // Stage 1: no memory access.  Returns PAIR_EXACT / PAIR_OUT, or PAIR_LOAD with the lower-bound entry to read.
 __device__ __forceinline__ int classify_prepare(const ObjRec &ob, const DilDesc &dd, int oi, float x, float y,
                                                 float z, const float *&addr) {
-    const float qx = fmaf(ob.r[0], x, fmaf(ob.r[1], y, fmaf(ob.r[2], z, ob.tx)));
-    const float qy = fmaf(ob.r[3], x, fmaf(ob.r[4], y, fmaf(ob.r[5], z, ob.ty)));
-    const float qz = fmaf(ob.r[6], x, fmaf(ob.r[7], y, fmaf(ob.r[8], z, ob.tz)));
-    const float gx = (qx - ob.minx) * ob.isx, gy = (qy - ob.miny) * ob.isy, gz = (qz - ob.minz) * ob.isz;
+    (void)oi;
+    const float gx = fmaf(ob.ga[0], x, fmaf(ob.ga[1], y, fmaf(ob.ga[2], z, ob.ga[3])));
+    const float gy = fmaf(ob.ga[4], x, fmaf(ob.ga[5], y, fmaf(ob.ga[6], z, ob.ga[7])));
+    const float gz = fmaf(ob.ga[8], x, fmaf(ob.ga[9], y, fmaf(ob.ga[10], z, ob.ga[11])));
     // in bounds <=> g in (-0.5, d - 0.5) on every axis (cell_of + the x1 < dim test of kernel.cu:47)
     const bool outside = (gx < -0.75f) | (gx > ob.fd0 - 0.25f) | (gy < -0.75f) | (gy > ob.fd1 - 0.25f) |
                          (gz < -0.75f) | (gz > ob.fd2 - 0.25f);
     const bool interior = (gx >= 1.5f) & (gx <= ob.fd0 - 1.5f) & (gy >= 1.5f) & (gy <= ob.fd1 - 1.5f) &
                           (gz >= 1.5f) & (gz <= ob.fd2 - 1.5f);
     const int ix = interior ? ((int)gx) >> 1 : 0, iy = interior ? ((int)gy) >> 1 : 0, iz = interior ? ((int)gz) >> 1 : 0;
-    addr = dd.data + (size_t)oi * dd.obj_stride + ((size_t)ix * dd.by + iy) * dd.bz + iz;
+    addr = dd.data + (ob.dil_off + (ix * dd.by + iy) * dd.bz + iz);   // 32-bit index (checked when the grid is built)
     if (outside) return (ob.cull_pad < 1e29f) ? PAIR_OUT : PAIR_EXACT;
     return interior ? PAIR_LOAD : PAIR_EXACT;
 }
@@ -416,15 +419,19 @@ __device__ __forceinline__ void winners_pass(const WinCtx &c) {
         xform(Fn, b0, b1, b2, xn, yn, zn);
         const float x = (float)X, y = (float)Y, z = (float)Z;
         float pot = 0.0f, gx = 0.0f, gy = 0.0f, gz = 0.0f;
-        unsigned long long m = c.mask[li];
-        while (m) {
-            const int o = __ffsll((long long)m) - 1;
-            m &= m - 1;
-            if (c.use_dil && classify_pair(c.objs[o], *c.dil, o, x, y, z) != PAIR_EXACT) continue;
-            float po, ax, ay, az, co;
-            pair_full_group<G>(c.objs[o], c.grids, gm, l, x, y, z, po, ax, ay, az, co);
-            pot = __fadd_rn(pot, po);
-            gx = __fadd_rn(gx, ax); gy = __fadd_rn(gy, ay); gz = __fadd_rn(gz, az);
+        const unsigned long long m64 = c.mask[li];
+#pragma unroll 1
+        for (int half = 0; half < 2; ++half) {   // 64-bit object mask walked as two 32-bit words (cheaper bit ops)
+            unsigned m = half ? (unsigned)(m64 >> 32) : (unsigned)m64;
+            while (m) {
+                const int o = __ffs(m) - 1 + 32 * half;
+                m &= m - 1;
+                if (c.use_dil && classify_pair(c.objs[o], *c.dil, o, x, y, z) != PAIR_EXACT) continue;
+                float po, ax, ay, az, co;
+                pair_full_group<G>(c.objs[o], c.grids, gm, l, x, y, z, po, ax, ay, az, co);
+                pot = __fadd_rn(pot, po);
+                gx = __fadd_rn(gx, ax); gy = __fadd_rn(gy, ay); gz = __fadd_rn(gz, az);
+            }
         }
         if (c.finger_soft && j >= 8) {
             pot = __fmul_rn(pot, 0.1f); gx = __fmul_rn(gx, 0.1f); gy = __fmul_rn(gy, 0.1f); gz = __fmul_rn(gz, 0.1f);
@@ -435,6 +442,57 @@ __device__ __forceinline__ void winners_pass(const WinCtx &c) {
         for (int s = l; s < NS; s += G)
             c.lg[(size_t)li * NS + s] = fg_slot(c.rc, c.frames + (size_t)i * NL * 12, j, s, X, Y, Z, wx, wy, wz);
     }
+}
+
+// dst = Ainv * src for [n][9] arrays in shared memory (all threads call; ends with a barrier).  The smoothness metric
+// A = K^T K is tridiagonal, so its inverse has the closed forms above and Ainv * g is two running
+// sums per DOF column instead of a dense n x n product: 9 threads scan, everyone combines.  tmp: [2][n][9] scratch.
+__device__ __forceinline__ void metric_apply(const StepArgs &a, int n, const double *src, double *dst, double *tmp) {
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    if (a.metric_kind == 0) {
+        for (int k = tid; k < n * ND; k += nthr) {
+            const int i = k / ND, d = k - i * ND;
+            const double *Ar = a.Ainv + (size_t)i * n;
+            double acc = 0.0;
+            for (int r = 0; r < n; ++r) acc = fma(__ldg(Ar + r), src[r * ND + d], acc);
+            dst[k] = acc;
+        }
+        __syncthreads();
+        return;
+    }
+    double *P = tmp, *S = tmp + n * ND;   // P_i = sum_{j<=i} j g_j, S_i = sum_{j<=i} g_j  (1-based i, j)
+    {   // one warp per DOF column: shuffle scans over the waypoints, 32 at a time with a carry
+        const int lane = tid & 31, warp = tid >> 5, nwarps = nthr >> 5;
+        for (int d = warp; d < ND; d += nwarps) {
+            double carry_p = 0.0, carry_s = 0.0;
+            for (int base = 0; base < n; base += 32) {
+                const int i = base + lane;
+                const double g = (i < n) ? src[i * ND + d] : 0.0;
+                double p = (double)(i + 1) * g, sa = g;
+#pragma unroll
+                for (int off = 1; off < 32; off <<= 1) {
+                    const double tp = __shfl_up_sync(0xffffffffu, p, off), ts = __shfl_up_sync(0xffffffffu, sa, off);
+                    if (lane >= off) { p += tp; sa += ts; }
+                }
+                p += carry_p; sa += carry_s;
+                if (i < n) { P[i * ND + d] = p; S[i * ND + d] = sa; }
+                carry_p = __shfl_sync(0xffffffffu, p, 31); carry_s = __shfl_sync(0xffffffffu, sa, 31);
+            }
+        }
+    }
+    __syncthreads();
+    const double np1 = (double)(n + 1);
+    for (int k = tid; k < n * ND; k += nthr) {
+        const int i = k / ND, d = k - i * ND;
+        const double ii = (double)(i + 1);
+        const double Pn = P[(n - 1) * ND + d], Sn = S[(n - 1) * ND + d];
+        const double tailS = Sn - S[k];
+        double v;
+        if (a.metric_kind == 1) v = P[k] + ii * tailS;
+        else v = ((np1 - ii) * P[k] + ii * (np1 * tailS - (Pn - P[k]))) / np1;
+        dst[k] = a.metric_scale * v;
+    }
+    __syncthreads();
 }
 
 // ----------------------------------------------------------------------------------------------------
@@ -487,6 +545,14 @@ __global__ void __launch_bounds__(THREADS, MINB) chomp_step_kernel(const StepArg
 
 #define OMGB_PROF(slot) do { if (a.prof && tid == 0) a.prof[(size_t)b * 16 + (slot)] = clock64(); } while (0)
     OMGB_PROF(0);
+    if (a.prof && tid == 0) {   // diagnostic timeline: SM id and global-timer start / end of this CTA
+        unsigned smid;
+        unsigned long long gt;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+        a.prof[(size_t)b * 16 + 13] = (long long)smid;
+        a.prof[(size_t)b * 16 + 14] = (long long)gt;
+    }
     // ---- phase 0: stage ---------------------------------------------------------------------------
     // xi, start, end and the goal rows may live in mapped pinned HOST memory (omgb_chomp_step_host, zero-copy): every
     // load of them is a PCIe round trip, so all of a thread's loads are issued back to back into registers before
@@ -551,6 +617,10 @@ __global__ void __launch_bounds__(THREADS, MINB) chomp_step_kernel(const StepArg
         for (int o = 0; o < O; ++o) {
             const ObjRec &ob = s_objs[o];
             if (ob.dis > 0.0f) continue;
+            {   // first level: link sphere vs the object's world-frame bounding sphere (most pairs end here)
+                const float dx = fx - ob.wsx, dy = fy - ob.wsy, dz = fz - ob.wsz, rr = rad + ob.wsr;
+                if (ob.wsr >= 0.0f && dx * dx + dy * dy + dz * dz > rr * rr) continue;
+            }
             const float qx = ob.r[0] * fx + ob.r[1] * fy + ob.r[2] * fz + ob.tx;
             const float qy = ob.r[3] * fx + ob.r[4] * fy + ob.r[5] * fz + ob.ty;
             const float qz = ob.r[6] * fx + ob.r[7] * fy + ob.r[8] * fz + ob.tz;
@@ -622,31 +692,35 @@ __global__ void __launch_bounds__(THREADS, MINB) chomp_step_kernel(const StepArg
         double X, Y, Z;
         xform(F, bp[0], bp[1], bp[2], X, Y, Z);
         const float x = (float)X, y = (float)Y, z = (float)Z;   // omg/cost.py:136 .float()
-        unsigned long long m = live ? s_mask[li] : 0ull;
+        const unsigned long long m64 = live ? s_mask[li] : 0ull;
         float pot = 0.0f, col = 0.0f, gx = 0.0f, gy = 0.0f, gz = 0.0f;
-        while (m) {
-            const int o = __ffsll((long long)m) - 1;
-            m &= m - 1;
-            float po, co;
-            bool inb;
-            if (use_dil) {
-                const int cls = classify_pair(s_objs[o], a.dil, o, x, y, z);
-                if (cls != PAIR_EXACT) {   // provably contributes nothing
-                    t_pin += (cls == PAIR_FAR) ? 1 : 0;
-                    continue;
+#pragma unroll 1
+        for (int half = 0; half < 2; ++half) {   // 64-bit object mask walked as two 32-bit words (cheaper bit ops)
+            unsigned m = half ? (unsigned)(m64 >> 32) : (unsigned)m64;
+            while (m) {
+                const int o = __ffs(m) - 1 + 32 * half;
+                m &= m - 1;
+                float po, co;
+                bool inb;
+                if (use_dil) {
+                    const int cls = classify_pair(s_objs[o], a.dil, o, x, y, z);
+                    if (cls != PAIR_EXACT) {   // provably contributes nothing
+                        t_pin += (cls == PAIR_FAR) ? 1 : 0;
+                        continue;
+                    }
                 }
+                t_exact += 1;
+                if (topk_mode) {
+                    inb = pair_potential(s_objs[o], a.grids, x, y, z, po, co);
+                } else {
+                    float ax, ay, az;
+                    inb = pair_full(s_objs[o], a.grids, x, y, z, po, ax, ay, az, co);
+                    gx = __fadd_rn(gx, ax); gy = __fadd_rn(gy, ay); gz = __fadd_rn(gz, az);
+                }
+                pot = __fadd_rn(pot, po);
+                col = __fadd_rn(col, co);
+                t_pin += inb ? 1 : 0;
             }
-            t_exact += 1;
-            if (topk_mode) {
-                inb = pair_potential(s_objs[o], a.grids, x, y, z, po, co);
-            } else {
-                float ax, ay, az;
-                inb = pair_full(s_objs[o], a.grids, x, y, z, po, ax, ay, az, co);
-                gx = __fadd_rn(gx, ax); gy = __fadd_rn(gy, ay); gz = __fadd_rn(gz, az);
-            }
-            pot = __fadd_rn(pot, po);
-            col = __fadd_rn(col, co);
-            t_pin += inb ? 1 : 0;
         }
         if (finger_soft && j >= 8) {   // omg/cost.py:350-353
             pot = __fmul_rn(pot, 0.1f); gx = __fmul_rn(gx, 0.1f); gy = __fmul_rn(gy, 0.1f);
@@ -896,14 +970,7 @@ __global__ void __launch_bounds__(THREADS, MINB) chomp_step_kernel(const StepArg
     if (prm.update == 1 || (prm.update == 2 && !terminate)) {
         OMGB_PROF(9);
         // ---- phase 6: covariant update -----------------------------------------------------------
-        for (int k = tid; k < n * ND; k += nthr) {
-            const int i = k / ND, d = k - i * ND;
-            const double *Ar = a.Ainv + (size_t)i * n;
-            double acc = 0.0;
-            for (int r = 0; r < n; ++r) acc = fma(__ldg(Ar + r), s_grad[r * ND + d], acc);
-            s_u[k] = acc;
-        }
-        __syncthreads();
+        metric_apply(a, n, s_grad, s_u, s_viol);   // (s_viol .. s_viol + 2*n*9: scratch, see make_layout)
         for (int k = tid; k < n * ND; k += nthr) {   // + Trajectory.update (core.py:43-51)
             const int i = k / ND, d = k - i * ND;
             double v = s_xi[k];
@@ -966,14 +1033,7 @@ __global__ void __launch_bounds__(THREADS, MINB) chomp_step_kernel(const StepArg
             __syncthreads();
             const double vmax = s_red[40];
             const int kmax = s_hist[260];
-            for (int k = tid; k < n * ND; k += nthr) {
-                const int i = k / ND, d = k - i * ND;
-                const double *Ar = a.Ainv + (size_t)i * n;
-                double acc = 0.0;
-                for (int r = 0; r < n; ++r) acc = fma(__ldg(Ar + r), s_viol[r * ND + d], acc);
-                s_u[k] = acc;
-            }
-            __syncthreads();
+            metric_apply(a, n, s_viol, s_u, s_viol + n * ND);
             const double scale = vmax / (fabs(s_u[kmax]) + 1e-8);
             for (int k = tid; k < n * ND; k += nthr) s_xi[k] += scale * s_u[k];
             ++limit_rounds;
@@ -983,6 +1043,11 @@ __global__ void __launch_bounds__(THREADS, MINB) chomp_step_kernel(const StepArg
         for (int k = tid; k < n * ND; k += nthr) g_xi[k] = s_xi[k];
     }
     OMGB_PROF(11);
+    if (a.prof && tid == 0) {
+        unsigned long long gt;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+        a.prof[(size_t)b * 16 + 15] = (long long)gt;
+    }
     if (tid == 0) {
         double *inf = s_red;   // staged in shared memory, written as one coalesced 128-byte row below
         inf[OMGB_INFO_OBS] = obs_sum;

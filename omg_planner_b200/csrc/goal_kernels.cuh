@@ -109,6 +109,10 @@ __global__ void __launch_bounds__(THREADS) goal_cost_kernel(const GoalArgs a) {
         for (int o = 0; o < O; ++o) {
             const ObjRec &ob = s_objs[o];
             if (ob.dis > 0.0f) continue;
+            {   // first level: link sphere vs the object's world-frame bounding sphere (most pairs end here)
+                const float dx = fx - ob.wsx, dy = fy - ob.wsy, dz = fz - ob.wsz, rr = rad + ob.wsr;
+                if (ob.wsr >= 0.0f && dx * dx + dy * dy + dz * dz > rr * rr) continue;
+            }
             const float qx = ob.r[0] * fx + ob.r[1] * fy + ob.r[2] * fz + ob.tx;
             const float qy = ob.r[3] * fx + ob.r[4] * fy + ob.r[5] * fz + ob.ty;
             const float qz = ob.r[6] * fx + ob.r[7] * fy + ob.r[8] * fz + ob.tz;
@@ -152,13 +156,17 @@ __global__ void __launch_bounds__(THREADS) goal_cost_kernel(const GoalArgs a) {
         xform(F, bp[0], bp[1], bp[2], X, Y, Z);
         const float x = (float)X, y = (float)Y, z = (float)Z;   // omg/cost.py:218 .float()
         float pot = 0.0f;
-        while (m) {
-            const int o = __ffsll((long long)m) - 1;
-            m &= m - 1;
-            if (use_dil && classify_pair(s_objs[o], a.dil, o, x, y, z) != PAIR_EXACT) continue;
-            float po, co;
-            pair_potential(s_objs[o], a.grids, x, y, z, po, co);
-            pot = __fadd_rn(pot, po);
+#pragma unroll 1
+        for (int half = 0; half < 2; ++half) {
+            unsigned mm = half ? (unsigned)(m >> 32) : (unsigned)m;
+            while (mm) {
+                const int o = __ffs(mm) - 1 + 32 * half;
+                mm &= mm - 1;
+                if (use_dil && classify_pair(s_objs[o], a.dil, o, x, y, z) != PAIR_EXACT) continue;
+                float po, co;
+                pair_potential(s_objs[o], a.grids, x, y, z, po, co);
+                pot = __fadd_rn(pot, po);
+            }
         }
         if (a.finger_soft && j >= 8) pot = __fmul_rn(pot, 0.1f);   // omg/cost.py:350-353
         float val = 0.0f;

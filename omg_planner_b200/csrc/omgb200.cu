@@ -38,7 +38,7 @@ static int fail(int code, const std::string &msg) {
 __global__ void prep_objects_kernel(const float *__restrict__ pose, const float *__restrict__ limits,
                                     const float *__restrict__ eps, const float *__restrict__ pad,
                                     const float *__restrict__ clr, const float *__restrict__ dis, int num_objects,
-                                    ObjRec *__restrict__ out) {
+                                    ObjRec *__restrict__ out, long long dil_obj_stride) {
     const int o = blockIdx.x * blockDim.x + threadIdx.x;
     if (o >= num_objects) return;
     const float *P = pose + 16 * o;
@@ -91,7 +91,22 @@ __global__ void prep_objects_kernel(const float *__restrict__ pose, const float 
     // clearance <= 1.  Otherwise the cull must never reject.
     r.cull_pad = (r.eps < 1.0f && r.clr <= 1.0f) ? (1e-3f + fmaxf(sx, fmaxf(sy, sz))) : 1e30f;
     r.isx = 1.0f / sx; r.isy = 1.0f / sy; r.isz = 1.0f / sz;
-    r.alox = r.aloy = r.aloz = -1e30f; r.ahix = r.ahiy = r.ahiz = 1e30f; r.pad0_ = 0.0f;   // (no active box yet)
+    r.alox = r.aloy = r.aloz = -1e30f; r.ahix = r.ahiy = r.ahiz = 1e30f;   // (no active box yet)
+    r.dil_off = (int)(dil_obj_stride * o);
+    // approximate world -> grid map for the cull / classification tests (their margins absorb its rounding)
+    r.ga[0] = r.r[0] * r.isx; r.ga[1] = r.r[1] * r.isx; r.ga[2] = r.r[2] * r.isx; r.ga[3] = (r.tx - r.minx) * r.isx;
+    r.ga[4] = r.r[3] * r.isy; r.ga[5] = r.r[4] * r.isy; r.ga[6] = r.r[5] * r.isy; r.ga[7] = (r.ty - r.miny) * r.isy;
+    r.ga[8] = r.r[6] * r.isz; r.ga[9] = r.r[7] * r.isz; r.ga[10] = r.r[8] * r.isz; r.ga[11] = (r.tz - r.minz) * r.isz;
+    {   // world-frame sphere around the region in which a sample can be in bounds, padded like the box test
+        const float cx = 0.5f * (r.lox + r.hix) - r.tx, cy = 0.5f * (r.loy + r.hiy) - r.ty, cz = 0.5f * (r.loz + r.hiz) - r.tz;
+        r.wsx = r.r[0] * cx + r.r[3] * cy + r.r[6] * cz;   // R^T (c - t)
+        r.wsy = r.r[1] * cx + r.r[4] * cy + r.r[7] * cz;
+        r.wsz = r.r[2] * cx + r.r[5] * cy + r.r[8] * cz;
+        const float hx = 0.5f * (r.hix - r.lox), hy = 0.5f * (r.hiy - r.loy), hz = 0.5f * (r.hiz - r.loz);
+        // 1.001 + 1e-3: fp32 rounding of the (nearly orthonormal) rotation and of the centre
+        r.wsr = (r.cull_pad < 1e29f) ? (sqrtf(hx * hx + hy * hy + hz * hz) * 1.001f + r.cull_pad + 1e-3f) : -1.0f;
+    }
+    r.pad1_[0] = r.pad1_[1] = 0.0f;
     r.grid_offset = (long long)o * r.d0 * r.d1 * r.d2;
     out[o] = r;
 }
@@ -364,6 +379,8 @@ struct omgb_scene {
     double *d_Ainv = nullptr, *d_proj = nullptr;
     int n = 0, c = 0;
     bool metric_set = false;
+    int metric_kind = 0;          // closed form of Ainv recognised by omgb_scene_set_metric (0 = none, dense product)
+    double metric_scale = 0.0;
     // staging for the host-buffer entry point
     float *d_dil = nullptr;
     DilDesc dil;
@@ -535,6 +552,7 @@ extern "C" int omgb_scene_set_sdf(omgb_scene_t *s, const float *d_sdf_grids, con
         dd.bx = (dx + 1) / 2; dd.by = (dy + 1) / 2; dd.bz = (dz + 1) / 2;
         dd.obj_stride = (long long)dd.bx * dd.by * dd.bz;
         const long long total = dd.obj_stride * num_objects;
+        if (total > 0x7fffffffLL) return fail(OMGB_ERR_UNSUPPORTED, "packed SDFs too large for the lower-bound grid index");
         cudaFree(s->d_dil);
         s->d_dil = nullptr;
         float *tmp = nullptr;
@@ -574,7 +592,7 @@ extern "C" int omgb_scene_set_objects(omgb_scene_t *s, const float *pose_inv, co
     OMGB_CUDA(cudaStreamSynchronize(st));   // h goes out of scope
     prep_objects_kernel<<<(O + 63) / 64, 64, 0, st>>>(s->d_objparams, s->d_limits, s->d_objparams + 16 * O,
                                                       s->d_objparams + 17 * O, s->d_objparams + 18 * O,
-                                                      s->d_objparams + 19 * O, O, s->d_objs);
+                                                      s->d_objparams + 19 * O, O, s->d_objs, s->dil.obj_stride);
     OMGB_CUDA(cudaGetLastError());
     if (s->dil.enabled) {   // active boxes depend on eps / clearance
         if (!s->d_bounds) OMGB_CUDA(cudaMalloc(&s->d_bounds, sizeof(int) * 6 * OMGB_MAX_OBJECTS));
@@ -605,6 +623,28 @@ extern "C" int omgb_scene_set_metric(omgb_scene_t *s, int n, const double *h_Ain
     }
     s->n = n; s->c = c;
     s->metric_set = true;
+    // The CHOMP metric A = K^T K (omg/config.py:208-220) is tridiagonal: Ainv = dt^2 min(i,j) with a free end
+    // (goal-set mode) and dt^2 min(i,j)(n+1-max(i,j))/(n+1) with a fixed end (1-based).  When the given matrix is one
+    // of these (to 1e-9 of its largest entry) the kernel applies it as two running sums per DOF; any other matrix
+    // takes the dense product.  OMGB_DENSE_METRIC=1 forces the dense product.
+    s->metric_kind = 0;
+    s->metric_scale = 0.0;
+    const char *env = getenv("OMGB_DENSE_METRIC");
+    if (!(env && atoi(env))) {
+        double amax = 0.0;
+        for (int k = 0; k < n * n; ++k) amax = fabs(h_Ainv[k]) > amax ? fabs(h_Ainv[k]) : amax;
+        for (int kind = 1; kind <= 2 && s->metric_kind == 0; ++kind) {
+            const double scale = kind == 1 ? h_Ainv[0] : h_Ainv[0] * (double)(n + 1) / (double)n;
+            bool ok = scale > 0.0;
+            for (int i = 1; i <= n && ok; ++i)
+                for (int j = 1; j <= n && ok; ++j) {
+                    const double mn = i < j ? i : j, mx = i < j ? j : i;
+                    const double want = kind == 1 ? scale * mn : scale * mn * (n + 1 - mx) / (double)(n + 1);
+                    ok = fabs(h_Ainv[(size_t)(i - 1) * n + (j - 1)] - want) <= 1e-9 * amax;
+                }
+            if (ok) { s->metric_kind = kind; s->metric_scale = scale; }
+        }
+    }
     return OMGB_OK;
 }
 
@@ -631,7 +671,7 @@ extern "C" int omgb_sdf_loss(const float *pose_init, const float *sdf_grids, con
     cudaStream_t st = (cudaStream_t)stream;
     ObjRec *recs = reinterpret_cast<ObjRec *>(workspace);
     prep_objects_kernel<<<(num_objects + 63) / 64, 64, 0, st>>>(pose_init, sdf_limits, epsilons, padding_scales,
-                                                                clearances, disables, num_objects, recs);
+                                                                clearances, disables, num_objects, recs, 0);
     OMGB_CUDA(cudaGetLastError());
     const size_t smem = sizeof(ObjRec) * (size_t)num_objects;
     if (smem > 48 * 1024)
@@ -783,6 +823,7 @@ static StepArgs make_args(const omgb_scene *s, const omgb_step_params_t *prm, in
     a.dil = s->dil;
     a.prof = s->d_prof;
     a.num_objects = s->num_objects; a.batch = batch; a.iteration = 0; a.stop_on_terminate = 0;
+    a.metric_kind = s->metric_kind; a.metric_scale = s->metric_scale;
     a.prm = *prm;
     if (!a.prm.goal_set_proj) a.prm.constraint_rows = 0;
     return a;

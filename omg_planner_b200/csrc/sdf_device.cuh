@@ -31,8 +31,11 @@ struct __align__(16) ObjRec {
     float isx, isy, isz;         // 1 / grid spacing per axis (cull only)
     float alox, aloy, aloz;      // object-frame AABB of the region where a sample can be <= eps or < clearance
     float ahix, ahiy, ahiz;      // (from the lower-bound grid; empty when alo > ahi)
-    float pad0_;
+    int dil_off;                 // o * (bricks per object) into the lower-bound grid
     long long grid_offset;       // o * d0*d1*d2
+    float ga[12];                // world -> APPROXIMATE grid coordinates, g = ga[4k..4k+2] . x + ga[4k+3] (cull/classify only)
+    float wsx, wsy, wsz, wsr;    // WORLD-frame sphere enclosing the padded in-bounds box (first-level cull); wsr < 0: never cull
+    float pad1_[2];
 };
 
 __device__ __forceinline__ float lerp_ref(float a, float b, float t) {   // kernel.cu:15-18

@@ -35,7 +35,8 @@ def main():
             _lib.check(eng.L.omgb_scene_set_profile(eng._h, _dp(prof)))
         out = eng.step(cfg, x, s, e, t)
     torch.cuda.synchronize()
-    p = prof.cpu().numpy().astype(np.float64)
+    raw = prof.cpu().numpy()
+    p = raw.astype(np.float64)
     exact = p[:, 12].copy()
     p = p[:, :12]
     d = np.diff(p, axis=1)
@@ -57,6 +58,21 @@ def main():
             info[bidx, 13], exact[bidx], info[bidx, 15], info[bidx, 14]))
     pct = np.percentile(tot, [50, 90, 99, 100])
     lines.append("total percentiles 50/90/99/100: %s" % np.round(pct))
+    # timeline from the global timer (ns): how full the machine is over the kernel's life
+    smid, t0, t1 = raw[:, 13], raw[:, 14] - raw[:, 14].min(), raw[:, 15] - raw[:, 14].min()
+    span = t1.max()
+    lines.append("timeline: kernel span %.1f us (first CTA start -> last CTA end); CTA duration mean %.1f us max %.1f us; "
+                 "sum of CTA durations / (444 slots x span) = %.3f" % (span / 1e3, (t1 - t0).mean() / 1e3,
+                                                                     (t1 - t0).max() / 1e3, (t1 - t0).sum() / (444 * span)))
+    grid_t = np.linspace(0, span, 23)[1:-1]
+    res = [(int(((t0 <= t) & (t1 > t)).sum())) for t in grid_t]
+    lines.append("resident CTAs at %s us: %s" % ([round(t / 1e3) for t in grid_t], res))
+    last_start = t0.max()
+    lines.append("last CTA starts at %.1f us; CTAs starting in the first 5 us: %d; SMs used %d; per-SM busy span min/mean/max %.1f/%.1f/%.1f us" % (
+        last_start / 1e3, int((t0 < 5e3).sum()), len(set(smid.tolist())),
+        min(t1[smid == s_].max() for s_ in set(smid.tolist())) / 1e3,
+        np.mean([t1[smid == s_].max() for s_ in set(smid.tolist())]) / 1e3,
+        max(t1[smid == s_].max() for s_ in set(smid.tolist())) / 1e3))
     txt = "\n".join(lines)
     print(txt)
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
