@@ -498,15 +498,11 @@ __device__ __forceinline__ void metric_apply(const StepArgs &a, int n, const dou
 // ----------------------------------------------------------------------------------------------------
 // the fused iteration
 // ----------------------------------------------------------------------------------------------------
-template <int LPI, int THREADS, int MINB, bool TOPK>
-__global__ void __launch_bounds__(THREADS, MINB) chomp_step_kernel(const StepArgs a) {
-    extern __shared__ __align__(16) unsigned char smem[];
-    if ((int)blockIdx.x >= a.batch) return;
-    const int b = a.order ? a.order[blockIdx.x] : (int)blockIdx.x;
-    if ((a.active && !a.active[b]) || (a.done && a.done[b])) {
-        if (a.cta_cost && threadIdx.x == 0) a.cta_cost[b] = 0;
-        return;
-    }
+// One CHOMP iteration of trajectory b by the calling CTA (every thread calls).  w_obs / w_smooth / step_size: the
+// schedules Optimizer.update() set for this iteration (omg/optimizer.py:59-80); iteration: index inside a plan.
+template <int LPI, bool TOPK>
+__device__ __forceinline__ void chomp_iteration(const StepArgs &a, unsigned char *smem, const int b, const double w_obs,
+                                                const double w_smooth, const double step_size, const int iteration) {
     const long long t_begin = clock64();
 
     const omgb_step_params_t &prm = a.prm;
@@ -560,6 +556,7 @@ __global__ void __launch_bounds__(THREADS, MINB) chomp_step_kernel(const StepArg
     // the device-memory staging below runs while they are in flight.
     double *g_xi = a.xi + (size_t)b * n * ND;
     const int n_x = n * ND, n_in = n_x + 2 * ND + c * ND;
+    // (.cg loads: in the persistent plan kernel the previous iteration of this trajectory may have run on another SM)
     auto stage_src = [&](int k) -> const double * {
         if (k < n_x) return g_xi + k;
         if (k < n_x + ND) return a.start + (size_t)b * ND + (k - n_x);
@@ -567,8 +564,8 @@ __global__ void __launch_bounds__(THREADS, MINB) chomp_step_kernel(const StepArg
         return a.goal_rows + (size_t)b * c * ND + (k - n_x - 2 * ND);
     };
     double stg0 = 0.0, stg1 = 0.0;
-    if (tid < n_in) stg0 = *stage_src(tid);
-    if (tid + nthr < n_in) stg1 = *stage_src(tid + nthr);
+    if (tid < n_in) stg0 = __ldcg(stage_src(tid));
+    if (tid + nthr < n_in) stg1 = __ldcg(stage_src(tid + nthr));
     {
         const int words = (int)(sizeof(ObjRec) / 4) * O;
         const uint32_t *src = reinterpret_cast<const uint32_t *>(a.objs);
@@ -578,7 +575,7 @@ __global__ void __launch_bounds__(THREADS, MINB) chomp_step_kernel(const StepArg
     for (int k = tid; k < n_li; k += nthr) { s_best[k] = 0.0f; s_bestp[k] = 0; }
     if (tid < n_in) s_xi[tid] = stg0;
     if (tid + nthr < n_in) s_xi[tid + nthr] = stg1;
-    for (int k = tid + 2 * nthr; k < n_in; k += nthr) s_xi[k] = *stage_src(k);   // (long trajectories)
+    for (int k = tid + 2 * nthr; k < n_in; k += nthr) s_xi[k] = __ldcg(stage_src(k));   // (long trajectories)
     __syncthreads();
 
     OMGB_PROF(1);
@@ -932,9 +929,9 @@ __global__ void __launch_bounds__(THREADS, MINB) chomp_step_kernel(const StepArg
         if (i < n - 1) sg = (2.0 * xc - xprev - s_xi[k + ND]) * inv_dt2;
         else sg = goal_set ? (xc - xprev) * inv_dt2 : (2.0 * xc - xprev - s_end[d]) * inv_dt2;
         sg *= prm.link_smooth_weight[d];
-        double wo = prm.obstacle_weight * og;
+        double wo = w_obs * og;
         wo = fmin(fmax(wo, -prm.clip_grad_scale), prm.clip_grad_scale);
-        const double ws = prm.smoothness_weight * sg;
+        const double ws = w_smooth * sg;
         const double gt = wo + ws;
         s_grad[k] = gt;
         red7[0] += wo * wo; red7[1] += ws * ws; red7[2] += gt * gt;
@@ -975,7 +972,7 @@ __global__ void __launch_bounds__(THREADS, MINB) chomp_step_kernel(const StepArg
             const int i = k / ND, d = k - i * ND;
             double v = s_xi[k];
             if (d < 7) {
-                double up = -prm.step_size * s_u[k];
+                double up = -step_size * s_u[k];
                 if (goal_set) {
                     double t1 = 0.0, t2 = 0.0;
                     for (int r = 0; r < c; ++r) {
@@ -983,7 +980,7 @@ __global__ void __launch_bounds__(THREADS, MINB) chomp_step_kernel(const StepArg
                         t1 = fma(m, s_u[(n - c + r) * ND + d], t1);
                         t2 = fma(m, s_xi[(n - c + r) * ND + d] - s_goal[r * ND + d], t2);
                     }
-                    up = up + prm.step_size * t1 - t2;
+                    up = up + step_size * t1 - t2;
                 }
                 v += up;
             } else {
@@ -1052,7 +1049,7 @@ __global__ void __launch_bounds__(THREADS, MINB) chomp_step_kernel(const StepArg
         double *inf = s_red;   // staged in shared memory, written as one coalesced 128-byte row below
         inf[OMGB_INFO_OBS] = obs_sum;
         inf[OMGB_INFO_SMOOTH] = smooth_sum;
-        inf[OMGB_INFO_COST] = prm.obstacle_weight * obs_sum + prm.smoothness_weight * smooth_sum;
+        inf[OMGB_INFO_COST] = w_obs * obs_sum + w_smooth * smooth_sum;
         inf[OMGB_INFO_COLLIDE] = (double)collide;
         inf[OMGB_INFO_REACH] = goal_dist;
         inf[OMGB_INFO_GRAD_NORM] = norm_g;
@@ -1068,11 +1065,67 @@ __global__ void __launch_bounds__(THREADS, MINB) chomp_step_kernel(const StepArg
         inf[OMGB_INFO_NONZERO] = (double)nnz;
         inf[OMGB_INFO_LIMIT_ROUNDS] = (double)limit_rounds;
         inf[OMGB_INFO_RESERVED] = (double)n_act;   // link instances that survived the cull (diagnostic)
-        if (a.done && a.stop_on_terminate && terminate && a.iteration > 0) a.done[b] = 1;
+        if (a.done && a.stop_on_terminate && terminate && iteration > 0) a.done[b] = 1;
         if (a.cta_cost) a.cta_cost[b] = (int)min((long long)0x7fffffff, clock64() - t_begin);
     }
     __syncwarp();
     if (tid < OMGB_INFO_STRIDE) a.info[(size_t)b * OMGB_INFO_STRIDE + tid] = s_red[tid];
+}
+
+// One launch = one iteration of every trajectory, CTA per trajectory (Optimizer.optimize granularity).
+template <int LPI, int THREADS, int MINB, bool TOPK>
+__global__ void __launch_bounds__(THREADS, MINB) chomp_step_kernel(const StepArgs a) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    if ((int)blockIdx.x >= a.batch) return;
+    const int b = a.order ? a.order[blockIdx.x] : (int)blockIdx.x;
+    if ((a.active && !a.active[b]) || (a.done && a.done[b])) {
+        if (a.cta_cost && threadIdx.x == 0) a.cta_cost[b] = 0;
+        return;
+    }
+    chomp_iteration<LPI, TOPK>(a, smem, b, a.prm.obstacle_weight, a.prm.smoothness_weight, a.prm.step_size, a.iteration);
+}
+
+// Persistent plan kernel: ONE launch runs `iters` iterations of every trajectory (the fixed-goal inner loop of
+// Planner.plan, omg/planner.py:612-627).  The grid is one CTA per resident slot; CTAs pull (iteration, trajectory)
+// items from a global counter in iteration-major order.  Item (it, b) depends only on item (it - 1, b), which has a
+// smaller id and therefore was claimed earlier by a CTA that is running: waiting on progress[b] cannot deadlock.
+// Trajectories are independent, so there is no grid-wide barrier between iterations and the machine stays full
+// until the last items of the whole plan (a per-iteration launch drains to a tail every iteration).
+struct PlanArgs {
+    const double *sched;     // [iters][3]: obstacle weight, smoothness weight, step size per iteration
+    int *progress;           // [B]: iterations of trajectory b completed so far
+    unsigned *counter;       // next item
+    int iters;
+};
+
+template <int LPI, int THREADS, int MINB, bool TOPK>
+__global__ void __launch_bounds__(THREADS, MINB) chomp_plan_kernel(const StepArgs a, const PlanArgs p) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    __shared__ unsigned s_item;
+    const unsigned total = (unsigned)a.batch * (unsigned)p.iters;
+    for (;;) {
+        __syncthreads();   // (the previous item's shared memory is dead)
+        if (threadIdx.x == 0) s_item = atomicAdd(p.counter, 1u);
+        __syncthreads();
+        const unsigned item = s_item;
+        if (item >= total) break;
+        const int it = (int)(item / (unsigned)a.batch), b = (int)(item % (unsigned)a.batch);
+        if (threadIdx.x == 0) {
+            volatile int *pr = p.progress + b;
+            while (*pr < it) __nanosleep(200);
+            __threadfence();   // acquire: the other CTA's xi / done writes are visible below
+        }
+        __syncthreads();
+        const bool skip = a.done && __ldcg(a.done + b);   // frozen by stop_on_terminate
+        if (!skip)
+            chomp_iteration<LPI, TOPK>(a, smem, b, __ldg(p.sched + 3 * it), __ldg(p.sched + 3 * it + 1),
+                                       __ldg(p.sched + 3 * it + 2), it);
+        __syncthreads();       // every thread's global stores of this item are issued ...
+        if (threadIdx.x == 0) {
+            __threadfence();   // ... and visible device-wide before the trajectory is released
+            atomicExch(p.progress + b, it + 1);
+        }
+    }
 }
 
 }  // namespace omgb

@@ -392,6 +392,12 @@ struct omgb_scene {
     // host-buffer entry point: 0 auto (zero-copy when every buffer is mapped pinned memory, else pipelined staging),
     // 1 staged in one piece, 2 staged + pipelined over chunks, 3 zero-copy required
     int host_mode = 0;
+    // persistent plan kernel state: schedules [iters][3], per-trajectory progress, the item counter
+    double *d_plan_sched = nullptr;
+    int *d_plan_progress = nullptr;
+    unsigned *d_plan_counter = nullptr;
+    int plan_sched_cap = 0, plan_progress_cap = 0;
+    int num_sms = 148;
     cudaStream_t pipe_stream[PIPE_CHUNKS] = {nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t pipe_done[PIPE_CHUNKS] = {nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t pipe_begin = nullptr;
@@ -413,6 +419,7 @@ extern "C" int omgb_scene_create(omgb_scene_t **out, int device) {
     cudaError_t e = cudaMalloc(&s->d_robot, sizeof(RobotConst));
     if (e != cudaSuccess) { delete s; return fail(OMGB_ERR_CUDA, cudaGetErrorString(e)); }
     cudaDeviceGetAttribute(&s->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+    cudaDeviceGetAttribute(&s->num_sms, cudaDevAttrMultiProcessorCount, device);
     *out = s;
     return OMGB_OK;
 }
@@ -423,6 +430,7 @@ extern "C" int omgb_scene_destroy(omgb_scene_t *s) {
     cudaFree(s->d_robot); cudaFree(s->d_limits); cudaFree(s->d_objparams); cudaFree(s->d_objs);
     cudaFree(s->d_Ainv); cudaFree(s->d_proj); cudaFree(s->d_stage); cudaFree(s->d_dil); cudaFree(s->d_bounds);
     for (int k = 0; k < ORDER_SLOTS; ++k) { cudaFree(s->order[k].d_order); cudaFree(s->order[k].d_cost); }
+    cudaFree(s->d_plan_sched); cudaFree(s->d_plan_progress); cudaFree(s->d_plan_counter);
     for (int k = 0; k < PIPE_CHUNKS; ++k) {
         if (s->pipe_stream[k]) cudaStreamDestroy(s->pipe_stream[k]);
         if (s->pipe_done[k]) cudaEventDestroy(s->pipe_done[k]);
@@ -713,31 +721,44 @@ static int carveout_percent(size_t smem, int ctas) {
 }
 
 template <int LPI, int THREADS, int MINB, bool TOPK>
-static int launch_one(const StepArgs &a, size_t smem, cudaStream_t st) {
+static int launch_one(const StepArgs &a, size_t smem, cudaStream_t st, const PlanArgs *plan, int num_sms) {
     // function attributes are per (instantiation, device); set again only when the footprint changes
-    static size_t cached_smem[64] = {0};
+    static size_t cached_smem[2][64] = {{0}};
     int dev = 0;
     cudaGetDevice(&dev);
-    if (dev < 0 || dev >= 64 || cached_smem[dev] != smem) {
-        OMGB_CUDA(cudaFuncSetAttribute(chomp_step_kernel<LPI, THREADS, MINB, TOPK>,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        OMGB_CUDA(cudaFuncSetAttribute(chomp_step_kernel<LPI, THREADS, MINB, TOPK>,
-                                       cudaFuncAttributePreferredSharedMemoryCarveout, carveout_percent(smem, MINB)));
-        if (dev >= 0 && dev < 64) cached_smem[dev] = smem;
+    const int which = plan ? 1 : 0;
+    if (dev < 0 || dev >= 64 || cached_smem[which][dev] != smem) {
+        if (plan) {
+            OMGB_CUDA(cudaFuncSetAttribute(chomp_plan_kernel<LPI, THREADS, MINB, TOPK>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            OMGB_CUDA(cudaFuncSetAttribute(chomp_plan_kernel<LPI, THREADS, MINB, TOPK>,
+                                           cudaFuncAttributePreferredSharedMemoryCarveout, carveout_percent(smem, MINB)));
+        } else {
+            OMGB_CUDA(cudaFuncSetAttribute(chomp_step_kernel<LPI, THREADS, MINB, TOPK>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            OMGB_CUDA(cudaFuncSetAttribute(chomp_step_kernel<LPI, THREADS, MINB, TOPK>,
+                                           cudaFuncAttributePreferredSharedMemoryCarveout, carveout_percent(smem, MINB)));
+        }
+        if (dev >= 0 && dev < 64) cached_smem[which][dev] = smem;
     }
-    chomp_step_kernel<LPI, THREADS, MINB, TOPK><<<a.batch, THREADS, smem, st>>>(a);
+    if (plan) {
+        const int slots = MINB * num_sms;   // one persistent CTA per resident slot
+        chomp_plan_kernel<LPI, THREADS, MINB, TOPK><<<a.batch < slots ? a.batch : slots, THREADS, smem, st>>>(a, *plan);
+    } else {
+        chomp_step_kernel<LPI, THREADS, MINB, TOPK><<<a.batch, THREADS, smem, st>>>(a);
+    }
     ++g_launches;
     OMGB_CUDA(cudaGetLastError());
     return OMGB_OK;
 }
 
 template <int LPI, int THREADS, int MINB>
-static int launch_cfg(const StepArgs &a, size_t smem, cudaStream_t st) {
-    return a.prm.top_k_collision > 0 ? launch_one<LPI, THREADS, MINB, true>(a, smem, st)
-                                     : launch_one<LPI, THREADS, MINB, false>(a, smem, st);
+static int launch_cfg(const StepArgs &a, size_t smem, cudaStream_t st, const PlanArgs *plan, int num_sms) {
+    return a.prm.top_k_collision > 0 ? launch_one<LPI, THREADS, MINB, true>(a, smem, st, plan, num_sms)
+                                     : launch_one<LPI, THREADS, MINB, false>(a, smem, st, plan, num_sms);
 }
 
-static int step_config() {   // 0: 256 threads x 3 CTAs/SM, 1: 512 x 2, 2: 512 x 1, 3: 256 x 2, 4: 384 x 2, 5 (default): 320 x 3
+static int step_config() {   // 1: 512 threads x 2 CTAs/SM, anything else (default): 320 x 3
     static int cfg = -1;
     if (cfg < 0) {
         const char *e = getenv("OMGB_STEP_CONFIG");
@@ -746,7 +767,8 @@ static int step_config() {   // 0: 256 threads x 3 CTAs/SM, 1: 512 x 2, 2: 512 x
     return cfg;
 }
 
-static int launch_step(omgb_scene *s, const StepArgs &a_in, cudaStream_t st) {
+// plan == nullptr: one iteration, CTA per trajectory; else the persistent plan kernel.
+static int launch_step(omgb_scene *s, const StepArgs &a_in, cudaStream_t st, const PlanArgs *plan = nullptr) {
     const StepArgs &a0 = a_in;
     const int lpi = s->p <= 16 ? 16 : 32;
     const SmemLayout L = make_layout(a0.prm.n_waypoints, a0.prm.constraint_rows, lpi, s->num_objects, s->p);
@@ -760,7 +782,7 @@ static int launch_step(omgb_scene *s, const StepArgs &a_in, cudaStream_t st) {
     static int env_lpt = -1;
     if (env_lpt < 0) { const char *e = getenv("OMGB_NO_LPT"); env_lpt = (e && atoi(e)) ? 0 : 1; }
     OrderSlot *os = nullptr;
-    if (env_lpt && s->use_lpt && a.batch >= 148) {
+    if (!plan && env_lpt && s->use_lpt && a.batch >= 148) {
         for (int k = 0; k < ORDER_SLOTS; ++k)
             if (s->order[k].key == (const void *)a.xi && s->order[k].batch == a.batch) os = &s->order[k];
         if (!os) {
@@ -785,21 +807,10 @@ static int launch_step(omgb_scene *s, const StepArgs &a_in, cudaStream_t st) {
     const int cfg = step_config();
     int rc_ = OMGB_OK;
     if (lpi == 16) {
-        switch (cfg) {
-            case 0: rc_ = launch_cfg<16, 256, 3>(a, L.total, st); break;
-            case 2: rc_ = launch_cfg<16, 512, 1>(a, L.total, st); break;
-            case 3: rc_ = launch_cfg<16, 256, 2>(a, L.total, st); break;
-            case 1: rc_ = launch_cfg<16, 512, 2>(a, L.total, st); break;
-            case 4: rc_ = launch_cfg<16, 384, 2>(a, L.total, st); break;
-            default: rc_ = launch_cfg<16, 320, 3>(a, L.total, st); break;
-        }
+        if (cfg == 1) rc_ = launch_cfg<16, 512, 2>(a, L.total, st, plan, s->num_sms);
+        else rc_ = launch_cfg<16, 320, 3>(a, L.total, st, plan, s->num_sms);
     } else {
-        switch (cfg) {
-            case 0: rc_ = launch_cfg<32, 256, 3>(a, L.total, st); break;
-            case 2: rc_ = launch_cfg<32, 512, 1>(a, L.total, st); break;
-            case 3: rc_ = launch_cfg<32, 256, 2>(a, L.total, st); break;
-            default: rc_ = launch_cfg<32, 512, 2>(a, L.total, st); break;
-        }
+        rc_ = launch_cfg<32, 512, 2>(a, L.total, st, plan, s->num_sms);
     }
     if (rc_) return rc_;
     if (os && (!os->valid || (++os->age % LPT_REFRESH) == 0)) {
@@ -858,15 +869,45 @@ extern "C" int omgb_chomp_plan(omgb_scene_t *s, const omgb_step_params_t *prm, i
     a.done = stop_on_terminate ? done : nullptr;
     a.stop_on_terminate = stop_on_terminate;
     a.prm.update = 1;
-    for (int it = 0; it < iters; ++it) {
-        a.iteration = it;
-        a.prm.obstacle_weight = ow[it];
-        a.prm.smoothness_weight = sw[it];
-        a.prm.step_size = ss[it];
-        rc_ = launch_step(s, a, st);
-        if (rc_) return rc_;
+    if (batch == 0 || iters == 0) return OMGB_OK;
+    static int env_loop = -1;
+    if (env_loop < 0) { const char *e = getenv("OMGB_PLAN_LAUNCHES"); env_loop = (e && atoi(e)) ? 1 : 0; }
+    if (env_loop || s->d_prof) {
+        // one launch per iteration (diagnostics / A-B; identical results)
+        for (int it = 0; it < iters; ++it) {
+            a.iteration = it;
+            a.prm.obstacle_weight = ow[it];
+            a.prm.smoothness_weight = sw[it];
+            a.prm.step_size = ss[it];
+            rc_ = launch_step(s, a, st);
+            if (rc_) return rc_;
+        }
+        return OMGB_OK;
     }
-    return OMGB_OK;
+    // persistent plan kernel: one launch, a device-side queue of (iteration, trajectory) items
+    if (iters > s->plan_sched_cap) {
+        cudaFree(s->d_plan_sched);
+        s->d_plan_sched = nullptr; s->plan_sched_cap = 0;
+        OMGB_CUDA(cudaMalloc(&s->d_plan_sched, sizeof(double) * 3 * iters));
+        s->plan_sched_cap = iters;
+    }
+    if (batch > s->plan_progress_cap) {
+        cudaFree(s->d_plan_progress);
+        s->d_plan_progress = nullptr; s->plan_progress_cap = 0;
+        OMGB_CUDA(cudaMalloc(&s->d_plan_progress, sizeof(int) * batch));
+        s->plan_progress_cap = batch;
+    }
+    if (!s->d_plan_counter) OMGB_CUDA(cudaMalloc(&s->d_plan_counter, sizeof(unsigned)));
+    if ((long long)batch * iters > 0x7fffffffLL) return fail(OMGB_ERR_INVALID, "omgb_chomp_plan: batch x iters too large");
+    std::vector<double> sched(3 * (size_t)iters);
+    for (int it = 0; it < iters; ++it) { sched[3 * it] = ow[it]; sched[3 * it + 1] = sw[it]; sched[3 * it + 2] = ss[it]; }
+    OMGB_CUDA(cudaMemcpyAsync(s->d_plan_sched, sched.data(), sizeof(double) * 3 * iters, cudaMemcpyHostToDevice, st));
+    OMGB_CUDA(cudaStreamSynchronize(st));   // (sched goes out of scope; pageable source)
+    OMGB_CUDA(cudaMemsetAsync(s->d_plan_progress, 0, sizeof(int) * batch, st));
+    OMGB_CUDA(cudaMemsetAsync(s->d_plan_counter, 0, sizeof(unsigned), st));
+    PlanArgs pa;
+    pa.sched = s->d_plan_sched; pa.progress = s->d_plan_progress; pa.counter = s->d_plan_counter; pa.iters = iters;
+    return launch_step(s, a, st, &pa);
 }
 
 // Device alias of a host pointer when it lies in mapped pinned memory (cudaHostAlloc / cudaHostRegister under UVA).

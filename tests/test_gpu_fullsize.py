@@ -112,3 +112,29 @@ def test_exact_accelerations_do_not_change_results(big):
     assert torch.equal(a[..., 3:], b[..., 3:]) and torch.equal(a[..., 1], b[..., 1])   # collide, P_in, flags, norms
     # obstacle cost / total cost are block sums whose fp64 summation order follows the active set: last-ulp only
     assert torch.allclose(a[..., [0, 2]], b[..., [0, 2]], rtol=1e-12, atol=0)
+
+
+def test_persistent_plan_kernel_equals_per_iteration_launches(big):
+    """omgb_chomp_plan runs the whole plan as one persistent launch with a device-side work queue; every trajectory must
+    end bit-identical to the same number of per-iteration launches (also with stop_on_terminate freezing)."""
+    sc, robot, xi, st, en, tails = big
+    mode = H.MODES["goalset_standoff_topk"]
+    cfg = ChompConfig(**mode)
+    eng = H.engine_for(sc, cfg, robot)
+    iters = 9
+    x1 = _dev(xi)
+    for it in range(iters):
+        cfg.obstacle_weight, cfg.smoothness_weight, cfg.step_size = cfg.schedule(it + 1)
+        info1 = eng.step(cfg, x1, _dev(st), _dev(en), _dev(tails))["info"]
+    for rep in range(2):   # twice: the queue state is reset per call
+        x2 = _dev(xi)
+        out = eng.plan(cfg, x2, _dev(st), _dev(en), _dev(tails), iters=iters)
+        torch.cuda.synchronize()
+        assert torch.equal(x1, x2)
+        assert torch.equal(info1[:, :15], out["info"][:, :15])
+    # more trajectories than resident CTA slots and a batch that is not a multiple of anything
+    sel = slice(0, 1001)
+    x3 = _dev(xi[sel])
+    eng.plan(cfg, x3, _dev(st[sel]), _dev(en[sel]), _dev(tails[sel]), iters=iters)
+    torch.cuda.synchronize()
+    assert torch.equal(x3, x1[sel])
