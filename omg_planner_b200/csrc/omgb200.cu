@@ -758,7 +758,7 @@ static int launch_cfg(const StepArgs &a, size_t smem, cudaStream_t st, const Pla
                                      : launch_one<LPI, THREADS, MINB, false>(a, smem, st, plan, num_sms);
 }
 
-static int step_config() {   // 1: 512 threads x 2 CTAs/SM, anything else (default): 320 x 3
+static int step_config() {   // OMGB_STEP_CONFIG: 1 = 512 threads x 2 CTAs/SM, 2 = 1024 x 1, else chosen by footprint
     static int cfg = -1;
     if (cfg < 0) {
         const char *e = getenv("OMGB_STEP_CONFIG");
@@ -804,13 +804,25 @@ static int launch_step(omgb_scene *s, const StepArgs &a_in, cudaStream_t st, con
         a.order = os->valid ? os->d_order : nullptr;
         a.cta_cost = os->d_cost;
     }
-    const int cfg = step_config();
+    // CTA shape by how many CTAs of this footprint fit in an SM's 228 KB (+1 KB reserved each): three 320-thread
+    // CTAs for the usual 30-waypoint trajectory, two of 512 or one of 1024 threads for long trajectories, so that
+    // ~30 warps stay resident per SM either way.  OMGB_STEP_CONFIG=1/2 forces 512x2 / 1024x1.
+    const int fit = (int)((228u * 1024u) / (L.total + 1024u));
+    int cfg = step_config();
+    if (cfg != 1 && cfg != 2) {
+        cfg = fit >= 3 ? 0 : (fit == 2 ? 1 : 2);
+        // small batches leave SMs under-filled: spend the idle warps on wider CTAs (lower latency per trajectory)
+        if (a.batch <= s->num_sms) cfg = 2;
+        else if (a.batch <= 2 * s->num_sms && cfg == 0) cfg = 1;
+    }
     int rc_ = OMGB_OK;
     if (lpi == 16) {
-        if (cfg == 1) rc_ = launch_cfg<16, 512, 2>(a, L.total, st, plan, s->num_sms);
-        else rc_ = launch_cfg<16, 320, 3>(a, L.total, st, plan, s->num_sms);
+        if (cfg == 0) rc_ = launch_cfg<16, 320, 3>(a, L.total, st, plan, s->num_sms);
+        else if (cfg == 1) rc_ = launch_cfg<16, 512, 2>(a, L.total, st, plan, s->num_sms);
+        else rc_ = launch_cfg<16, 1024, 1>(a, L.total, st, plan, s->num_sms);
     } else {
-        rc_ = launch_cfg<32, 512, 2>(a, L.total, st, plan, s->num_sms);
+        if (cfg == 2) rc_ = launch_cfg<32, 1024, 1>(a, L.total, st, plan, s->num_sms);
+        else rc_ = launch_cfg<32, 512, 2>(a, L.total, st, plan, s->num_sms);
     }
     if (rc_) return rc_;
     if (os && (!os->valid || (++os->age % LPT_REFRESH) == 0)) {
