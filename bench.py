@@ -172,6 +172,7 @@ def run_b200(a):
 
     torch.cuda.set_device(local)
     if world > 1:
+        os.environ["NCCL_DEBUG"] = os.environ.get("OMGB_NCCL_DEBUG", "WARN")   # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     cfg = ChompConfig(timesteps=a.waypoints, **mode)
     robot = PandaConstants()
@@ -221,6 +222,7 @@ def run_b200(a):
     clocks = sampler.stop()
     dev_ms = sum(s.elapsed_time(e) for s, e in evs)
     p_in_per_launch = float(torch.stack(pins).mean().item())
+    print("rank %d: device ms/step %.4f, P_in per launch %.0f" % (rank, dev_ms / a.steps, p_in_per_launch), file=sys.stderr)
     t = torch.tensor([dev_ms], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
