@@ -858,6 +858,7 @@ extern "C" int omgb_chomp_step(omgb_scene_t *s, const omgb_step_params_t *prm, i
                                float *dbg_pts, double *row_obs, void *stream) {
     int rc_ = check_step(s, prm, batch, "omgb_chomp_step");
     if (rc_) return rc_;
+    if (batch == 0) return OMGB_OK;   // (an empty tensor's data pointer is null)
     if (!xi || !start || !end || !info || (prm->goal_set_proj && !goal_rows))
         return fail(OMGB_ERR_INVALID, "omgb_chomp_step: null buffer");
     OMGB_CUDA(cudaSetDevice(s->device));
@@ -871,7 +872,8 @@ extern "C" int omgb_chomp_plan(omgb_scene_t *s, const omgb_step_params_t *prm, i
                                double *info, void *stream) {
     int rc_ = check_step(s, prm, batch, "omgb_chomp_plan");
     if (rc_) return rc_;
-    if (iters < 0 || !ow || !sw || !ss) return fail(OMGB_ERR_INVALID, "omgb_chomp_plan: bad schedule");
+    if (iters < 0 || (iters > 0 && (!ow || !sw || !ss))) return fail(OMGB_ERR_INVALID, "omgb_chomp_plan: bad schedule");
+    if (batch == 0 || iters == 0) return OMGB_OK;
     if (!xi || !start || !end || !info || (prm->goal_set_proj && !goal_rows) || (stop_on_terminate && !done))
         return fail(OMGB_ERR_INVALID, "omgb_chomp_plan: null buffer");
     OMGB_CUDA(cudaSetDevice(s->device));
