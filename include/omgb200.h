@@ -77,7 +77,7 @@ typedef struct {
     int32_t constraint_rows;       /* c: reach_tail_length with use_standoff, else 1; 0 when !goal_set_proj */
     int32_t top_k_collision;       /* cfg.top_k_collision; 0 = sum over all points */
     int32_t uncheck_finger_collision; /* cfg.uncheck_finger_collision (0 or -1) */
-    int32_t consider_finger;       /* must be 0 (cfg.consider_finger) */
+    int32_t consider_finger;       /* cfg.consider_finger: finger links in the top-k sum, finger DOFs updated */
     int32_t allow_collision_point; /* cfg.allow_collision_point */
     int32_t pre_terminate;         /* cfg.pre_terminate */
     int32_t joint_limit_max_steps; /* cfg.joint_limit_max_steps */

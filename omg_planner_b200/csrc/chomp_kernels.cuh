@@ -971,7 +971,7 @@ __device__ __forceinline__ void chomp_iteration(const StepArgs &a, unsigned char
         for (int k = tid; k < n * ND; k += nthr) {   // + Trajectory.update (core.py:43-51)
             const int i = k / ND, d = k - i * ND;
             double v = s_xi[k];
-            if (d < 7) {
+            if (d < 7 || prm.consider_finger) {   // cfg.consider_finger: the finger DOFs move too (core.py:47-48)
                 double up = -step_size * s_u[k];
                 if (goal_set) {
                     double t1 = 0.0, t2 = 0.0;
@@ -983,9 +983,8 @@ __device__ __forceinline__ void chomp_iteration(const StepArgs &a, unsigned char
                     up = up + step_size * t1 - t2;
                 }
                 v += up;
-            } else {
-                v = fmin(fmax(v, 0.0), 0.04);
             }
+            if (d >= 7) v = fmin(fmax(v, 0.0), 0.04);   // core.py:51
             s_viol[k] = v;   // staged: other threads still read s_xi rows n-c..n-1
         }
         __syncthreads();

@@ -706,7 +706,6 @@ static int check_step(const omgb_scene *s, const omgb_step_params_t *prm, int ba
     const int c = prm->goal_set_proj ? prm->constraint_rows : 0;
     if (c != s->c || (prm->goal_set_proj && c < 1))
         return fail(OMGB_ERR_INVALID, std::string(who) + ": constraint_rows differs from the metric set on the scene");
-    if (prm->consider_finger) return fail(OMGB_ERR_UNSUPPORTED, std::string(who) + ": consider_finger is not supported");
     if (prm->top_k_collision < 0) return fail(OMGB_ERR_INVALID, std::string(who) + ": negative top_k_collision");
     if (!(prm->time_interval > 0)) return fail(OMGB_ERR_INVALID, std::string(who) + ": time_interval must be > 0");
     return OMGB_OK;

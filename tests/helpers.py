@@ -54,6 +54,16 @@ MODES = {
 }
 
 
+def mode_from_fixture(g):
+    """mode dict of a tests/golden/chomp_*.npz fixture (tools/make_golden.py): [goal_set_proj, use_standoff,
+    top_k_collision(, consider_finger)]."""
+    m = [int(v) for v in g["mode"]]
+    mode = dict(goal_set_proj=bool(m[0]), use_standoff=bool(m[1]), top_k_collision=m[2])
+    if len(m) > 3 and m[3]:
+        mode["consider_finger"] = True
+    return mode
+
+
 def goal_rows_for(mode, tails, ends):
     if not mode["goal_set_proj"]:
         return None

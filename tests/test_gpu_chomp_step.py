@@ -45,15 +45,14 @@ def test_replay_reference_fixtures(path):
     g = np.load(path)
     sc = S.make_scene(**eval(str(g["scene_args"])))
     assert abs(sc["sdf_grids"].astype(np.float64).sum() - float(g["sdf_checksum"])) < 1e-6
-    gsp, standoff, topk = [int(v) for v in g["mode"]]
-    mode = dict(goal_set_proj=bool(gsp), use_standoff=bool(standoff), top_k_collision=topk)
+    mode = H.mode_from_fixture(g)
     cfg = ChompConfig(**mode)
     robot = PandaConstants(body_points=g["body_points"])
     eng = H.engine_for(sc, cfg, robot)
     rows = H.goal_rows_for(mode, g["tails"], g["end"])
     iters = g["history"].shape[1] - 1
     hist, infos, grads = _run_gpu(eng, cfg, g["xi0"], g["start"], g["end"], rows, iters, want_grad=True)
-    err = np.abs(hist - g["history"])[..., :7].max(axis=(2, 3))           # [B, iters+1]
+    err = np.abs(hist - g["history"]).max(axis=(2, 3))                    # [B, iters+1], all 9 DOFs
     print("max |xi - xi_ref| per iteration:", err.max(0))
     assert err.max() <= TOL_RAD, "first divergence at iteration %s" % (np.argwhere(err > TOL_RAD)[:1],)
     keys = [str(k) for k in g["info_keys"]]

@@ -6,6 +6,7 @@ import os
 import numpy as np
 import pytest
 
+import helpers as H
 from omg_planner_b200 import scene as S
 from oracle import chomp_ref as R
 
@@ -17,8 +18,7 @@ def load_case(path):
     args = eval(str(g["scene_args"]))  # repr of a plain dict written by tools/make_golden.py
     sc = S.make_scene(**args)
     assert abs(sc["sdf_grids"].astype(np.float64).sum() - float(g["sdf_checksum"])) < 1e-6, "scene generator drifted"
-    gsp, standoff, topk = [int(v) for v in g["mode"]]
-    return g, sc, dict(goal_set_proj=bool(gsp), use_standoff=bool(standoff), top_k_collision=topk)
+    return g, sc, H.mode_from_fixture(g)
 
 
 def test_fixtures_present():

@@ -30,6 +30,11 @@ MODES = {
     "goalset_standoff_topk": dict(goal_set_proj=True, use_standoff=True, top_k_collision=1000),
     "goalset_single_full": dict(goal_set_proj=True, use_standoff=False, top_k_collision=0),
     "goalset_standoff_topk200": dict(goal_set_proj=True, use_standoff=True, top_k_collision=200),
+    # cfg.consider_finger = True: finger links stay in the top-k sum (cost.py:401-402), finger DOFs are updated
+    # (core.py:47-48)
+    "fixed_topk_finger": dict(goal_set_proj=False, use_standoff=True, top_k_collision=1000, consider_finger=True),
+    "goalset_standoff_topk_finger": dict(goal_set_proj=True, use_standoff=True, top_k_collision=300,
+                                         consider_finger=True),
 }
 SCENE_ARGS = dict(num_objects=6, grid=48, seed=11, grid_choices=[32, 40, 48])
 N_TRAJ, N_WPT, N_ITER = 6, 30, 25
@@ -46,7 +51,11 @@ def main():
     robot = R.PandaRef()
     out_dir = os.path.join(ROOT, "tests", "golden")
     os.makedirs(out_dir, exist_ok=True)
+    only = sys.argv[1:]
     for name, mode in MODES.items():
+        if only and name not in only:
+            continue
+        cfg.consider_finger = False
         for k, v in mode.items():
             cfg[k] = v
         cfg.timesteps = N_WPT
@@ -83,7 +92,8 @@ def main():
                 grads[b, it] = info["gradient"]
         path = os.path.join(out_dir, "chomp_%s.npz" % name)
         np.savez_compressed(
-            path, mode=np.array([int(mode["goal_set_proj"]), int(mode["use_standoff"]), mode["top_k_collision"]]),
+            path, mode=np.array([int(mode["goal_set_proj"]), int(mode["use_standoff"]), mode["top_k_collision"],
+                                 int(mode.get("consider_finger", False))]),
             scene_args=np.array(repr(SCENE_ARGS)), sdf_checksum=np.float64(sc["sdf_grids"].astype(np.float64).sum()),
             body_points=robot.body_points, xi0=xi, start=st, end=en, tails=tails, history=hist, infos=infos,
             flags=flags, grads=grads, tie_slack=slack, info_keys=np.array(INFO_KEYS), flag_keys=np.array(FLAG_KEYS))
