@@ -20,6 +20,11 @@
  *   omgb_batch_obstacle_cost   Cost.batch_obstacle_cost             omg/cost.py:192-286
  *   omgb_goal_costs            Learner.cost_vector, device half     omg/online_learner.py:104-150 (omg/util.py:261-290,
  *                                                                   omg/cost.py:192-286 with arc_length, the two sums)
+ *   omgb_chomp_plan_history    plan() with history_trajectories     omg/planner.py:605-628
+ *   omgb_traj_interpolate      Trajectory.interpolate_waypoints     omg/core.py:59-78 -> omg/util.py:238-258
+ *   omgb_sdf_pack              SignedDensityField.from_pth/.resize  omg/sdf_tools.py:187-193, 37-39,
+ *                              + Env.combine_sdfs                   omg/core.py:366-411
+ *   omgb_point_sdf             PointEnv.compute_sdf_from_points     omg/core.py:426-457 (scipy cKDTree.query)
  */
 #ifndef OMGB200_H_
 #define OMGB200_H_
@@ -170,6 +175,16 @@ int omgb_chomp_plan(omgb_scene_t *scene, const omgb_step_params_t *params, int i
                     int stop_on_terminate, int batch, double *xi, const double *start, const double *end,
                     const double *goal_rows, uint8_t *done, double *info, void *stream);
 
+/* omgb_chomp_plan that also records what Planner.plan keeps per iteration (omg/planner.py:605-628):
+ * hist_xi DEVICE [iters,B,n,9] fp64 = xi after every iteration (history_trajectories[1:]; the caller holds
+ * history_trajectories[0], the initial xi), hist_info DEVICE [iters,B,OMGB_INFO_STRIDE] = every iteration's info row.
+ * Either may be NULL.  A trajectory frozen by stop_on_terminate repeats its last row in later slots. */
+int omgb_chomp_plan_history(omgb_scene_t *scene, const omgb_step_params_t *params, int iters,
+                            const double *obstacle_weights, const double *smoothness_weights,
+                            const double *step_sizes, int stop_on_terminate, int batch, double *xi,
+                            const double *start, const double *end, const double *goal_rows, uint8_t *done,
+                            double *info, double *hist_xi, double *hist_info, void *stream);
+
 /* Same as omgb_chomp_step with HOST buffers (pinned or pageable); xi and info are valid on return (the stream is
  * synchronised).  Transfer strategy: omgb_scene_set_host_mode. */
 int omgb_chomp_step_host(omgb_scene_t *scene, const omgb_step_params_t *params, int batch, double *h_xi,
@@ -195,6 +210,36 @@ int omgb_batch_obstacle_cost(omgb_scene_t *scene, const double *joints, int num_
 int omgb_goal_costs(omgb_scene_t *scene, int batch, const double *from, long long from_stride, const double *goals,
                     int num_goals, int goals_shared, int arc_length, double time_interval,
                     int uncheck_finger_collision, float *costs, void *stream);
+
+/* ---- trajectory initialisation and the SDF asset path (no scene; they run on the calling thread's current
+ * CUDA device) ------------------------------------------------------------------------------------------------ */
+
+/* omg/util.py:238-258 for a batch: waypoints DEVICE [B,K,9] fp64 at knots linspace(0,1,K) (the reference always
+ * passes K = 2: start and end), sampled at the n interior points of linspace(0,1,n+2) -> xi DEVICE [B,n,9].
+ * mode 1 = scipy CubicSpline(bc_type="clamped") (cfg.traj_interpolate = "cubic"), mode 0 = interp1d "linear". */
+int omgb_traj_interpolate(const double *waypoints, int batch, int num_knots, int n_waypoints, int mode,
+                          double *xi, void *stream);
+
+/* One object's raw signed-distance grid as loaded from disk (DEVICE pointer). */
+typedef struct {
+    const void *data;
+    int32_t shape[3];   /* logical [X,Y,Z] (SignedDensityField.data.shape) */
+    int32_t layout;     /* 0: stored [X,Y,Z]; 1: stored [Y,X,Z] -- the .pth files hold sdf_torch[0,0] =
+                           data.permute(1,0,2) (real_world/convert_sdf.py:43, undone by omg/sdf_tools.py:191) */
+    int32_t dtype;      /* 0: fp32, 1: fp64 */
+    float scale;        /* SignedDensityField.resize ratio (omg/sdf_tools.py:37-39, fp32 multiply); 1 = none */
+} omgb_sdf_source_t;
+
+/* Env.combine_sdfs (omg/core.py:366-411): sources HOST [O] -> d_out DEVICE [O,X,Y,Z] fp32, every grid in the corner
+ * of its slot, the rest 1.0.  (The [O,10] limits are host arithmetic on 10 numbers per object; the host mirror
+ * computes them with the reference's own expression.) */
+int omgb_sdf_pack(const omgb_sdf_source_t *sources, int num_objects, int dim_x, int dim_y, int dim_z, float *d_out,
+                  void *stream);
+
+/* PointEnv.compute_sdf_from_points (omg/core.py:426-457): for every voxel (gx[i], gy[j], gz[k]) the distance to the
+ * nearest of d_points [N,3] (all DEVICE fp64) -> d_out32 [X,Y,Z] fp32 and/or d_out64 fp64 (either may be NULL). */
+int omgb_point_sdf(const double *d_points, int num_points, const double *d_gx, const double *d_gy,
+                   const double *d_gz, int dim_x, int dim_y, int dim_z, float *d_out32, double *d_out64, void *stream);
 
 #ifdef __cplusplus
 }

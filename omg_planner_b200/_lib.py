@@ -8,7 +8,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(_HERE)
 LIB_PATH = os.environ.get("OMGB_LIB") or os.path.join(_HERE, "lib", "libomgb200.so")   # OMGB_LIB: A/B experiments
 SOURCES = [os.path.join(_HERE, "csrc", f) for f in ("omgb200.cu", "chomp_kernels.cuh", "goal_kernels.cuh",
-                                                     "sdf_device.cuh")] + [
+                                                     "sdf_device.cuh", "sdf_asset_kernels.cuh", "traj_kernels.cuh")] + [
     os.path.join(ROOT, "include", "omgb200.h")]
 
 INFO_STRIDE = 16
@@ -19,7 +19,8 @@ INFO_KEYS = ["obs", "smooth", "cost", "collide", "reach", "grad", "weighted_obs_
 EXPORTS = ["omgb_version", "omgb_last_error", "omgb_scene_create", "omgb_scene_destroy", "omgb_scene_set_robot",
            "omgb_scene_set_sdf", "omgb_scene_set_profile", "omgb_scene_set_options", "omgb_scene_set_host_mode", "omgb_launch_count", "omgb_scene_set_objects", "omgb_scene_set_metric",
            "omgb_sdf_loss_workspace_bytes", "omgb_sdf_loss", "omgb_chomp_step", "omgb_chomp_plan",
-           "omgb_chomp_step_host", "omgb_batch_obstacle_cost", "omgb_goal_costs"]
+           "omgb_chomp_step_host", "omgb_batch_obstacle_cost", "omgb_goal_costs", "omgb_chomp_plan_history",
+           "omgb_traj_interpolate", "omgb_sdf_pack", "omgb_point_sdf"]
 
 
 class StepParams(ctypes.Structure):
@@ -33,6 +34,12 @@ class StepParams(ctypes.Structure):
         ("smoothness_weight", ctypes.c_double), ("step_size", ctypes.c_double), ("clip_grad_scale", ctypes.c_double),
         ("terminate_smooth_loss", ctypes.c_double), ("link_smooth_weight", ctypes.c_double * 9),
     ]
+
+
+class SdfSource(ctypes.Structure):
+    """omgb_sdf_source_t"""
+    _fields_ = [("data", ctypes.c_void_p), ("shape", ctypes.c_int32 * 3), ("layout", ctypes.c_int32),
+                ("dtype", ctypes.c_int32), ("scale", ctypes.c_float)]
 
 
 def nvcc_command(out=LIB_PATH):
@@ -83,6 +90,10 @@ def lib():
     L.omgb_sdf_loss.argtypes = [vp] * 8 + [ci] * 5 + [vp] * 5
     L.omgb_chomp_step.argtypes = [vp, ctypes.POINTER(StepParams), ci] + [vp] * 11
     L.omgb_chomp_plan.argtypes = [vp, ctypes.POINTER(StepParams), ci, vp, vp, vp, ci, ci] + [vp] * 7
+    L.omgb_chomp_plan_history.argtypes = [vp, ctypes.POINTER(StepParams), ci, vp, vp, vp, ci, ci] + [vp] * 9
+    L.omgb_traj_interpolate.argtypes = [vp, ci, ci, ci, ci, vp, vp]
+    L.omgb_sdf_pack.argtypes = [ctypes.POINTER(SdfSource), ci, ci, ci, ci, vp, vp]
+    L.omgb_point_sdf.argtypes = [vp, ci, vp, vp, vp, ci, ci, ci, vp, vp, vp]
     L.omgb_chomp_step_host.argtypes = [vp, ctypes.POINTER(StepParams), ci] + [vp] * 6
     L.omgb_batch_obstacle_cost.argtypes = [vp, vp, ci, ci, vp, cd, ci, vp, vp, vp, vp]
     L.omgb_goal_costs.argtypes = [vp, ci, vp, ctypes.c_longlong, vp, ci, ci, ci, cd, ci, vp, vp]

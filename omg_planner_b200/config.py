@@ -29,7 +29,16 @@ class ChompConfig(object):
         use_standoff=True, pre_terminate=True, uncheck_finger_collision=0, allow_collision_point=5,
         soft_joint_limit_padding=0.2, clip_grad_scale=10.0, consider_finger=False, reach_tail_length=5,
         timesteps=30, time_interval=0.1, report_cost=False, report_time=False, timeout=-1.0,
-        base_link="panda_link0", ol_alg="MD", dist_eps=0.1, normalize_cost=True, traj_init="grasp")
+        base_link="panda_link0", ol_alg="MD", dist_eps=0.1, normalize_cost=True, traj_init="grasp",
+        # trajectory initialisation / outer loop (omg/config.py:63,89,96-99,69,129)
+        traj_interpolate="cubic", dynamic_timestep=False, traj_delta=0.05, traj_max_step=50, traj_min_step=2,
+        goal_idx=-2, silent=True, scene_file="",
+        # SDF assets (omg/config.py:54,55,60)
+        target_size=1.0, obstacle_size=1, penalize_constant=5,
+        # goal-set construction (omg/config.py:53,66,71,82,83,87,88,94,95,101,102)
+        ik_clearance=0.03, goal_set_max_num=100, ik_seed_num=12, standoff_dist=0.08, remove_flip_grasp=True,
+        augment_flip_grasp=True, target_hand_filter_angle=120, increment_iks=False, ik_parallel=True,
+        y_upsample=False, z_upsample=True)
 
     def __init__(self, **kw):
         for k, v in self._DEFAULTS.items():

@@ -121,6 +121,8 @@ struct StepArgs {
     const int *order;        // [B] or null: CTA -> trajectory map (longest-first scheduling hint; never changes results)
     int *cta_cost;           // [B] or null: clocks this trajectory's CTA took (feeds the next launch's order)
     long long *prof;         // [B,16] or null: clock64() at phase boundaries (diagnostic)
+    double *hist_xi;         // [iters,B,n,9] or null: xi after every iteration (Planner.history_trajectories[1:])
+    double *hist_info;       // [iters,B,16] or null: the info row of every iteration (Planner.info)
     DilDesc dil;
     SmemLayout lay;          // computed on the host (make_layout)
     RobotParams rp;
@@ -1068,7 +1070,29 @@ __device__ __forceinline__ void chomp_iteration(const StepArgs &a, unsigned char
         if (a.cta_cost) a.cta_cost[b] = (int)min((long long)0x7fffffff, clock64() - t_begin);
     }
     __syncwarp();
-    if (tid < OMGB_INFO_STRIDE) a.info[(size_t)b * OMGB_INFO_STRIDE + tid] = s_red[tid];
+    if (tid < OMGB_INFO_STRIDE) {
+        a.info[(size_t)b * OMGB_INFO_STRIDE + tid] = s_red[tid];
+        if (a.hist_info) a.hist_info[((size_t)iteration * a.batch + b) * OMGB_INFO_STRIDE + tid] = s_red[tid];
+    }
+    if (a.hist_xi) {   // planner.py:622: history_trajectories.append(np.copy(traj.data))
+        double *h = a.hist_xi + ((size_t)iteration * a.batch + b) * (size_t)(n * ND);
+        for (int k = tid; k < n * ND; k += nthr) h[k] = s_xi[k];
+    }
+}
+
+// A trajectory frozen by stop_on_terminate keeps its last state and info row in the history (the reference's loop has
+// ended for it, planner.py:627-628; the host mirror truncates at the recorded iteration).
+__device__ __forceinline__ void copy_history(const StepArgs &a, int b, int it) {
+    if (it <= 0) return;
+    const int n = a.prm.n_waypoints;
+    if (a.hist_xi) {
+        const double *src = a.hist_xi + ((size_t)(it - 1) * a.batch + b) * (size_t)(n * ND);
+        double *dst = a.hist_xi + ((size_t)it * a.batch + b) * (size_t)(n * ND);
+        for (int k = threadIdx.x; k < n * ND; k += blockDim.x) dst[k] = __ldcg(src + k);
+    }
+    if (a.hist_info && threadIdx.x < OMGB_INFO_STRIDE)
+        a.hist_info[((size_t)it * a.batch + b) * OMGB_INFO_STRIDE + threadIdx.x] =
+            __ldcg(a.hist_info + ((size_t)(it - 1) * a.batch + b) * OMGB_INFO_STRIDE + threadIdx.x);
 }
 
 // One launch = one iteration of every trajectory, CTA per trajectory (Optimizer.optimize granularity).
@@ -1079,6 +1103,7 @@ __global__ void __launch_bounds__(THREADS, MINB) chomp_step_kernel(const StepArg
     const int b = a.order ? a.order[blockIdx.x] : (int)blockIdx.x;
     if ((a.active && !a.active[b]) || (a.done && a.done[b])) {
         if (a.cta_cost && threadIdx.x == 0) a.cta_cost[b] = 0;
+        if (a.done && a.done[b]) copy_history(a, b, a.iteration);
         return;
     }
     chomp_iteration<LPI, TOPK>(a, smem, b, a.prm.obstacle_weight, a.prm.smoothness_weight, a.prm.step_size, a.iteration);
@@ -1119,6 +1144,8 @@ __global__ void __launch_bounds__(THREADS, MINB) chomp_plan_kernel(const StepArg
         if (!skip)
             chomp_iteration<LPI, TOPK>(a, smem, b, __ldg(p.sched + 3 * it), __ldg(p.sched + 3 * it + 1),
                                        __ldg(p.sched + 3 * it + 2), it);
+        else
+            copy_history(a, b, it);
         __syncthreads();       // every thread's global stores of this item are issued ...
         if (threadIdx.x == 0) {
             __threadfence();   // ... and visible device-wide before the trajectory is released

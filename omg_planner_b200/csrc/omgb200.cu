@@ -12,6 +12,8 @@
 #include "chomp_kernels.cuh"
 #include "goal_kernels.cuh"
 #include "sdf_device.cuh"
+#include "sdf_asset_kernels.cuh"
+#include "traj_kernels.cuh"
 
 namespace omgb {
 
@@ -869,6 +871,15 @@ extern "C" int omgb_chomp_plan(omgb_scene_t *s, const omgb_step_params_t *prm, i
                                const double *sw, const double *ss, int stop_on_terminate, int batch, double *xi,
                                const double *start, const double *end, const double *goal_rows, uint8_t *done,
                                double *info, void *stream) {
+    return omgb_chomp_plan_history(s, prm, iters, ow, sw, ss, stop_on_terminate, batch, xi, start, end, goal_rows,
+                                   done, info, nullptr, nullptr, stream);
+}
+
+extern "C" int omgb_chomp_plan_history(omgb_scene_t *s, const omgb_step_params_t *prm, int iters, const double *ow,
+                                       const double *sw, const double *ss, int stop_on_terminate, int batch,
+                                       double *xi, const double *start, const double *end, const double *goal_rows,
+                                       uint8_t *done, double *info, double *hist_xi, double *hist_info,
+                                       void *stream) {
     int rc_ = check_step(s, prm, batch, "omgb_chomp_plan");
     if (rc_) return rc_;
     if (iters < 0 || (iters > 0 && (!ow || !sw || !ss))) return fail(OMGB_ERR_INVALID, "omgb_chomp_plan: bad schedule");
@@ -881,6 +892,7 @@ extern "C" int omgb_chomp_plan(omgb_scene_t *s, const omgb_step_params_t *prm, i
     StepArgs a = make_args(s, prm, batch, xi, start, end, goal_rows, nullptr, nullptr, info, nullptr, nullptr);
     a.done = stop_on_terminate ? done : nullptr;
     a.stop_on_terminate = stop_on_terminate;
+    a.hist_xi = hist_xi; a.hist_info = hist_info;
     a.prm.update = 1;
     if (batch == 0 || iters == 0) return OMGB_OK;
     static int env_loop = -1;
@@ -1081,6 +1093,93 @@ extern "C" int omgb_goal_costs(omgb_scene_t *s, int batch, const double *from, l
         if (s->device < 64) cached[s->device] = a.smem_total;
     }
     goal_cost_kernel<THREADS><<<batch * num_goals, THREADS, a.smem_total, (cudaStream_t)stream>>>(a);
+    ++g_launches;
+    OMGB_CUDA(cudaGetLastError());
+    return OMGB_OK;
+}
+
+// ----------------------------------------------------------------------------------------------------
+// trajectory initialisation (omg/util.py:238-258) and the SDF asset path (omg/core.py:366-457); these run on
+// the CURRENT device of the calling thread and need no scene
+// ----------------------------------------------------------------------------------------------------
+static int grid_for(long long work_items, int threads) {
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    long long blocks = (work_items + threads - 1) / threads;
+    const long long cap = (long long)sms * 16;   // grid-stride kernels: a multiple of the SM count
+    if (blocks > cap) blocks = cap;
+    return (int)(blocks < 1 ? 1 : blocks);
+}
+
+extern "C" int omgb_traj_interpolate(const double *waypoints, int batch, int num_knots, int n_waypoints, int mode,
+                                     double *xi, void *stream) {
+    if (batch < 0 || n_waypoints < 0) return fail(OMGB_ERR_INVALID, "omgb_traj_interpolate: negative size");
+    if (num_knots < 2 || num_knots > TRAJ_MAX_KNOTS)
+        return fail(OMGB_ERR_INVALID, "omgb_traj_interpolate: 2 <= num_knots <= 32 required");
+    if (mode != 0 && mode != 1) return fail(OMGB_ERR_INVALID, "omgb_traj_interpolate: mode is 0 (linear) or 1 (cubic)");
+    if (batch == 0 || n_waypoints == 0) return OMGB_OK;
+    if (!waypoints || !xi) return fail(OMGB_ERR_INVALID, "omgb_traj_interpolate: null buffer");
+    const long long total = (long long)batch * n_waypoints * ND;
+    traj_interpolate_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(waypoints, batch, num_knots,
+                                                                                    n_waypoints, mode, xi);
+    ++g_launches;
+    OMGB_CUDA(cudaGetLastError());
+    return OMGB_OK;
+}
+
+struct SdfSourceTable {
+    SdfSource src[OMGB_MAX_OBJECTS];
+};
+
+__global__ void __launch_bounds__(256) sdf_pack_entry(const __grid_constant__ SdfSourceTable tab, int num_objects, int X,
+                                                      int Y, int Z, float *__restrict__ dst);
+
+extern "C" int omgb_sdf_pack(const omgb_sdf_source_t *sources, int num_objects, int dim_x, int dim_y, int dim_z,
+                             float *d_out, void *stream) {
+    if (num_objects < 0 || num_objects > OMGB_MAX_OBJECTS)
+        return fail(OMGB_ERR_INVALID, "omgb_sdf_pack: 0 <= num_objects <= 64 required");
+    if (num_objects == 0) return OMGB_OK;
+    if (!sources || !d_out || dim_x <= 0 || dim_y <= 0 || dim_z <= 0)
+        return fail(OMGB_ERR_INVALID, "omgb_sdf_pack: null buffer or empty shape");
+    SdfSourceTable tab;
+    memset(&tab, 0, sizeof(tab));
+    for (int o = 0; o < num_objects; ++o) {
+        const omgb_sdf_source_t &q = sources[o];
+        if (!q.data || q.shape[0] <= 0 || q.shape[1] <= 0 || q.shape[2] <= 0 || q.shape[0] > dim_x ||
+            q.shape[1] > dim_y || q.shape[2] > dim_z)
+            return fail(OMGB_ERR_INVALID, "omgb_sdf_pack: object grid missing or larger than the padded shape");
+        if ((q.layout != 0 && q.layout != 1) || (q.dtype != 0 && q.dtype != 1))
+            return fail(OMGB_ERR_INVALID, "omgb_sdf_pack: layout and dtype are 0 or 1");
+        tab.src[o].data = q.data;
+        tab.src[o].sx = q.shape[0]; tab.src[o].sy = q.shape[1]; tab.src[o].sz = q.shape[2];
+        tab.src[o].layout = q.layout; tab.src[o].dtype = q.dtype; tab.src[o].scale = q.scale;
+    }
+    const long long groups = (long long)num_objects * dim_x * dim_y * ((dim_z + 3) / 4);
+    sdf_pack_entry<<<grid_for(groups, 256), 256, 0, (cudaStream_t)stream>>>(tab, num_objects, dim_x, dim_y, dim_z, d_out);
+    ++g_launches;
+    OMGB_CUDA(cudaGetLastError());
+    return OMGB_OK;
+}
+
+__global__ void __launch_bounds__(256) sdf_pack_entry(const __grid_constant__ SdfSourceTable tab, int num_objects, int X,
+                                                      int Y, int Z, float *__restrict__ dst) {
+    sdf_pack_body(tab.src, num_objects, X, Y, Z, dst);
+}
+
+extern "C" int omgb_point_sdf(const double *d_points, int num_points, const double *d_gx, const double *d_gy,
+                              const double *d_gz, int dim_x, int dim_y, int dim_z, float *d_out32, double *d_out64,
+                              void *stream) {
+    if (num_points < 1) return fail(OMGB_ERR_INVALID, "omgb_point_sdf: at least one point required");
+    if (dim_x < 0 || dim_y < 0 || dim_z < 0) return fail(OMGB_ERR_INVALID, "omgb_point_sdf: negative shape");
+    const long long total = (long long)dim_x * dim_y * dim_z;
+    if (total == 0) return OMGB_OK;
+    if (!d_points || !d_gx || !d_gy || !d_gz || (!d_out32 && !d_out64))
+        return fail(OMGB_ERR_INVALID, "omgb_point_sdf: null buffer");
+    const long long blocks = (total + 255) / 256;
+    if (blocks > 0x7fffffffLL) return fail(OMGB_ERR_INVALID, "omgb_point_sdf: grid too large");
+    point_sdf_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(d_points, num_points, d_gx, d_gy, d_gz, dim_x,
+                                                                    dim_y, dim_z, d_out32, d_out64);
     ++g_launches;
     OMGB_CUDA(cudaGetLastError());
     return OMGB_OK;

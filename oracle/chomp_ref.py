@@ -66,6 +66,7 @@ class RefConfig(object):
         self.time_interval = 0.1
         # goal selection (omg/config.py:39,67,68,79)
         self.optim_steps = 50
+        self.extra_smooth_steps = 20                      # omg/config.py:77
         self.ol_alg = "MD"
         self.dist_eps = 0.1
         self.normalize_cost = True
