@@ -184,8 +184,11 @@ class ChompEngine(object):
             out["potentials"], out["points"] = dpot, dpts
         return out
 
-    def plan(self, cfg, xi, start, end, goal_rows=None, iters=None, stop_on_terminate=False, first_step=1):
-        """iters fused iterations with the reference's schedules (optimizer.py:63-80)."""
+    def plan(self, cfg, xi, start, end, goal_rows=None, iters=None, stop_on_terminate=False, first_step=1,
+             history=False):
+        """iters fused iterations with the reference's schedules (optimizer.py:63-80) in ONE persistent launch.
+        history=True also records xi and the info row after every iteration (Planner.history_trajectories[1:] and
+        Planner.info, omg/planner.py:621-622): out["hist_xi"] [iters,B,n,9], out["hist_info"] [iters,B,16]."""
         self.set_metric(cfg)
         iters = cfg.optim_steps + cfg.extra_smooth_steps if iters is None else iters
         B, n, c = xi.shape[0], cfg.timesteps, cfg.constraint_rows
@@ -194,12 +197,17 @@ class ChompEngine(object):
         ow, sw, ss = (np.ascontiguousarray(sched[:, k]) for k in range(3))
         info = torch.empty((B, _lib.INFO_STRIDE), dtype=torch.float64, device=xi.device)
         done = torch.zeros((B,), dtype=torch.uint8, device=xi.device)
+        hx = torch.empty((iters, B, n, 9), dtype=torch.float64, device=xi.device) if history else None
+        hi = torch.empty((iters, B, _lib.INFO_STRIDE), dtype=torch.float64, device=xi.device) if history else None
         prm = self.params_from(cfg, True)
-        _lib.check(self.L.omgb_chomp_plan(self._h, ctypes.byref(prm), iters, _hp(ow), _hp(sw), _hp(ss),
-                                          int(stop_on_terminate), B, _dp(xi), _dp(start), _dp(end),
-                                          _dp(goal_rows) if c > 0 else None, _dp(done), _dp(info), _stream()),
-                   "omgb_chomp_plan")
-        return {"info": info, "done": done}
+        _lib.check(self.L.omgb_chomp_plan_history(self._h, ctypes.byref(prm), iters, _hp(ow), _hp(sw), _hp(ss),
+                                                  int(stop_on_terminate), B, _dp(xi), _dp(start), _dp(end),
+                                                  _dp(goal_rows) if c > 0 else None, _dp(done), _dp(info), _dp(hx),
+                                                  _dp(hi), _stream()), "omgb_chomp_plan_history")
+        out = {"info": info, "done": done}
+        if history:
+            out["hist_xi"], out["hist_info"] = hx, hi
+        return out
 
     def set_host_mode(self, mode):
         """0 auto (zero-copy on mapped pinned buffers, else pipelined staging), 1 staged, 2 staged + pipelined,

@@ -1,0 +1,227 @@
+"""Planner: the reference's outer loop (omg/planner.py:90-135, 187-222, 600-653) over the fused kernels.
+
+  * fixed goal, or a goal set without goal switching (ol_alg "Baseline"/"Proj"): the whole plan -- every iteration of
+    every trajectory, early exit on terminate, history_trajectories and the info list -- is ONE persistent launch
+    (omgb_chomp_plan_history) plus one info-only launch for the trajectories that did not terminate.
+  * goal set with the online learner: per iteration one fused goal-scoring launch (Learner.update_goal), the learner's
+    [B,G] update on the host (BASELINE north_star keeps goal reweighting on the host), one fused CHOMP launch.
+
+Same names and results as the reference: `Planner(env, traj)`, `.plan(traj) -> info list`, `.history_trajectories`,
+`.info`, `.selected_goals`, `.cost`, `.optim`, `.learner`, `.grasp_init(env)`.  Goal sets come in through
+env.objects[target].grasps / .reach_grasps (built by goal_set.py from grasp poses, or given).
+Batched extension: traj.data [B,n,9]; then `.info` is a list (per trajectory) of info lists and
+`.history_trajectories` a list (per trajectory) of [len,n,9] arrays, each cut where the reference's loop would have
+stopped for that trajectory."""
+import time
+
+import numpy as np
+import torch
+
+from . import _lib
+from .cost import Cost
+from .online_learner import Learner
+from .optimizer import Optimizer
+
+_INFO_FLAGS = ("terminate", "violate_limit", "execute", "failure_terminate")
+
+
+def info_from_row(cfg, r, n):
+    """info dict (omg/cost.py:509-530) from one omgb info row; the fused plan does not keep per-iteration gradients."""
+    return {
+        "collision_pts": None, "obs": r[0], "smooth": r[1], "grasp": 0, "weighted_obs": None, "weighted_smooth": None,
+        "weighted_smooth_grad": r[7], "weighted_obs_grad": r[6], "weighted_grasp_grad": 0, "weighted_grasp": 0,
+        "failure_terminate": bool(r[11]), "cost": r[2], "grad": r[5], "terminate": bool(r[8]), "collide": r[3],
+        "standoff_idx": n - cfg.reach_tail_length if cfg.use_standoff else n - 1, "reach": r[4],
+        "execute": bool(r[10]), "violate_limit": bool(r[9]), "p_in": r[12], "text": [],
+    }
+
+
+class Planner(object):
+    def __init__(self, env, traj, lazy=False):
+        self.cfg = env.config
+        self.env = env
+        self.traj = traj
+        self.cost = Cost(env)
+        self.optim = Optimizer(env, self.cost)
+        self.lazy = lazy
+        if self.cfg.goal_set_proj:
+            self.grasp_init(env)
+            self.learner = Learner(env, traj, self.cost)
+        else:
+            self.traj.interpolate_waypoints()
+        self.history_trajectories = []
+        self.info = []
+        self.selected_goals = []
+
+    def update(self, env, traj):
+        """omg/planner.py:121-152 without the grasp loading."""
+        self.cfg = env.config
+        self.env = env
+        self.traj = traj
+        self.cost.env = env
+        self.cost.cfg = env.config
+        if len(env.objects) > 0:
+            self.cost.target_obj = env.objects[env.target_idx]
+        self.optim = Optimizer(env, self.cost)
+        if self.cfg.goal_set_proj:
+            self.grasp_init(env)
+            self.learner = Learner(env, traj, self.cost)
+        else:
+            self.traj.interpolate_waypoints()
+        self.history_trajectories, self.info = [], []
+
+    def grasp_init(self, env=None):
+        """omg/planner.py:187-222: goal set from the target's grasps, initial goal by cfg.goal_idx, trajectory
+        re-initialised towards it.  Batched: goal_set [B,G,9] / start [B,9] select per trajectory."""
+        cfg, traj = self.cfg, self.traj
+        env = self.env if env is None else env
+        if cfg.scene_file == "" or cfg.traj_init == "grasp":
+            if len(env.objects) > 0:
+                target = env.objects[env.target_idx]
+                if len(target.grasps) > 0:
+                    traj.goal_set = target.grasps
+                    traj.goal_potentials = getattr(target, "grasp_potentials", [])
+                if cfg.goal_set_proj and cfg.use_standoff and len(target.reach_grasps) > 0:
+                    traj.goal_set = np.asarray(target.reach_grasps)[..., -1, :]
+        if len(traj.goal_set) == 0:
+            return
+        gs = np.asarray(traj.goal_set, dtype=np.float64)
+        start = np.asarray(traj.start, dtype=np.float64)
+        batched = gs.ndim == 3
+        st = start[:, None, :] if start.ndim == 2 else start
+        proj_dist = np.linalg.norm((st - gs) * cfg.link_smooth_weight, axis=-1)
+        traj.goal_quality = np.ones(proj_dist.shape)
+        if cfg.goal_idx >= 0:
+            idx = np.full(proj_dist.shape[:-1], cfg.goal_idx, dtype=int)
+        elif cfg.goal_idx == -1:
+            pots = np.asarray(getattr(traj, "goal_potentials", 0.0))
+            pots = pots if pots.size else 0.0
+            idx = np.argmin(pots + cfg.dist_eps * proj_dist, axis=-1)
+        else:
+            idx = np.zeros(proj_dist.shape[:-1], dtype=int)
+        if cfg.ol_alg == "Proj":
+            idx = np.argmin(proj_dist, axis=-1)
+        if batched:
+            traj.goal_idx = np.asarray(idx)
+            traj.end = gs[np.arange(gs.shape[0]), traj.goal_idx]
+        else:
+            traj.goal_idx = int(idx)
+            traj.end = traj.goal_set[traj.goal_idx]
+        traj.interpolate_waypoints()
+
+    # ---- the outer loop ---------------------------------------------------------------------------------
+    def plan(self, traj):
+        """omg/planner.py:600-653."""
+        cfg = self.cfg
+        batched = np.asarray(traj.data).ndim == 3
+        self.history_trajectories = [np.copy(traj.data)]
+        self.info = []
+        self.selected_goals = []
+        start_time_ = time.time()
+        alg_switch = cfg.ol_alg != "Baseline" and cfg.ol_alg != "Proj"
+        if cfg.goal_set_proj and len(traj.goal_set) == 0:
+            return self.info                                    # "planning not run"
+        iters = cfg.optim_steps + cfg.extra_smooth_steps
+        if cfg.goal_set_proj and alg_switch:
+            self._plan_with_learner(traj, iters, start_time_)
+        else:
+            self._plan_fused(traj, iters)
+        plan_time = time.time() - start_time_
+        for lst in (self.info if batched else [self.info]):
+            lst[-1]["time"] = plan_time
+        return self.info
+
+    def _plan_with_learner(self, traj, iters, start_time_):
+        """Goal switching: the reference's loop verbatim over the fused Learner / Optimizer calls.  A batch runs
+        until every trajectory has terminated; per-trajectory results are cut at the trajectory's own stop."""
+        cfg = self.cfg
+        batched = np.asarray(traj.data).ndim == 3
+        B = np.asarray(traj.data).shape[0] if batched else 1
+        infos, hist, sel = [], [np.copy(traj.data)], []
+        stop = np.full(B, -1)
+        for t in range(iters):
+            if t < cfg.optim_steps:
+                self.learner.update_goal()
+                sel.append(np.copy(traj.goal_idx))
+            info = self.optim.optimize(traj, force_update=True)
+            infos.append(info)
+            hist.append(np.copy(traj.data))
+            term = np.array([i["terminate"] for i in (info if batched else [info])])
+            if t > 0:
+                stop[(stop < 0) & term] = t
+            if (stop >= 0).all():
+                break
+            if cfg.timeout != -1 and time.time() - start_time_ > cfg.timeout and t > 0:
+                break
+        final = None
+        if (stop < 0).any():
+            final = self.optim.optimize(traj, info_only=True)
+        if not batched:
+            self.info = infos + ([final] if final is not None else [])
+            self.history_trajectories = hist if final is not None else hist[:-1]
+            self.selected_goals = [int(s) for s in sel]
+            return
+        self.info, self.history_trajectories, self.selected_goals = [], [], []
+        # a trajectory whose loop ended early keeps the state (and goal) it had then (the batch kept stepping it)
+        data = np.array(traj.data)
+        for b in np.nonzero(stop >= 0)[0]:
+            data[b] = hist[stop[b] + 1][b]
+            if sel:
+                traj.goal_idx[b] = sel[min(stop[b], len(sel) - 1)][b]
+                traj.end[b] = np.asarray(traj.goal_set)[b, traj.goal_idx[b]]
+        traj.set(data)
+        for b in range(B):
+            last = stop[b] if stop[b] >= 0 else len(infos) - 1
+            lst = [infos[t][b] for t in range(last + 1)]
+            h = [hist[t][b] for t in range(last + 2)]
+            if stop[b] >= 0:
+                del h[-1]
+            else:
+                lst.append(final[b])
+            self.info.append(lst)
+            self.history_trajectories.append(np.stack(h))
+            self.selected_goals.append([int(s[b]) for s in sel[:min(last + 1, cfg.optim_steps)]])
+
+    def _plan_fused(self, traj, iters):
+        """No goal switching: one persistent launch for the whole plan, one info-only launch afterwards."""
+        cfg, cost = self.cfg, self.cost
+        cost.sync()
+        ecfg = cost.engine_cfg()
+        xi, start, end, rows, batched = cost._traj_tensors(traj)
+        B, n = xi.shape[0], xi.shape[1]
+        xi0 = xi.clone()
+        first = self.optim.step + 1
+        out = cost.engine.plan(ecfg, xi, start, end, rows, iters=iters, stop_on_terminate=True, first_step=first,
+                               history=True)
+        hist_info = out["hist_info"].cpu().numpy()                      # [iters,B,16]
+        hist_xi = out["hist_xi"].cpu().numpy()
+        term = hist_info[:, :, 8] > 0
+        term[0] = False                                                 # the t > 0 rule (planner.py:627)
+        stopped = term.any(0)
+        stop = np.where(stopped, term.argmax(0), iters - 1)             # last iteration run, per trajectory
+        # the reference's Optimizer.step counter: one update() per optimize() call (optimizer.py:59-63)
+        self.optim.step += int(stop.max()) + 1
+        final = None
+        if (~stopped).any():
+            active = torch.from_numpy((~stopped).astype(np.uint8)).to(xi.device)
+            self.optim.update()                                         # schedule of the info-only call
+            ecfg = cost.engine_cfg()
+            final = cost.engine.step(ecfg, xi, start, end, rows, active=active, update=0)["info"].cpu().numpy()
+        infos, hists = [], []
+        xi0 = xi0.cpu().numpy()
+        for b in range(B):
+            k = int(stop[b])
+            lst = [info_from_row(cfg, hist_info[t, b], n) for t in range(k + 1)]
+            h = [xi0[b]] + [hist_xi[t, b] for t in range(k + 1)]
+            if stopped[b]:
+                del h[-1]                                               # planner.py:634-635
+            else:
+                lst.append(info_from_row(cfg, final[b], n))
+            infos.append(lst)
+            hists.append(h)
+        new = xi.cpu().numpy()
+        traj.set(new if batched else new[0])
+        if batched:
+            self.info, self.history_trajectories = infos, [np.stack(h) for h in hists]
+        else:
+            self.info, self.history_trajectories = infos[0], hists[0]
