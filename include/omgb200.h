@@ -25,6 +25,10 @@
  *   omgb_sdf_pack              SignedDensityField.from_pth/.resize  omg/sdf_tools.py:187-193, 37-39,
  *                              + Env.combine_sdfs                   omg/core.py:366-411
  *   omgb_point_sdf             PointEnv.compute_sdf_from_points     omg/core.py:426-457 (scipy cKDTree.query)
+ *   omgb_ik_solve              solve_one_pose_ik for every grasp x  omg/planner.py:16-87, 296-455 ->
+ *                              seed (robot.inverse_kinematics)      ycb_render/robotPose/robot_pykdl.py:257-289 ->
+ *                                                                   orocos_kdl/src/chainiksolverpos_nr_jl.cpp:61-101
+ *   omgb_hand_poses            forward_kinematics_parallel()[:, 7]  omg/planner.py:262-283 (hand frame only)
  */
 #ifndef OMGB200_H_
 #define OMGB200_H_
@@ -240,6 +244,30 @@ int omgb_sdf_pack(const omgb_sdf_source_t *sources, int num_objects, int dim_x, 
  * nearest of d_points [N,3] (all DEVICE fp64) -> d_out32 [X,Y,Z] fp32 and/or d_out64 fp64 (either may be NULL). */
 int omgb_point_sdf(const double *d_points, int num_points, const double *d_gx, const double *d_gy,
                    const double *d_gz, int dim_x, int dim_y, int dim_z, float *d_out32, double *d_out64, void *stream);
+
+/* ---- goal-set construction: batched inverse kinematics ---------------------------------------------
+ * The reference solves IK with KDL's ChainIkSolverPos_NR_JL (Newton-Raphson with joint limits, <= 100 steps, 1e-6 twist
+ * tolerance) over ChainIkSolverVel_pinv (truncated pseudo-inverse from SVD_HH) for the chain panda_link0 -> panda_hand
+ * (robot_pykdl.py:114-146), one grasp pose and one seed at a time in a 4-process pool (omg/planner.py:400-436).
+ * omgb_ik_solve runs the same iteration for every (pose, seed) pair in one launch.
+ *
+ * chain_frames HOST [8,4,4] fp64: parent->joint transforms of the 7 arm joints and the fixed hand joint
+ *   (robot_kinematics._pose_0[:8]); every joint turns about its local z (the URDF's axis="0 0 1").
+ * q_min / q_max HOST [7]: the padded joint limits handed to the solver (robot_pykdl.py:123-138).
+ * d_targets DEVICE [P, T, 7] fp64: for pose p the chain of T targets (position xyz, quaternion xyzw) solved in order,
+ *   each seeded with the previous solution (solve_one_pose_ik: the last standoff pose first, then the reach tail);
+ *   T = 1 for a single solve.
+ * d_seeds DEVICE [S, 7].  Outputs: d_sols DEVICE [P, S, T, 7]; d_solved DEVICE int32 [P, S] = number of solves that
+ *   succeeded before the first failure (== T: the whole chain solved); d_steps DEVICE int32 [P, S, T] or NULL =
+ *   Newton steps of each solve attempted. */
+int omgb_ik_solve(const double *chain_frames, const double *q_min, const double *q_max, const double *d_targets,
+                  int num_poses, int chain_length, const double *d_seeds, int num_seeds, double *d_sols,
+                  int *d_solved, int *d_steps, void *stream);
+
+/* Hand frame (panda_hand in the base frame) of num_configs joint vectors: d_joints DEVICE fp64, row m at
+ * d_joints + m * joint_stride (first 7 entries used) -> d_poses DEVICE [M,4,4] row-major. */
+int omgb_hand_poses(const double *chain_frames, const double *d_joints, long long joint_stride, int num_configs,
+                    double *d_poses, void *stream);
 
 #ifdef __cplusplus
 }

@@ -8,7 +8,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(_HERE)
 LIB_PATH = os.environ.get("OMGB_LIB") or os.path.join(_HERE, "lib", "libomgb200.so")   # OMGB_LIB: A/B experiments
 SOURCES = [os.path.join(_HERE, "csrc", f) for f in ("omgb200.cu", "chomp_kernels.cuh", "goal_kernels.cuh",
-                                                     "sdf_device.cuh", "sdf_asset_kernels.cuh", "traj_kernels.cuh")] + [
+                                                     "sdf_device.cuh", "sdf_asset_kernels.cuh", "traj_kernels.cuh",
+                                                     "ik_kernels.cu", "host_common.h")] + [
     os.path.join(ROOT, "include", "omgb200.h")]
 
 INFO_STRIDE = 16
@@ -20,7 +21,7 @@ EXPORTS = ["omgb_version", "omgb_last_error", "omgb_scene_create", "omgb_scene_d
            "omgb_scene_set_sdf", "omgb_scene_set_profile", "omgb_scene_set_options", "omgb_scene_set_host_mode", "omgb_launch_count", "omgb_scene_set_objects", "omgb_scene_set_metric",
            "omgb_sdf_loss_workspace_bytes", "omgb_sdf_loss", "omgb_chomp_step", "omgb_chomp_plan",
            "omgb_chomp_step_host", "omgb_batch_obstacle_cost", "omgb_goal_costs", "omgb_chomp_plan_history",
-           "omgb_traj_interpolate", "omgb_sdf_pack", "omgb_point_sdf"]
+           "omgb_traj_interpolate", "omgb_sdf_pack", "omgb_point_sdf", "omgb_ik_solve", "omgb_hand_poses"]
 
 
 class StepParams(ctypes.Structure):
@@ -42,9 +43,23 @@ class SdfSource(ctypes.Structure):
                 ("dtype", ctypes.c_int32), ("scale", ctypes.c_float)]
 
 
-def nvcc_command(out=LIB_PATH):
-    return ["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-shared",
-            "-Xcompiler", "-fPIC,-ffp-contract=off", "-o", out, SOURCES[0]]
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler",
+              "-fPIC,-ffp-contract=off"]
+# translation units: (source, extra flags).  ik_kernels.cu is compiled without FMA contraction so that the Newton
+# iteration rounds like the CPU code it is checked against.
+UNITS = [("omgb200.cu", []), ("ik_kernels.cu", ["-fmad=false"])]
+
+
+def nvcc_commands(out=LIB_PATH, verbose=False):
+    obj_dir = os.path.join(os.path.dirname(out), "obj")
+    cmds, objs = [], []
+    for src, extra in UNITS:
+        obj = os.path.join(obj_dir, src.replace(".cu", ".o"))
+        cmds.append(["nvcc"] + (["-Xptxas=-v"] if verbose else []) + NVCC_FLAGS + extra +
+                    ["-c", "-o", obj, os.path.join(_HERE, "csrc", src)])
+        objs.append(obj)
+    cmds.append(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", out] + objs)
+    return obj_dir, cmds
 
 
 def build(force=False, verbose=False):
@@ -53,10 +68,13 @@ def build(force=False, verbose=False):
     if not force and os.path.exists(LIB_PATH) and os.path.getmtime(LIB_PATH) >= newest:
         return LIB_PATH
     os.makedirs(os.path.dirname(LIB_PATH), exist_ok=True)
-    cmd = nvcc_command()
-    if verbose:
-        cmd.insert(1, "-Xptxas=-v")
-    subprocess.check_call(cmd)
+    obj_dir, cmds = nvcc_commands(verbose=verbose)
+    os.makedirs(obj_dir, exist_ok=True)
+    procs = [subprocess.Popen(c) for c in cmds[:-1]]
+    for p, c in zip(procs, cmds[:-1]):
+        if p.wait() != 0:
+            raise subprocess.CalledProcessError(p.returncode, c)
+    subprocess.check_call(cmds[-1])
     return LIB_PATH
 
 
@@ -94,6 +112,8 @@ def lib():
     L.omgb_traj_interpolate.argtypes = [vp, ci, ci, ci, ci, vp, vp]
     L.omgb_sdf_pack.argtypes = [ctypes.POINTER(SdfSource), ci, ci, ci, ci, vp, vp]
     L.omgb_point_sdf.argtypes = [vp, ci, vp, vp, vp, ci, ci, ci, vp, vp, vp]
+    L.omgb_ik_solve.argtypes = [vp, vp, vp, vp, ci, ci, vp, ci, vp, vp, vp, vp]
+    L.omgb_hand_poses.argtypes = [vp, vp, ctypes.c_longlong, ci, vp, vp]
     L.omgb_chomp_step_host.argtypes = [vp, ctypes.POINTER(StepParams), ci] + [vp] * 6
     L.omgb_batch_obstacle_cost.argtypes = [vp, vp, ci, ci, vp, cd, ci, vp, vp, vp, vp]
     L.omgb_goal_costs.argtypes = [vp, ci, vp, ctypes.c_longlong, vp, ci, ci, ci, cd, ci, vp, vp]

@@ -9,6 +9,7 @@
 #include <vector>
 
 #include "../../include/omgb200.h"
+#include "host_common.h"
 #include "chomp_kernels.cuh"
 #include "goal_kernels.cuh"
 #include "sdf_device.cuh"
@@ -24,6 +25,8 @@ static int fail(int code, const std::string &msg) {
     g_err = msg;
     return code;
 }
+int host_fail(int code, const std::string &msg) { return fail(code, msg); }
+void host_count_launch() { ++g_launches; }
 
 #define OMGB_CUDA(call)                                                                      \
     do {                                                                                     \

@@ -84,20 +84,20 @@ class Learner(object):
         gs = np.asarray(traj.goal_set, dtype=np.float64)
         self.batched = np.asarray(traj.data).ndim == 3
         self.B = np.asarray(traj.data).shape[0] if self.batched else 1
-        self.N = gs.shape[-2]
+        self.N = gs.shape[-2] if gs.ndim >= 2 else 0   # (no goals yet: the reference builds empty arrays too)
         self.T = self.cfg.optim_steps
         B, N = self.B, self.N
         self.Ti = np.zeros((B, N))
         self.Tis = []
         self.weights = np.ones(N)
         self.t = 0.0
-        self._p = np.ones((B, N)) / N
+        self._p = np.ones((B, N)) / max(N, 1)
         self.sum_costs = np.zeros((B, N))
         self.eta = np.sqrt(np.log(N + 1) / self.T)
         self.etas = [self.eta * (2 ** x) for x in [-2, -1, 0, 2, 4]]
         self.delta = np.ones(N) / (4 * N + 1)
         self.num_experts = len(self.etas)
-        self._experts_p = np.ones((B, self.num_experts, N)) / N
+        self._experts_p = np.ones((B, self.num_experts, N)) / max(N, 1)
         self.experts_costs = np.zeros((B, self.num_experts))
         self._q = np.ones((B, self.num_experts)) / self.num_experts
 

@@ -19,6 +19,7 @@ import torch
 
 from . import _lib
 from .cost import Cost
+from .goal_set import GoalSetMixin
 from .online_learner import Learner
 from .optimizer import Optimizer
 
@@ -36,7 +37,7 @@ def info_from_row(cfg, r, n):
     }
 
 
-class Planner(object):
+class Planner(GoalSetMixin):
     def __init__(self, env, traj, lazy=False):
         self.cfg = env.config
         self.env = env
@@ -45,6 +46,14 @@ class Planner(object):
         self.optim = Optimizer(env, self.cost)
         self.lazy = lazy
         if self.cfg.goal_set_proj:
+            # omg/planner.py:103-114.  Objects that carry grasp poses (compute_grasp) get their goal sets built here
+            # -- batched IK, flip augmentation, collision / diversity filters (goal_set.py); objects whose
+            # .grasps / .reach_grasps are already set are used as they are.
+            if getattr(self.cfg, "use_external_grasp", False):
+                self.load_goal_from_external(self.cfg.external_grasps)
+            if self.cfg.scene_file == "" or self.cfg.traj_init == "grasp":
+                self.load_grasp_set(env)
+                self.setup_goal_set(env)
             self.grasp_init(env)
             self.learner = Learner(env, traj, self.cost)
         else:
@@ -96,7 +105,8 @@ class Planner(object):
         elif cfg.goal_idx == -1:
             pots = np.asarray(getattr(traj, "goal_potentials", 0.0))
             pots = pots if pots.size else 0.0
-            idx = np.argmin(pots + cfg.dist_eps * proj_dist, axis=-1)
+            costs = pots + cfg.dist_eps * proj_dist
+            idx = np.argmin(costs, axis=-1) if batched else np.argmin(costs)   # (the reference's flat argmin)
         else:
             idx = np.zeros(proj_dist.shape[:-1], dtype=int)
         if cfg.ol_alg == "Proj":
@@ -105,7 +115,7 @@ class Planner(object):
             traj.goal_idx = np.asarray(idx)
             traj.end = gs[np.arange(gs.shape[0]), traj.goal_idx]
         else:
-            traj.goal_idx = int(idx)
+            traj.goal_idx = int(np.asarray(idx).reshape(-1)[0])
             traj.end = traj.goal_set[traj.goal_idx]
         traj.interpolate_waypoints()
 
