@@ -349,6 +349,15 @@ def run_b200(a):
     }
     if cpu is not None:
         line["cpu_baseline"] = cpu
+    if world == 1 and not a.no_aux:
+        # the kernels either side of the CHOMP loop (goal-set IK, SDF packing, point-cloud field, trajectory
+        # initialisation): reported beside the headline, never part of it
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "tools"))
+            import bench_aux
+            line["aux_kernels"] = bench_aux.run_aux(peak)
+        except Exception as e:   # noqa: BLE001
+            line["aux_kernels"] = {"error": repr(e)}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -396,6 +405,7 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=64)
     ap.add_argument("--cpu-steps", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-aux", action="store_true")
     a = ap.parse_args()
     if a.impl == "reference":
         run_reference(a)

@@ -1158,8 +1158,16 @@ extern "C" int omgb_sdf_pack(const omgb_sdf_source_t *sources, int num_objects, 
         tab.src[o].sx = q.shape[0]; tab.src[o].sy = q.shape[1]; tab.src[o].sz = q.shape[2];
         tab.src[o].layout = q.layout; tab.src[o].dtype = q.dtype; tab.src[o].scale = q.scale;
     }
-    const long long groups = (long long)num_objects * dim_x * dim_y * ((dim_z + 3) / 4);
-    sdf_pack_entry<<<grid_for(groups, 256), 256, 0, (cudaStream_t)stream>>>(tab, num_objects, dim_x, dim_y, dim_z, d_out);
+    if ((long long)num_objects * dim_x > 65535LL * 1024)
+        return fail(OMGB_ERR_INVALID, "omgb_sdf_pack: too many (object, x) planes");
+    const int plane = dim_y * ((dim_z + 3) / 4);
+    const long long planes = (long long)num_objects * dim_x;
+    if (planes > 0x7fffffffLL) return fail(OMGB_ERR_INVALID, "omgb_sdf_pack: shape too large");
+    int bx = (plane + 1023) / 1024;   // ~4 groups (64 B) per thread
+    if (bx < 1) bx = 1;
+    // grid.y is limited to 65535: fold the rest into z
+    dim3 grid((unsigned)bx, (unsigned)(planes > 65535 ? 65535 : planes), (unsigned)((planes + 65534) / 65535));
+    sdf_pack_entry<<<grid, 256, 0, (cudaStream_t)stream>>>(tab, num_objects, dim_x, dim_y, dim_z, d_out);
     ++g_launches;
     OMGB_CUDA(cudaGetLastError());
     return OMGB_OK;
@@ -1179,10 +1187,11 @@ extern "C" int omgb_point_sdf(const double *d_points, int num_points, const doub
     if (total == 0) return OMGB_OK;
     if (!d_points || !d_gx || !d_gy || !d_gz || (!d_out32 && !d_out64))
         return fail(OMGB_ERR_INVALID, "omgb_point_sdf: null buffer");
-    const long long blocks = (total + 255) / 256;
+    const long long items = (long long)dim_x * dim_y * ((dim_z + POINT_ZV - 1) / POINT_ZV);   // (x, y, z-chunk)
+    const long long blocks = (items + POINT_THREADS - 1) / POINT_THREADS;
     if (blocks > 0x7fffffffLL) return fail(OMGB_ERR_INVALID, "omgb_point_sdf: grid too large");
-    point_sdf_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(d_points, num_points, d_gx, d_gy, d_gz, dim_x,
-                                                                    dim_y, dim_z, d_out32, d_out64);
+    point_sdf_kernel<<<(int)blocks, POINT_THREADS, 0, (cudaStream_t)stream>>>(d_points, num_points, d_gx, d_gy, d_gz,
+                                                                             dim_x, dim_y, dim_z, d_out32, d_out64);
     ++g_launches;
     OMGB_CUDA(cudaGetLastError());
     return OMGB_OK;

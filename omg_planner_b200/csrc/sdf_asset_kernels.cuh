@@ -32,31 +32,42 @@ __device__ __forceinline__ float sdf_source_at(const SdfSource &s, int x, int y,
     return v;
 }
 
-// grid-stride over groups of 4 consecutive z (one 128-bit store each when Z % 4 == 0; scalar tail otherwise)
+// blockIdx.y = (object, x) plane of the padded tensor; threads grid-stride over the plane's (y, z/4) groups: one
+// 128-bit store each when Z % 4 == 0, and one 128-bit load when the source row allows it (both layouts keep z
+// contiguous), so the kernel moves every byte exactly once with full-width transactions.  No 64-bit divisions.
 __device__ __forceinline__ void sdf_pack_body(const SdfSource *__restrict__ src, int num_objects, int X, int Y, int Z,
                                               float *__restrict__ dst) {
     const int zq = (Z + 3) >> 2;
-    const long long per_obj = (long long)X * Y * zq;
-    const long long total = per_obj * num_objects;
-    const bool vec = (Z & 3) == 0;
-    for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < total;
-         g += (long long)gridDim.x * blockDim.x) {
-        const int o = (int)(g / per_obj);
-        long long r = g - (long long)o * per_obj;
-        const int z0 = (int)(r % zq) * 4;
-        r /= zq;
-        const int y = (int)(r % Y), x = (int)(r / Y);
-        const SdfSource s = src[o];
+    const int plane = Y * zq;
+    const long long pl = (long long)blockIdx.z * 65535 + blockIdx.y;   // (object, x) plane
+    const int o = (int)(pl / X), x = (int)(pl - (long long)o * X);
+    if (o >= num_objects) return;
+    const SdfSource s = src[o];
+    const bool vec_st = (Z & 3) == 0;
+    const bool vec_ld = s.dtype == 0 && (s.sz & 3) == 0 && ((reinterpret_cast<size_t>(s.data) & 15) == 0);
+    float *plane_out = dst + ((size_t)o * X + x) * (size_t)Y * Z;
+    for (int g = blockIdx.x * blockDim.x + threadIdx.x; g < plane; g += gridDim.x * blockDim.x) {
+        const int y = g / zq, z0 = (g - y * zq) * 4;
         float v[4];
         const bool row_in = x < s.sx && y < s.sy;
+        if (row_in && vec_ld && z0 + 3 < s.sz) {
+            const size_t idx = s.layout ? ((size_t)y * s.sx + x) * s.sz + z0 : ((size_t)x * s.sy + y) * s.sz + z0;
+            const float4 t = __ldcs(reinterpret_cast<const float4 *>(reinterpret_cast<const float *>(s.data) + idx));
+            v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+            if (s.scale != 1.0f) {
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const int z = z0 + q;
-            v[q] = (row_in && z < s.sz) ? sdf_source_at(s, x, y, z) : 1.0f;
+                for (int q = 0; q < 4; ++q) v[q] = __fmul_rn(v[q], s.scale);
+            }
+        } else {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int z = z0 + q;
+                v[q] = (row_in && z < s.sz) ? sdf_source_at(s, x, y, z) : 1.0f;
+            }
         }
-        float *out = dst + (((size_t)o * X + x) * Y + y) * Z + z0;
-        if (vec) {
-            *reinterpret_cast<float4 *>(out) = make_float4(v[0], v[1], v[2], v[3]);
+        float *out = plane_out + (size_t)y * Z + z0;
+        if (vec_st) {
+            __stcs(reinterpret_cast<float4 *>(out), make_float4(v[0], v[1], v[2], v[3]));
         } else {
 #pragma unroll
             for (int q = 0; q < 4; ++q)
@@ -66,43 +77,68 @@ __device__ __forceinline__ void sdf_pack_body(const SdfSource *__restrict__ src,
 }
 
 constexpr int POINT_TILE = 1024;
+constexpr int POINT_ZV = 8;          // voxels of one z-row per thread
+constexpr int POINT_THREADS = 128;
 
-// One thread per voxel; the cloud streams through shared memory in tiles of POINT_TILE points.
-__global__ void __launch_bounds__(256) point_sdf_kernel(const double *__restrict__ points, int num_points,
-                                                        const double *__restrict__ gx, const double *__restrict__ gy,
-                                                        const double *__restrict__ gz, int X, int Y, int Z,
-                                                        float *__restrict__ out32, double *__restrict__ out64) {
+// One thread per (x, y, chunk of POINT_ZV voxels along z); the cloud streams through shared memory in tiles of
+// POINT_TILE points (every lane reads the same point: broadcast).  The voxels of a thread share x and y, so
+// dx*dx + dy*dy -- the first two terms of cKDTree's sum -- is computed once per point and only (.. + dz*dz) per voxel:
+// the same IEEE operations per (voxel, point) as the reference, 4.6 instead of 9 fp64 instructions.
+__global__ void __launch_bounds__(POINT_THREADS) point_sdf_kernel(const double *__restrict__ points, int num_points,
+                                                                  const double *__restrict__ gx,
+                                                                  const double *__restrict__ gy,
+                                                                  const double *__restrict__ gz, int X, int Y, int Z,
+                                                                  float *__restrict__ out32,
+                                                                  double *__restrict__ out64) {
     __shared__ double s_p[POINT_TILE * 3];
-    const long long total = (long long)X * Y * Z;
-    const long long base = (long long)blockIdx.x * blockDim.x;
-    const long long v = base + threadIdx.x;
-    const bool live = v < total;
-    double px = 0.0, py = 0.0, pz = 0.0;
+    const int chunks = (Z + POINT_ZV - 1) / POINT_ZV;
+    const long long items = (long long)X * Y * chunks;
+    const long long it = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = it < items;
+    double px = 0.0, py = 0.0, pz[POINT_ZV], best[POINT_ZV];
+    int z0 = 0;
+    long long row = 0;
     if (live) {
-        const int z = (int)(v % Z);
-        const long long r = v / Z;
-        px = __ldg(gx + (int)(r / Y)); py = __ldg(gy + (int)(r % Y)); pz = __ldg(gz + z);
+        const int ch = (int)(it % chunks);
+        row = it / chunks;
+        z0 = ch * POINT_ZV;
+        px = __ldg(gx + (int)(row / Y));
+        py = __ldg(gy + (int)(row % Y));
     }
-    double best = __longlong_as_double(0x7ff0000000000000LL);   // +inf
+#pragma unroll
+    for (int v = 0; v < POINT_ZV; ++v) {
+        pz[v] = (live && z0 + v < Z) ? __ldg(gz + z0 + v) : 0.0;
+        best[v] = __longlong_as_double(0x7ff0000000000000LL);   // +inf
+    }
     for (int t0 = 0; t0 < num_points; t0 += POINT_TILE) {
         const int cnt = min(POINT_TILE, num_points - t0);
         __syncthreads();
         for (int k = threadIdx.x; k < cnt * 3; k += blockDim.x) s_p[k] = __ldg(points + (size_t)t0 * 3 + k);
         __syncthreads();
         if (live) {
-#pragma unroll 4
+#pragma unroll 2
             for (int k = 0; k < cnt; ++k) {
-                const double dx = __dsub_rn(px, s_p[3 * k]), dy = __dsub_rn(py, s_p[3 * k + 1]),
-                             dz = __dsub_rn(pz, s_p[3 * k + 2]);
-                const double d2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
-                best = fmin(best, d2);
+                const double qx = s_p[3 * k], qy = s_p[3 * k + 1], qz = s_p[3 * k + 2];
+                const double dx = __dsub_rn(px, qx), dy = __dsub_rn(py, qy);
+                const double dxy = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
+#pragma unroll
+                for (int v = 0; v < POINT_ZV; ++v) {
+                    const double dz = __dsub_rn(pz[v], qz);
+                    best[v] = fmin(best[v], __dadd_rn(dxy, __dmul_rn(dz, dz)));
+                }
             }
         }
     }
     if (live) {
-        const double d = __dsqrt_rn(best);
-        if (out64) out64[v] = d;
-        if (out32) out32[v] = (float)d;
+#pragma unroll
+        for (int v = 0; v < POINT_ZV; ++v) {
+            if (z0 + v < Z) {
+                const double d = __dsqrt_rn(best[v]);
+                const size_t o = (size_t)row * Z + z0 + v;
+                if (out64) out64[o] = d;
+                if (out32) out32[o] = (float)d;
+            }
+        }
     }
 }
 

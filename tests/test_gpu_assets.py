@@ -131,9 +131,9 @@ def test_point_sdf_bit_exact_vs_reference_fixture_and_oracle():
         grids, limits = C.combine_sdfs(env)
         np.testing.assert_array_equal(grids.cpu().numpy(), g[tag + "_sdf_torch"])
         np.testing.assert_array_equal(limits.cpu().numpy(), g[tag + "_limits"])
-    # a table-top sized cloud: 6000 points, ~64^3 voxels, several shared-memory tiles with a ragged last tile
+    # a table-top sized cloud: 2500 points, ~50^3 voxels, several shared-memory tiles with a ragged last tile
     rng = np.random.RandomState(12)
-    pts = rng.uniform([0.2, -0.4, 0.0], [0.9, 0.4, 0.5], (6000, 3))
+    pts = rng.uniform([0.3, -0.3, 0.0], [0.8, 0.3, 0.4], (2500, 3))
     f, d64 = C.compute_sdf_from_points(pts, keep_fp64=True)
     want, origin, _ = A.point_sdf(pts)
     assert d64.shape == want.shape
