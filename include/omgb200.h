@@ -21,6 +21,11 @@
  *   omgb_goal_costs            Learner.cost_vector, device half     omg/online_learner.py:104-150 (omg/util.py:261-290,
  *                                                                   omg/cost.py:192-286 with arc_length, the two sums)
  *   omgb_chomp_plan_history    plan() with history_trajectories     omg/planner.py:605-628
+ *   omgb_chomp_plan_step       one iteration of plan() when the     omg/planner.py:612-628
+ *                              goal changes between iterations
+ *   omgb_learner_update        Learner.update_goal after the        omg/online_learner.py:151-160, 162-249
+ *                              collision costs (cost vector, FTL /
+ *                              FTC / Exp / MD / Proj, goal selection)
  *   omgb_traj_interpolate      Trajectory.interpolate_waypoints     omg/core.py:59-78 -> omg/util.py:238-258
  *   omgb_sdf_pack              SignedDensityField.from_pth/.resize  omg/sdf_tools.py:187-193, 37-39,
  *                              + Env.combine_sdfs                   omg/core.py:366-411
@@ -214,6 +219,48 @@ int omgb_batch_obstacle_cost(omgb_scene_t *scene, const double *joints, int num_
 int omgb_goal_costs(omgb_scene_t *scene, int batch, const double *from, long long from_stride, const double *goals,
                     int num_goals, int goals_shared, int arc_length, double time_interval,
                     int uncheck_finger_collision, float *costs, void *stream);
+
+/* One iteration (index `iteration`, 0-based) of a plan whose goal rows may change between iterations (goal-set mode
+ * with the online learner): omgb_chomp_step with the plan's bookkeeping -- trajectories with done[b] != 0 are frozen,
+ * done[b] is set when iteration > 0 reports terminate (stop_on_terminate), hist_xi / hist_info (layouts of
+ * omgb_chomp_plan_history, may be NULL) receive slot `iteration`.  The schedule comes from params. */
+int omgb_chomp_plan_step(omgb_scene_t *scene, const omgb_step_params_t *params, int iteration,
+                         int stop_on_terminate, int batch, double *xi, const double *start, const double *end,
+                         const double *goal_rows, uint8_t *done, double *info, double *hist_xi, double *hist_info,
+                         void *stream);
+
+/* ---- the online learner's goal re-weighting (omg/online_learner.py:151-249), all pointers DEVICE ------------------ */
+enum {
+    OMGB_LEARNER_FTL = 0, OMGB_LEARNER_FTC = 1, OMGB_LEARNER_EXP = 2, OMGB_LEARNER_MD = 3, OMGB_LEARNER_PROJ = 4,
+    OMGB_LEARNER_INIT = 5   /* Learner.__init__ (:91-102): goal = argmin of the cost vector, no state change */
+};
+
+typedef struct {
+    int32_t alg;                  /* cfg.ol_alg as one of the enum values above */
+    int32_t num_goals;            /* G = len(traj.goal_set), <= 256 */
+    int32_t n_waypoints;          /* cfg.timesteps */
+    int32_t first_waypoint;       /* the waypoint the goal lines start from (:108-110) */
+    int32_t constraint_rows;      /* c of the goal rows written out (>= 1) */
+    int32_t normalize_cost;       /* cfg.normalize_cost */
+    double base_obstacle_weight;  /* cfg.base_obstacle_weight */
+    double smoothness_base_weight;/* cfg.smoothness_base_weight */
+    double dist_eps;              /* cfg.dist_eps */
+    double eta;                   /* Learner.eta = sqrt(log(G + 1) / optim_steps) (Exp) */
+    double etas[5];               /* Learner.etas (MD experts) */
+} omgb_learner_params_t;
+
+/* For every trajectory b: cost vector from collision [B,G] fp32 (omgb_goal_costs) and the joint-difference term
+ * between xi[b, first_waypoint] and goal_set[b, g]; update of the goal distribution; goal_idx[b] = argmax p;
+ * end[b] = goal_set[b, goal_idx]; goal_rows[b] = reach[b, goal_idx] ([c,9]) or, when reach is NULL, goal_set[b, goal_idx]
+ * repeated c times (c = 1 without standoff).
+ * goal_set: [B,G,9] or [G,9] when goals_shared; reach: [B,G,c,9] / [G,c,9] or NULL.
+ * State (in/out, the Learner's fields): p [B,G], sum_costs [B,G], experts_p [B,5,G], experts_costs [B,5], q [B,5], fp64.
+ * done [B] uint8 or NULL: trajectories whose plan has ended keep their goal.  cost_vector [B,G] fp64 out or NULL.
+ * selected [B] int32 out or NULL (the iteration's slot of Planner.selected_goals). */
+int omgb_learner_update(const omgb_learner_params_t *params, int batch, const double *xi, const float *collision,
+                        const double *goal_set, int goals_shared, const double *reach, double *p, double *sum_costs,
+                        double *experts_p, double *experts_costs, double *q, const uint8_t *done, int32_t *goal_idx,
+                        double *end, double *goal_rows, double *cost_vector, int32_t *selected, void *stream);
 
 /* ---- trajectory initialisation and the SDF asset path (no scene; they run on the calling thread's current
  * CUDA device) ------------------------------------------------------------------------------------------------ */

@@ -8,7 +8,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(_HERE)
 LIB_PATH = os.environ.get("OMGB_LIB") or os.path.join(_HERE, "lib", "libomgb200.so")   # OMGB_LIB: A/B experiments
 SOURCES = [os.path.join(_HERE, "csrc", f) for f in ("omgb200.cu", "chomp_kernels.cuh", "goal_kernels.cuh",
-                                                     "sdf_device.cuh", "sdf_asset_kernels.cuh", "traj_kernels.cuh",
+                                                     "sdf_device.cuh", "sdf_asset_kernels.cuh", "traj_kernels.cuh", "learner_kernels.cuh",
                                                      "ik_kernels.cu", "host_common.h")] + [
     os.path.join(ROOT, "include", "omgb200.h")]
 
@@ -21,7 +21,8 @@ EXPORTS = ["omgb_version", "omgb_last_error", "omgb_scene_create", "omgb_scene_d
            "omgb_scene_set_sdf", "omgb_scene_set_profile", "omgb_scene_set_options", "omgb_scene_set_host_mode", "omgb_launch_count", "omgb_scene_set_objects", "omgb_scene_set_metric",
            "omgb_sdf_loss_workspace_bytes", "omgb_sdf_loss", "omgb_chomp_step", "omgb_chomp_plan",
            "omgb_chomp_step_host", "omgb_batch_obstacle_cost", "omgb_goal_costs", "omgb_chomp_plan_history",
-           "omgb_traj_interpolate", "omgb_sdf_pack", "omgb_point_sdf", "omgb_ik_solve", "omgb_hand_poses"]
+           "omgb_traj_interpolate", "omgb_sdf_pack", "omgb_point_sdf", "omgb_ik_solve", "omgb_hand_poses", "omgb_chomp_plan_step",
+           "omgb_learner_update"]
 
 
 class StepParams(ctypes.Structure):
@@ -35,6 +36,18 @@ class StepParams(ctypes.Structure):
         ("smoothness_weight", ctypes.c_double), ("step_size", ctypes.c_double), ("clip_grad_scale", ctypes.c_double),
         ("terminate_smooth_loss", ctypes.c_double), ("link_smooth_weight", ctypes.c_double * 9),
     ]
+
+
+LEARNER_ALGS = {"FTL": 0, "FTC": 1, "Exp": 2, "MD": 3, "Proj": 4, "INIT": 5}
+
+
+class LearnerParams(ctypes.Structure):
+    """omgb_learner_params_t"""
+    _fields_ = [("alg", ctypes.c_int32), ("num_goals", ctypes.c_int32), ("n_waypoints", ctypes.c_int32),
+                ("first_waypoint", ctypes.c_int32), ("constraint_rows", ctypes.c_int32),
+                ("normalize_cost", ctypes.c_int32), ("base_obstacle_weight", ctypes.c_double),
+                ("smoothness_base_weight", ctypes.c_double), ("dist_eps", ctypes.c_double), ("eta", ctypes.c_double),
+                ("etas", ctypes.c_double * 5)]
 
 
 class SdfSource(ctypes.Structure):
@@ -114,6 +127,8 @@ def lib():
     L.omgb_point_sdf.argtypes = [vp, ci, vp, vp, vp, ci, ci, ci, vp, vp, vp]
     L.omgb_ik_solve.argtypes = [vp, vp, vp, vp, ci, ci, vp, ci, vp, vp, vp, vp]
     L.omgb_hand_poses.argtypes = [vp, vp, ctypes.c_longlong, ci, vp, vp]
+    L.omgb_chomp_plan_step.argtypes = [vp, ctypes.POINTER(StepParams), ci, ci, ci] + [vp] * 9
+    L.omgb_learner_update.argtypes = [ctypes.POINTER(LearnerParams), ci, vp, vp, vp, ci] + [vp] * 13
     L.omgb_chomp_step_host.argtypes = [vp, ctypes.POINTER(StepParams), ci] + [vp] * 6
     L.omgb_batch_obstacle_cost.argtypes = [vp, vp, ci, ci, vp, cd, ci, vp, vp, vp, vp]
     L.omgb_goal_costs.argtypes = [vp, ci, vp, ctypes.c_longlong, vp, ci, ci, ci, cd, ci, vp, vp]

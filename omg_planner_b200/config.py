@@ -33,6 +33,7 @@ class ChompConfig(object):
         # trajectory initialisation / outer loop (omg/config.py:63,89,96-99,69,129)
         traj_interpolate="cubic", dynamic_timestep=False, traj_delta=0.05, traj_max_step=50, traj_min_step=2,
         goal_idx=-2, silent=True, scene_file="",
+        host_learner=False,   # True: keep the learner's [B,G] update on the host (Planner._plan_with_learner)
         # SDF assets (omg/config.py:54,55,60)
         target_size=1.0, obstacle_size=1, penalize_constant=5,
         # goal-set construction (omg/config.py:53,66,71,82,83,87,88,94,95,101,102)

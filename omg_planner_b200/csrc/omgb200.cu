@@ -13,6 +13,7 @@
 #include "chomp_kernels.cuh"
 #include "goal_kernels.cuh"
 #include "sdf_device.cuh"
+#include "learner_kernels.cuh"
 #include "sdf_asset_kernels.cuh"
 #include "traj_kernels.cuh"
 
@@ -1188,10 +1189,70 @@ extern "C" int omgb_point_sdf(const double *d_points, int num_points, const doub
     if (!d_points || !d_gx || !d_gy || !d_gz || (!d_out32 && !d_out64))
         return fail(OMGB_ERR_INVALID, "omgb_point_sdf: null buffer");
     const long long items = (long long)dim_x * dim_y * ((dim_z + POINT_ZV - 1) / POINT_ZV);   // (x, y, z-chunk)
-    const long long blocks = (items + POINT_THREADS - 1) / POINT_THREADS;
+    const long long blocks = (items + 31) / 32;   // 32 work items per block, POINT_SLICES warps each
     if (blocks > 0x7fffffffLL) return fail(OMGB_ERR_INVALID, "omgb_point_sdf: grid too large");
     point_sdf_kernel<<<(int)blocks, POINT_THREADS, 0, (cudaStream_t)stream>>>(d_points, num_points, d_gx, d_gy, d_gz,
                                                                              dim_x, dim_y, dim_z, d_out32, d_out64);
+    ++g_launches;
+    OMGB_CUDA(cudaGetLastError());
+    return OMGB_OK;
+}
+
+// ----------------------------------------------------------------------------------------------------
+// goal-set plans with goal switching, device resident: one plan iteration + the learner's update
+// ----------------------------------------------------------------------------------------------------
+extern "C" int omgb_chomp_plan_step(omgb_scene_t *s, const omgb_step_params_t *prm, int iteration, int stop_on_terminate,
+                                    int batch, double *xi, const double *start, const double *end,
+                                    const double *goal_rows, uint8_t *done, double *info, double *hist_xi,
+                                    double *hist_info, void *stream) {
+    int rc_ = check_step(s, prm, batch, "omgb_chomp_plan_step");
+    if (rc_) return rc_;
+    if (iteration < 0) return fail(OMGB_ERR_INVALID, "omgb_chomp_plan_step: negative iteration");
+    if (batch == 0) return OMGB_OK;
+    if (!xi || !start || !end || !info || (prm->goal_set_proj && !goal_rows) || (stop_on_terminate && !done))
+        return fail(OMGB_ERR_INVALID, "omgb_chomp_plan_step: null buffer");
+    OMGB_CUDA(cudaSetDevice(s->device));
+    StepArgs a = make_args(s, prm, batch, xi, start, end, goal_rows, nullptr, nullptr, info, nullptr, nullptr);
+    a.done = done;
+    a.stop_on_terminate = stop_on_terminate;
+    a.iteration = iteration;
+    a.hist_xi = hist_xi; a.hist_info = hist_info;
+    a.prm.update = 1;
+    return launch_step(s, a, (cudaStream_t)stream);
+}
+
+extern "C" int omgb_learner_update(const omgb_learner_params_t *prm, int batch, const double *xi,
+                                   const float *collision, const double *goal_set, int goals_shared,
+                                   const double *reach, double *p, double *sum_costs, double *experts_p,
+                                   double *experts_costs, double *q, const uint8_t *done, int32_t *goal_idx,
+                                   double *end, double *goal_rows, double *cost_vector, int32_t *selected,
+                                   void *stream) {
+    if (!prm) return fail(OMGB_ERR_INVALID, "omgb_learner_update: null params");
+    if (batch < 0) return fail(OMGB_ERR_INVALID, "omgb_learner_update: negative batch");
+    if (prm->alg < OMGB_LEARNER_FTL || prm->alg > OMGB_LEARNER_INIT)
+        return fail(OMGB_ERR_INVALID, "omgb_learner_update: unknown algorithm");
+    if (prm->num_goals < 1 || prm->num_goals > LRN_MAX_GOALS)
+        return fail(OMGB_ERR_INVALID, "omgb_learner_update: 1 <= num_goals <= 256 required");
+    if (prm->n_waypoints < 1 || prm->first_waypoint < 0 || prm->first_waypoint >= prm->n_waypoints ||
+        prm->constraint_rows < 1)
+        return fail(OMGB_ERR_INVALID, "omgb_learner_update: bad waypoint / constraint_rows");
+    if (batch == 0) return OMGB_OK;
+    if (!xi || !goal_set || !goal_idx || !end || !p || (prm->alg != OMGB_LEARNER_PROJ && !collision))
+        return fail(OMGB_ERR_INVALID, "omgb_learner_update: null buffer");
+    if ((prm->alg == OMGB_LEARNER_FTL || prm->alg == OMGB_LEARNER_EXP) && !sum_costs)
+        return fail(OMGB_ERR_INVALID, "omgb_learner_update: sum_costs required");
+    if (prm->alg == OMGB_LEARNER_MD && (!experts_p || !experts_costs || !q))
+        return fail(OMGB_ERR_INVALID, "omgb_learner_update: expert state required");
+    LearnerArgs a;
+    memset(&a, 0, sizeof(a));
+    a.prm = *prm;
+    a.xi = xi; a.collision = collision;
+    a.goal_set = goal_set; a.goal_stride_b = goals_shared ? 0 : (long long)prm->num_goals * ND;
+    a.reach = reach; a.reach_stride_b = goals_shared ? 0 : (long long)prm->num_goals * prm->constraint_rows * ND;
+    a.p = p; a.sum_costs = sum_costs; a.experts_p = experts_p; a.experts_costs = experts_costs; a.q = q;
+    a.done = done; a.goal_idx = goal_idx; a.end = end; a.goal_rows = goal_rows; a.cost_vector = cost_vector;
+    a.selected_hist = selected; a.batch = batch;
+    learner_update_kernel<<<batch, LRN_THREADS, 0, (cudaStream_t)stream>>>(a);
     ++g_launches;
     OMGB_CUDA(cudaGetLastError());
     return OMGB_OK;

@@ -78,12 +78,15 @@ __device__ __forceinline__ void sdf_pack_body(const SdfSource *__restrict__ src,
 
 constexpr int POINT_TILE = 1024;
 constexpr int POINT_ZV = 8;          // voxels of one z-row per thread
-constexpr int POINT_THREADS = 128;
+constexpr int POINT_SLICES = 4;      // warps of a block share 32 voxel chunks and split the cloud
+constexpr int POINT_THREADS = 32 * POINT_SLICES;
 
-// One thread per (x, y, chunk of POINT_ZV voxels along z); the cloud streams through shared memory in tiles of
-// POINT_TILE points (every lane reads the same point: broadcast).  The voxels of a thread share x and y, so
-// dx*dx + dy*dy -- the first two terms of cKDTree's sum -- is computed once per point and only (.. + dz*dz) per voxel:
-// the same IEEE operations per (voxel, point) as the reference, 4.6 instead of 9 fp64 instructions.
+// Work item = (x, y, chunk of POINT_ZV voxels along z), one per LANE; the block's POINT_SLICES warps all work on the
+// same 32 items and each scans every POINT_SLICES-th point of the cloud (a workspace grid has only ~10^5 voxels: the
+// split over points is what fills 148 SMs).  The cloud streams through shared memory in tiles; all lanes of a warp
+// read the same point (broadcast).  The voxels of a lane share x and y, so dx*dx + dy*dy -- the first two terms of
+// cKDTree's sum -- is computed once per point and only (.. + dz*dz) per voxel: the same IEEE operations per
+// (voxel, point) as the reference, 4.6 instead of 9 fp64 instructions.  min is exact, so the split changes nothing.
 __global__ void __launch_bounds__(POINT_THREADS) point_sdf_kernel(const double *__restrict__ points, int num_points,
                                                                   const double *__restrict__ gx,
                                                                   const double *__restrict__ gy,
@@ -91,9 +94,11 @@ __global__ void __launch_bounds__(POINT_THREADS) point_sdf_kernel(const double *
                                                                   float *__restrict__ out32,
                                                                   double *__restrict__ out64) {
     __shared__ double s_p[POINT_TILE * 3];
+    __shared__ double s_best[POINT_SLICES][POINT_ZV][32];
+    const int lane = threadIdx.x & 31, slice = threadIdx.x >> 5;
     const int chunks = (Z + POINT_ZV - 1) / POINT_ZV;
     const long long items = (long long)X * Y * chunks;
-    const long long it = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long it = (long long)blockIdx.x * 32 + lane;
     const bool live = it < items;
     double px = 0.0, py = 0.0, pz[POINT_ZV], best[POINT_ZV];
     int z0 = 0;
@@ -117,7 +122,7 @@ __global__ void __launch_bounds__(POINT_THREADS) point_sdf_kernel(const double *
         __syncthreads();
         if (live) {
 #pragma unroll 2
-            for (int k = 0; k < cnt; ++k) {
+            for (int k = slice; k < cnt; k += POINT_SLICES) {
                 const double qx = s_p[3 * k], qy = s_p[3 * k + 1], qz = s_p[3 * k + 2];
                 const double dx = __dsub_rn(px, qx), dy = __dsub_rn(py, qy);
                 const double dxy = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
@@ -129,15 +134,20 @@ __global__ void __launch_bounds__(POINT_THREADS) point_sdf_kernel(const double *
             }
         }
     }
-    if (live) {
 #pragma unroll
-        for (int v = 0; v < POINT_ZV; ++v) {
-            if (z0 + v < Z) {
-                const double d = __dsqrt_rn(best[v]);
-                const size_t o = (size_t)row * Z + z0 + v;
-                if (out64) out64[o] = d;
-                if (out32) out32[o] = (float)d;
-            }
+    for (int v = 0; v < POINT_ZV; ++v) s_best[slice][v][lane] = best[v];
+    __syncthreads();
+    // combine the slices: thread (slice, lane) finishes voxels v = slice, slice + POINT_SLICES, ... of lane's chunk
+    if (live) {
+        for (int v = slice; v < POINT_ZV; v += POINT_SLICES) {
+            if (z0 + v >= Z) continue;
+            double m = s_best[0][v][lane];
+#pragma unroll
+            for (int q = 1; q < POINT_SLICES; ++q) m = fmin(m, s_best[q][v][lane]);
+            const double d = __dsqrt_rn(m);
+            const size_t o = (size_t)row * Z + z0 + v;
+            if (out64) out64[o] = d;
+            if (out32) out32[o] = (float)d;
         }
     }
 }

@@ -226,3 +226,76 @@ class Learner(object):
         self.Tis.append(self.Ti if self.batched else self.Ti[0])
         changed = idx != old
         return changed if self.batched else bool(changed[0])
+
+
+class DeviceLearnerState(object):
+    """The Learner's state as device tensors plus the omgb_learner_update call (one launch for the whole batch):
+    cost vector, FTL / FTC / Exp / MD / Proj, goal selection and the gather of the new goal rows, without leaving the
+    GPU.  Built from a host Learner (so earlier host updates carry over) and written back with .store()."""
+
+    def __init__(self, learner, device):
+        import ctypes
+
+        import torch
+
+        from . import _lib
+
+        self.learner, self.device, self._lib, self._ct, self._torch = learner, device, _lib, ctypes, torch
+        cfg = learner.cfg
+        B, G, E = learner.B, learner.N, learner.num_experts
+        if G > 256:
+            raise RuntimeError("the device learner handles at most 256 goals per trajectory")
+        dev = lambda a, dt=np.float64: torch.from_numpy(np.ascontiguousarray(a, dtype=dt)).to(device)
+        self.p, self.sum_costs = dev(learner._p), dev(learner.sum_costs)
+        self.experts_p, self.experts_costs, self.q = dev(learner._experts_p), dev(learner.experts_costs), dev(learner._q)
+        gs = np.asarray(learner.traj.goal_set, dtype=np.float64)
+        self.shared = gs.ndim == 2 and B > 1
+        self.goal_set = dev(gs if (gs.ndim == 3 or self.shared) else gs[None])
+        self.reach = None
+        self.c = 1
+        if cfg.use_standoff:
+            rg = np.asarray(learner.env.objects[learner.env.target_idx].reach_grasps, dtype=np.float64)
+            self.reach = dev(rg if (rg.ndim == 4 or self.shared) else rg[None])
+            self.c = rg.shape[-2]
+            self.reach_goals = self.reach[..., -1, :].contiguous()
+        else:
+            self.reach_goals = self.goal_set
+        self.goal_idx = dev(np.atleast_1d(np.asarray(learner.traj.goal_idx)).astype(np.int32), np.int32)
+        if self.goal_idx.numel() != B:
+            self.goal_idx = self.goal_idx.expand(B).contiguous()
+        self.prm = _lib.LearnerParams()
+        self.prm.alg = _lib.LEARNER_ALGS[learner.alg_name]
+        self.prm.num_goals, self.prm.n_waypoints, self.prm.constraint_rows = G, cfg.timesteps, self.c
+        self.prm.normalize_cost = int(bool(cfg.normalize_cost))
+        self.prm.base_obstacle_weight = float(cfg.base_obstacle_weight)
+        self.prm.smoothness_base_weight = float(cfg.smoothness_base_weight)
+        self.prm.dist_eps = float(cfg.dist_eps)
+        self.prm.eta = float(learner.eta)
+        for k in range(E):
+            self.prm.etas[k] = float(learner.etas[k])
+
+    def update(self, engine, xi, end, goal_rows, done=None, selected=None, cost_vector=None):
+        """Learner.update_goal for the batch: advances t, scores the goals (omgb_goal_costs) and updates / selects
+        (omgb_learner_update); end [B,9] and goal_rows [B,c,9] are overwritten in place."""
+        lrn, cfg, ct = self.learner, self.learner.cfg, self._ct
+        lrn.t += 1
+        first = min(1 + int((lrn.t / cfg.optim_steps) * cfg.timesteps) - 1, cfg.timesteps - 1)
+        self.prm.first_waypoint = first
+        coll = None
+        if lrn.alg_name != "Proj":
+            coll = engine.goal_costs(xi, first, self.reach_goals, float(cfg.time_interval), 0)
+        vp = ct.c_void_p
+        ptr = lambda t: None if t is None else vp(t.data_ptr())
+        self._lib.check(self._lib.lib().omgb_learner_update(
+            ct.byref(self.prm), xi.shape[0], ptr(xi), ptr(coll), ptr(self.goal_set), int(self.shared), ptr(self.reach),
+            ptr(self.p), ptr(self.sum_costs), ptr(self.experts_p), ptr(self.experts_costs), ptr(self.q), ptr(done),
+            ptr(self.goal_idx), ptr(end), ptr(goal_rows), ptr(cost_vector), ptr(selected),
+            vp(self._torch.cuda.current_stream().cuda_stream)), "omgb_learner_update")
+
+    def store(self):
+        """Copy the state back into the host Learner (p, q, experts, sums) and the trajectory's goal."""
+        lrn = self.learner
+        lrn._p, lrn.sum_costs = self.p.cpu().numpy(), self.sum_costs.cpu().numpy()
+        lrn._experts_p, lrn.experts_costs, lrn._q = (self.experts_p.cpu().numpy(), self.experts_costs.cpu().numpy(),
+                                                       self.q.cpu().numpy())
+        lrn._select(self.goal_idx.cpu().numpy())

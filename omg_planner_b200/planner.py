@@ -37,6 +37,43 @@ def info_from_row(cfg, r, n):
     }
 
 
+class InfoList(object):
+    """The info list of one trajectory of a batched plan (Planner.info[b]): a read-only sequence whose dicts are built
+    from the recorded info rows when they are looked at (a 1024-trajectory x 70-iteration plan has 72k of them)."""
+
+    def __init__(self, cfg, rows, n, extra=None):
+        self._cfg, self._rows, self._n, self._extra, self._cache = cfg, rows, n, extra, {}
+
+    def __len__(self):
+        return self._rows.shape[0] + (1 if self._extra is not None else 0)
+
+    def __getitem__(self, k):
+        if isinstance(k, slice):
+            return [self[i] for i in range(*k.indices(len(self)))]
+        if k < 0:
+            k += len(self)
+        if not 0 <= k < len(self):
+            raise IndexError(k)
+        if k not in self._cache:
+            row = self._rows[k] if k < self._rows.shape[0] else self._extra
+            self._cache[k] = info_from_row(self._cfg, row, self._n)
+        return self._cache[k]
+
+    def __iter__(self):
+        return (self[i] for i in range(len(self)))
+
+
+def _to_host(t, cache, key):
+    """Device tensor -> numpy through a cached pinned staging buffer (large histories: pageable copies are slow)."""
+    buf = cache.get(key)
+    if buf is None or buf.shape != t.shape or buf.dtype != t.dtype:
+        buf = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+        cache[key] = buf
+    buf.copy_(t, non_blocking=True)
+    torch.cuda.current_stream().synchronize()
+    return buf.numpy()
+
+
 class Planner(GoalSetMixin):
     def __init__(self, env, traj, lazy=False):
         self.cfg = env.config
@@ -133,7 +170,10 @@ class Planner(GoalSetMixin):
             return self.info                                    # "planning not run"
         iters = cfg.optim_steps + cfg.extra_smooth_steps
         if cfg.goal_set_proj and alg_switch:
-            self._plan_with_learner(traj, iters, start_time_)
+            if self.learner.N <= 256 and not getattr(cfg, "host_learner", False):
+                self._plan_with_device_learner(traj, iters)
+            else:
+                self._plan_with_learner(traj, iters, start_time_)
         else:
             self._plan_fused(traj, iters)
         plan_time = time.time() - start_time_
@@ -141,9 +181,94 @@ class Planner(GoalSetMixin):
             lst[-1]["time"] = plan_time
         return self.info
 
+    def _plan_with_device_learner(self, traj, iters):
+        """Goal switching without leaving the GPU: per iteration omgb_goal_costs -> omgb_learner_update (cost vector,
+        FTL / FTC / Exp / MD / Proj, goal selection, new goal rows) -> omgb_chomp_plan_step (frozen trajectories,
+        history), all on one stream with no host synchronisation until the plan is over."""
+        from .online_learner import DeviceLearnerState
+
+        cfg, cost, lrn = self.cfg, self.cost, self.learner
+        cost.sync()
+        ecfg = cost.engine_cfg()
+        eng = cost.engine
+        xi, start, end, rows, batched = cost._traj_tensors(traj)
+        B, n, c = xi.shape[0], xi.shape[1], ecfg.constraint_rows
+        xi0 = xi.clone()
+        st = DeviceLearnerState(lrn, xi.device)
+        done = torch.zeros((B,), dtype=torch.uint8, device=xi.device)
+        info = torch.empty((B, _lib.INFO_STRIDE), dtype=torch.float64, device=xi.device)
+        hist_xi = torch.empty((iters, B, n, 9), dtype=torch.float64, device=xi.device)
+        hist_info = torch.zeros((iters, B, _lib.INFO_STRIDE), dtype=torch.float64, device=xi.device)
+        n_sel = min(iters, cfg.optim_steps)
+        selected = torch.zeros((max(n_sel, 1), B), dtype=torch.int32, device=xi.device)
+        import ctypes
+        vp = ctypes.c_void_p
+        stream = vp(torch.cuda.current_stream().cuda_stream)
+        prm = _lib.StepParams()
+        step0 = self.optim.step
+        for t in range(iters):
+            if t < cfg.optim_steps:
+                st.update(eng, xi, end, rows, done=done, selected=selected[t])
+            self.optim.update()                                          # schedule, written back into cfg
+            eng.set_metric(ecfg)
+            ecfg = cost.engine_cfg()
+            eng.params_from(ecfg, True, into=prm)
+            _lib.check(eng.L.omgb_chomp_plan_step(eng._h, ctypes.byref(prm), t, 1, B, vp(xi.data_ptr()),
+                                                  vp(start.data_ptr()), vp(end.data_ptr()), vp(rows.data_ptr()),
+                                                  vp(done.data_ptr()), vp(info.data_ptr()), vp(hist_xi.data_ptr()),
+                                                  vp(hist_info.data_ptr()), stream), "omgb_chomp_plan_step")
+        stage = self.__dict__.setdefault("_stage", {})
+        h_info, h_xi, sel = (_to_host(hist_info, stage, "info").copy(), _to_host(hist_xi, stage, "xi"),
+                             selected.cpu().numpy())
+        term = h_info[:, :, 8] > 0
+        term[0] = False
+        stopped = term.any(0)
+        stop = np.where(stopped, term.argmax(0), iters - 1)
+        self.optim.step = step0 + int(stop.max()) + 1      # one Optimizer.update() per iteration the loop ran
+        final = None
+        if (~stopped).any():
+            active = torch.from_numpy((~stopped).astype(np.uint8)).to(xi.device)
+            self.optim.update()
+            ecfg = cost.engine_cfg()
+            final = eng.step(ecfg, xi, start, end, rows, active=active, update=0)["info"].cpu().numpy()
+        st.store()
+        sel_lists = self._assemble(traj, batched, xi0.cpu().numpy(), h_xi, h_info, stop, stopped, final,
+                                   xi.cpu().numpy(), sel=sel, n_sel=n_sel)
+        lrn.Ti = np.zeros((B, lrn.N))
+        for b in range(B):
+            np.add.at(lrn.Ti[b], sel_lists[b], 1)
+
+    def _assemble(self, traj, batched, xi0, h_xi, h_info, stop, stopped, final, new_xi, sel=None, n_sel=0):
+        """history_trajectories / info (/ selected_goals) per trajectory, each cut where the reference's loop would
+        have stopped for it (omg/planner.py:627-635).  Batched plans get views and lazily built dicts."""
+        cfg = self.cfg
+        B, n = xi0.shape[0], xi0.shape[1]
+        hist = np.concatenate([xi0[None], h_xi], axis=0)                # [iters + 1, B, n, 9]
+        infos, hists, sels = [], [], []
+        for b in range(B):
+            k = int(stop[b])
+            # terminated: the state after the terminating iteration is dropped from the history (:634-635)
+            hists.append(hist[:k + 1, b] if stopped[b] else hist[:k + 2, b])
+            extra = None if stopped[b] else final[b]
+            infos.append(InfoList(cfg, h_info[:k + 1, b], n, extra))
+            if sel is not None:
+                sels.append([int(v) for v in sel[:min(k + 1, n_sel), b]])
+        traj.set(new_xi if batched else new_xi[0])
+        if batched:
+            self.info, self.history_trajectories = infos, hists
+            if sel is not None:
+                self.selected_goals = sels
+        else:
+            self.info, self.history_trajectories = list(infos[0]), list(hists[0])
+            if sel is not None:
+                self.selected_goals = sels[0]
+        return sels
+
     def _plan_with_learner(self, traj, iters, start_time_):
-        """Goal switching: the reference's loop verbatim over the fused Learner / Optimizer calls.  A batch runs
-        until every trajectory has terminated; per-trajectory results are cut at the trajectory's own stop."""
+        """Goal switching with the learner's update on the host (BASELINE north_star's split; used for goal sets larger
+        than the device learner's 256 goals, or with cfg.host_learner): the reference's loop verbatim over the fused
+        Learner / Optimizer calls.  A batch runs until every trajectory has terminated; per-trajectory results are cut
+        at the trajectory's own stop."""
         cfg = self.cfg
         batched = np.asarray(traj.data).ndim == 3
         B = np.asarray(traj.data).shape[0] if batched else 1
@@ -203,8 +328,9 @@ class Planner(GoalSetMixin):
         first = self.optim.step + 1
         out = cost.engine.plan(ecfg, xi, start, end, rows, iters=iters, stop_on_terminate=True, first_step=first,
                                history=True)
-        hist_info = out["hist_info"].cpu().numpy()                      # [iters,B,16]
-        hist_xi = out["hist_xi"].cpu().numpy()
+        stage = self.__dict__.setdefault("_stage", {})
+        hist_info = _to_host(out["hist_info"], stage, "info").copy()    # [iters,B,16]
+        hist_xi = _to_host(out["hist_xi"], stage, "xi")
         term = hist_info[:, :, 8] > 0
         term[0] = False                                                 # the t > 0 rule (planner.py:627)
         stopped = term.any(0)
@@ -217,21 +343,4 @@ class Planner(GoalSetMixin):
             self.optim.update()                                         # schedule of the info-only call
             ecfg = cost.engine_cfg()
             final = cost.engine.step(ecfg, xi, start, end, rows, active=active, update=0)["info"].cpu().numpy()
-        infos, hists = [], []
-        xi0 = xi0.cpu().numpy()
-        for b in range(B):
-            k = int(stop[b])
-            lst = [info_from_row(cfg, hist_info[t, b], n) for t in range(k + 1)]
-            h = [xi0[b]] + [hist_xi[t, b] for t in range(k + 1)]
-            if stopped[b]:
-                del h[-1]                                               # planner.py:634-635
-            else:
-                lst.append(info_from_row(cfg, final[b], n))
-            infos.append(lst)
-            hists.append(h)
-        new = xi.cpu().numpy()
-        traj.set(new if batched else new[0])
-        if batched:
-            self.info, self.history_trajectories = infos, [np.stack(h) for h in hists]
-        else:
-            self.info, self.history_trajectories = infos[0], hists[0]
+        self._assemble(traj, batched, xi0.cpu().numpy(), hist_xi, hist_info, stop, stopped, final, xi.cpu().numpy())

@@ -1,0 +1,58 @@
+#!/usr/bin/env python
+"""Goal-set plans with the online learner (the reference's default mode: goal_set_proj, ol_alg MD), whole Planner.plan
+wall time for a batch: learner update on the host (north_star's split) vs device-resident pipeline
+(omgb_goal_costs -> omgb_learner_update -> omgb_chomp_plan_step).  One JSON line."""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+def main():
+    import torch
+
+    import helpers as H
+    from omg_planner_b200 import core as C
+    from omg_planner_b200 import scene as S
+    from omg_planner_b200.config import ChompConfig
+    from omg_planner_b200.planner import Planner
+    from omg_planner_b200.robot import PandaConstants
+
+    B, G = int(os.environ.get("B", 1024)), int(os.environ.get("G", 20))
+    sc = S.make_scene(num_objects=10, grid=128, seed=0)
+    robot = PandaConstants()
+    goals, reach = S.make_goal_sets(B, G, robot.joint_lower_limit, robot.joint_upper_limit, seed=4, spread=0.3)
+    res = {"workload": "%d trajectories x %d goals x 30 waypoints, 10 SDFs @128^3, ol_alg MD, standoff, 50 + 20 iterations, "
+                       "pre_terminate off (every iteration runs)" % (B, G)}
+    for host in (True, False):
+        cfg = ChompConfig(goal_set_proj=True, use_standoff=True, ol_alg="MD", pre_terminate=False, host_learner=host)
+        env = H.make_env(sc, cfg, robot)
+        target = env.objects[env.target_idx]
+        target.grasps, target.reach_grasps = goals, reach
+        traj = C.Trajectory(30, cfg=cfg, start=np.tile(S.START_CONF, (B, 1)), end=goals[:, 0])
+        planner = Planner(env, traj)
+        for rep in range(2):   # second pass = warm
+            traj = C.Trajectory(30, cfg=cfg, start=np.tile(S.START_CONF, (B, 1)), end=goals[:, 0])
+            traj.goal_set = goals
+            planner.update(env, traj)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            planner.plan(traj)
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+        iters = cfg.optim_steps + cfg.extra_smooth_steps
+        res["host_learner" if host else "device_learner"] = {
+            "plan_wall_s": dt, "ms_per_iteration": dt / iters * 1e3, "trajectory_iterations_per_s": B * iters / dt,
+            "goals_selected": int(len(set(np.array(planner.selected_goals).reshape(-1).tolist())))}
+    res["speedup"] = res["host_learner"]["plan_wall_s"] / res["device_learner"]["plan_wall_s"]
+    print(json.dumps(res))
+
+
+if __name__ == "__main__":
+    main()
