@@ -11,6 +11,17 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-fil
     python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-aux > gpurun_out/b_launch_$TAG.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:chomp_step -s 6 -c 1 -f -o gpurun_out/chomp_full_$TAG \
     python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-aux > gpurun_out/b_ncu_$TAG.log 2>&1
-ncu --set full --clock-control none -k regex:"sdf_pack|ik_chain|point_sdf" -c 6 -f -o gpurun_out/aux_full_$TAG \
-    python tools/bench_aux.py > gpurun_out/aux_ncu_$TAG.log 2>&1
+python tools/ncu_summary.py gpurun_out/chomp_full_$TAG.ncu-rep "chomp_step_kernel, bench.py --steps 3 --warmup 3 ($TAG)" > gpurun_out/ncu_chomp_$TAG.txt
+for K in sdf_pack_entry point_sdf_kernel ik_chain_kernel; do
+  ncu --set full --clock-control none -k regex:$K -s 1 -c 1 -f -o gpurun_out/aux_${K}_$TAG \
+      python tools/bench_aux.py > gpurun_out/aux_ncu_${K}_$TAG.log 2>&1
+  python tools/ncu_summary.py gpurun_out/aux_${K}_$TAG.ncu-rep "$K, tools/bench_aux.py ($TAG)" > gpurun_out/ncu_${K}_$TAG.txt
+  rm -f gpurun_out/aux_${K}_$TAG.ncu-rep
+done
+python tools/bench_goalset_plan.py > gpurun_out/goalset_plan_$TAG.json 2> gpurun_out/goalset_plan_$TAG.err
+B=64 ncu --set full --clock-control none -k regex:"learner_update|goal_cost" -s 20 -c 2 -f -o gpurun_out/learner_$TAG \
+    python tools/bench_goalset_plan.py > gpurun_out/learner_ncu_$TAG.log 2>&1
+python tools/ncu_summary.py gpurun_out/learner_$TAG.ncu-rep "goal_cost_kernel + learner_update_kernel, B=64 tools/bench_goalset_plan.py ($TAG)" > gpurun_out/ncu_learner_$TAG.txt
+rm -f gpurun_out/learner_$TAG.ncu-rep
+du -sh gpurun_out
 ls -la gpurun_out | tail -12
