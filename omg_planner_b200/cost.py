@@ -87,6 +87,25 @@ class Cost(object):
             self._obj_sig = osig
 
     # ---- reference API ----------------------------------------------------------------------------------
+    def forward_poses(self, joints):
+        """omg/cost.py:45-58: link poses, joint origins and joint axes of ONE configuration (degrees, with the dummy
+        eighth joint) from the scene's robot_kinematics object -- the same delegation as the reference; the fused
+        kernels do their own forward kinematics and never call this."""
+        robot = self.env.robot
+        poses, origins, axes = robot.robot_kinematics.forward_kinematics_parallel(
+            joints[None, ...], base_link=self.cfg.base_link, return_joint_info=True)
+        return poses[0], origins[0], axes[0]
+
+    def forward_points(self, pose, pts, normals=None):
+        """omg/cost.py:60-72: body points [m,3,p] through link poses [n,m,4,4] -> [p,n,m,3]."""
+        r = pose[..., :3, :3]
+        t = pose[..., :3, [3]]
+        x = np.matmul(r, pts[None, ...]) + t
+        if normals is None:
+            return x.transpose([3, 1, 0, 2])
+        normal = np.matmul(r, normals[None, ...])
+        return np.concatenate([x, normal], 2).transpose([3, 1, 0, 2])
+
     def _traj_tensors(self, traj):
         dev = self.engine.device
         data = np.asarray(traj.data, dtype=np.float64)

@@ -91,6 +91,8 @@ class Planner(GoalSetMixin):
             if self.cfg.scene_file == "" or self.cfg.traj_init == "grasp":
                 self.load_grasp_set(env)
                 self.setup_goal_set(env)
+            else:
+                self.load_goal_from_scene()
             self.grasp_init(env)
             self.learner = Learner(env, traj, self.cost)
         else:
@@ -115,6 +117,30 @@ class Planner(GoalSetMixin):
         else:
             self.traj.interpolate_waypoints()
         self.history_trajectories, self.info = [], []
+
+    def load_goal_from_scene(self):
+        """omg/planner.py:154-174: goals saved with a scene file (<scene_path>/<scene_file>.mat: 'goals',
+        'reach_grasps', optionally 'grasp_qualities' / 'grasp_potentials'); standoff is not used with them unless
+        cfg.force_standoff."""
+        import os
+
+        import scipy.io as sio
+
+        cfg = self.cfg
+        path = os.path.join(getattr(cfg, "scene_path", ""), cfg.scene_file + ".mat")
+        if cfg.traj_init == "scene" and not hasattr(cfg, "force_standoff"):
+            cfg.use_standoff = False
+        if os.path.exists(path):
+            scene = sio.loadmat(path)
+            cfg.goal_set_max_num = len(scene["goals"])
+            self.traj.goal_set = scene["goals"]
+            self.env.objects[self.env.target_idx].reach_grasps = scene["reach_grasps"]
+            if "grasp_qualities" in scene:
+                self.traj.goal_quality = scene["grasp_qualities"][0]
+                self.traj.goal_potentials = scene["grasp_potentials"][0]
+            else:
+                self.traj.goal_quality = np.zeros(cfg.goal_set_max_num)
+                self.traj.goal_potentials = np.zeros(cfg.goal_set_max_num)
 
     def grasp_init(self, env=None):
         """omg/planner.py:187-222: goal set from the target's grasps, initial goal by cfg.goal_idx, trajectory
