@@ -34,6 +34,33 @@ def test_argument_validation_without_gpu():
     assert L.omgb_batch_obstacle_cost(None, None, 0, 0, None, 0.1, 0, None, None, None, None) == -1
 
 
+def test_argument_validation_of_the_data_path_entry_points_without_gpu():
+    """Entry points added around the CHOMP loop reject bad arguments before touching CUDA (status -1, message set)."""
+    import ctypes
+
+    L = _lib.lib()
+    assert L.omgb_traj_interpolate(None, 4, 1, 30, 1, None, None) == -1          # fewer than 2 knots
+    assert L.omgb_traj_interpolate(None, 4, 2, 30, 7, None, None) == -1          # unknown mode
+    assert L.omgb_traj_interpolate(None, 0, 2, 30, 1, None, None) == 0           # empty batch is fine
+    assert L.omgb_sdf_pack(None, 65, 8, 8, 8, None, None) == -1                  # more than OMGB_MAX_OBJECTS
+    assert L.omgb_sdf_pack(None, 0, 8, 8, 8, None, None) == 0
+    assert L.omgb_point_sdf(None, 0, None, None, None, 4, 4, 4, None, None, None) == -1   # no points
+    frames = np.tile(np.eye(4), (8, 1, 1))
+    lim = np.zeros(7)
+    assert L.omgb_ik_solve(frames.ctypes.data, lim.ctypes.data, lim.ctypes.data, None, 3, 0, None, 2, None, None, None,
+                           None) == -1                                             # chain_length < 1
+    assert L.omgb_ik_solve(frames.ctypes.data, None, None, None, 3, 1, None, 2, None, None, None, None) == -1
+    assert L.omgb_ik_solve(frames.ctypes.data, lim.ctypes.data, lim.ctypes.data, None, 0, 1, None, 2, None, None, None,
+                           None) == 0                                              # no poses
+    assert L.omgb_hand_poses(frames.ctypes.data, None, 3, 5, None, None) == -1   # stride < 7
+    prm = _lib.LearnerParams()
+    prm.alg, prm.num_goals, prm.n_waypoints, prm.first_waypoint, prm.constraint_rows = 9, 4, 30, 0, 1
+    assert L.omgb_learner_update(ctypes.byref(prm), 2, None, None, None, 0, *([None] * 13)) == -1   # unknown algorithm
+    prm.alg, prm.num_goals = 3, 300
+    assert L.omgb_learner_update(ctypes.byref(prm), 2, None, None, None, 0, *([None] * 13)) == -1   # > 256 goals
+    assert b"256" in L.omgb_last_error()
+
+
 @pytest.mark.parametrize("gsp", [True, False])
 @pytest.mark.parametrize("n", [30, 50, 7])
 def test_metric_matrices_match_oracle_and_closed_form(gsp, n):
