@@ -51,6 +51,28 @@ def main():
             "plan_wall_s": dt, "ms_per_iteration": dt / iters * 1e3, "trajectory_iterations_per_s": B * iters / dt,
             "goals_selected": int(len(set(np.array(planner.selected_goals).reshape(-1).tolist())))}
     res["speedup"] = res["host_learner"]["plan_wall_s"] / res["device_learner"]["plan_wall_s"]
+    # one trajectory (the reference's own shape): whole Planner.plan latency, fixed goal (one persistent launch) and
+    # goal set with the MD learner (device pipeline)
+    one = {}
+    for name, kw in (("fixed_goal", dict(goal_set_proj=False)), ("goal_set_md", dict(goal_set_proj=True, ol_alg="MD"))):
+        cfg = ChompConfig(use_standoff=True, pre_terminate=False, **kw)
+        env = H.make_env(sc, cfg, robot)
+        target = env.objects[env.target_idx]
+        target.grasps, target.reach_grasps = goals[0], reach[0]
+        traj = C.Trajectory(30, cfg=cfg, start=S.START_CONF, end=goals[0, 0])
+        planner = Planner(env, traj)
+        ts = []
+        for rep in range(4):
+            traj = C.Trajectory(30, cfg=cfg, start=S.START_CONF, end=goals[0, 0])
+            traj.goal_set = goals[0]
+            planner.update(env, traj)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            planner.plan(traj)
+            torch.cuda.synchronize()
+            ts.append(time.perf_counter() - t0)
+        one[name] = {"plan_wall_ms": min(ts[1:]) * 1e3, "iterations": cfg.optim_steps + cfg.extra_smooth_steps}
+    res["single_trajectory_plan"] = one
     print(json.dumps(res))
 
 
