@@ -46,6 +46,21 @@ def rotY(a):   # omg/util.py:50-59
     return np.array([[c, 0, s, 0], [0, 1, 0, 0], [-s, 0, c, 0], [0, 0, 0, 1]])
 
 
+def unpack_pose(pose):
+    """omg/util.py:115-120: (x, y, z, qw, qx, qy, qz) -> 4x4 (transforms3d's quat2mat formula)."""
+    w, x, y, z = [float(v) for v in pose[3:]]
+    nq = w * w + x * x + y * y + z * z
+    out = np.eye(4)
+    if nq > np.finfo(np.float64).eps:
+        s = 2.0 / nq
+        X, Y, Z = x * s, y * s, z * s
+        wX, wY, wZ, xX, xY, xZ, yY, yZ, zZ = w * X, w * Y, w * Z, x * X, x * Y, x * Z, y * Y, y * Z, z * Z
+        out[:3, :3] = [[1.0 - (yY + zZ), xY - wZ, xZ + wY], [xY + wZ, 1.0 - (xX + zZ), yZ - wX],
+                       [xZ - wY, yZ + wX, 1.0 - (xX + yY)]]
+    out[:3, 3] = pose[:3]
+    return out
+
+
 def _pose_mat(obj):
     """4x4 object->world pose of an env object (omg/core.py:88-97 keeps both .pose_mat and the packed .pose)."""
     return np.asarray(obj.pose_mat, dtype=np.float64)
@@ -206,7 +221,10 @@ class GoalSetMixin(object):
                     pose_grasp = target_obj.grasps_poses
                 z_upsample = False
             else:   # placement
-                pose_grasp = np.linalg.inv(np.asarray(target_obj.rel_hand_pose_mat, dtype=np.float64))[None]
+                rel = (np.asarray(target_obj.rel_hand_pose_mat, dtype=np.float64)
+                       if getattr(target_obj, "rel_hand_pose_mat", None) is not None
+                       else unpack_pose(np.asarray(target_obj.rel_hand_pose, dtype=np.float64)))
+                pose_grasp = np.linalg.inv(rel)[None]
                 z_upsample = cfg.z_upsample
             self.solve_and_process_ik(target_obj, pose_grasp, z_upsample)
 

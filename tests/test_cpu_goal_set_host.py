@@ -41,8 +41,8 @@ class OracleIk(object):
 
 
 class OracleCost(object):
-    def __init__(self, scene, cfg, body_points):
-        self.scene, self.robot = scene, R.PandaRef(body_points=body_points)
+    def __init__(self, scene, cfg, body_points, attached=False):
+        self.scene, self.robot = dict(scene, attached=attached), R.PandaRef(body_points=body_points)
         self.cfg = R.RefConfig(goal_set_proj=True, use_standoff=cfg.use_standoff)
 
     def batch_obstacle_cost(self, joints, special_check_id=0, uncheck_finger_collision=-1, **kw):
@@ -101,6 +101,7 @@ def build(g, device_free=True):
     env.robot = types.SimpleNamespace(robot_kinematics=rk, joint_lower_limit=robot.joint_lower_limit,
                                       joint_upper_limit=robot.joint_upper_limit)
     traj = types.SimpleNamespace(start=np.array(g["start"]), goal_set=[])
+    env.objects[env.target_idx].attached = bool(int(g["attached"])) if "attached" in g.files else False
     return sc, cfg, robot, env, traj
 
 
@@ -108,19 +109,20 @@ def build(g, device_free=True):
 def test_goal_set_host_logic_matches_reference(path, monkeypatch):
     g = np.load(path)
     sc, cfg, robot, env, traj = build(g)
-    p = HostPlanner(cfg, env, traj, OracleCost(sc, cfg, g["body_points"]), OracleIk(robot))
     target = env.objects[env.target_idx]
+    z_up = bool(int(g["z_upsample"])) if "z_upsample" in g.files else False
+    p = HostPlanner(cfg, env, traj, OracleCost(sc, cfg, g["body_points"], target.attached), OracleIk(robot))
     # the product's own pose -> quaternion conversion: same goals, to the sensitivity of KDL's 1e-6 stop rule
-    reach, grasps = p.solve_goal_set_ik(target, env, g["pose_grasp"].copy())
+    reach, grasps = p.solve_goal_set_ik(target, env, g["pose_grasp"].copy(), z_upsample=z_up)
     assert np.array(grasps).shape == g["grasps_raw"].shape
     assert np.abs(np.array(grasps) - g["grasps_raw"]).max() < 1e-3   # (each is a solution to 1e-6 in task space)
     # with the fixture run's conversions everything is bit-identical
     monkeypatch.setattr(GS, "poses_to_targets", harness_targets)
     target.pose_mat = harness_object_pose(target.pose_mat)
-    reach, grasps = p.solve_goal_set_ik(target, env, g["pose_grasp"].copy())
+    reach, grasps = p.solve_goal_set_ik(target, env, g["pose_grasp"].copy(), z_upsample=z_up)
     np.testing.assert_array_equal(np.array(grasps), g["grasps_raw"])
     np.testing.assert_array_equal(np.array(reach), g["reach_raw"])
-    p.solve_and_process_ik(target, g["pose_grasp"].copy(), False)
+    p.solve_and_process_ik(target, g["pose_grasp"].copy(), z_up)
     np.testing.assert_array_equal(np.array(target.grasps), g["grasps_processed"])
     np.testing.assert_array_equal(np.array(target.reach_grasps), g["reach_processed"])
     np.random.seed(int(g["np_random_seed"]))

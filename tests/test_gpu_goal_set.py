@@ -120,6 +120,7 @@ def _env_for(g):
     for i, o in enumerate(env.objects):
         o.compute_grasp = i == env.target_idx
         o.grasp_potentials, o.grasp_vis_points, o.seeds, o.grasps_poses = [], [], [], []
+    env.objects[env.target_idx].attached = bool(int(g["attached"])) if "attached" in g.files else False
     return sc, cfg, robot, env
 
 
@@ -133,7 +134,11 @@ def test_goal_set_construction_matches_reference(path):
     planner = Planner(env, traj)     # nothing to build yet
     # the steps of Planner.__init__ (omg/planner.py:103-114), one by one as the fixture recorded them
     target.compute_grasp = True
-    target.grasps_poses = g["pose_grasp"].copy()
+    if target.attached:   # placement: load_grasp_set takes the inverse of the hand pose relative to the object
+        target.rel_hand_pose_mat = np.linalg.inv(g["pose_grasp"][0])
+        cfg.z_upsample = bool(int(g["z_upsample"]))
+    else:
+        target.grasps_poses = g["pose_grasp"].copy()
     planner.load_grasp_set(env)      # batched IK -> flip augmentation -> hand-rotation filter
     assert np.array(target.grasps).shape == g["grasps_processed"].shape
     assert np.abs(np.array(target.grasps) - g["grasps_processed"]).max() < 1e-3
@@ -159,7 +164,7 @@ def test_goal_set_construction_matches_reference(path):
 
 def test_raw_ik_goal_lists_and_pool_quirk():
     """solve_goal_set_ik alone: same goals in the same order as the reference; ik_parallel drops the last pose."""
-    g = np.load(GOALSETS[-1])   # standoff_parallel
+    g = np.load([p for p in GOALSETS if p.endswith("standoff_parallel.npz")][0])
     sc, cfg, robot, env = _env_for(g)
     target = env.objects[env.target_idx]
     traj = C.Trajectory(30, cfg=cfg, start=g["start"], end=g["start"])

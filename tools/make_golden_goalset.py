@@ -32,6 +32,10 @@ SCENE_ARGS = dict(num_objects=6, grid=48, seed=11, grid_choices=[32, 40, 48])
 CASES = {
     "standoff_parallel": dict(use_standoff=True, ik_parallel=True, n_grasps=14, seed=1),
     "single_sequential": dict(use_standoff=False, ik_parallel=False, n_grasps=10, seed=2),
+    # placement: the target is attached to the hand, one relative hand pose up-sampled by 50 rotations about the
+    # object's z axis (omg/planner.py:324-335, 493-498); no wrist-flip augmentation / hand-rotation filter, reach tails
+    # are not reversed, the table's collision parameters change (omg/cost.py:325-328)
+    "placement_zupsample": dict(use_standoff=True, ik_parallel=False, n_grasps=1, seed=3, attached=True, z_upsample=True),
 }
 
 
@@ -87,7 +91,10 @@ def main():
 
     cfg.ROBOT = RefRobot()
     sc = S.make_scene(**SCENE_ARGS)
+    only = sys.argv[1:]
     for name, case in CASES.items():
+        if only and name not in only:
+            continue
         cfg.goal_set_proj = True
         cfg.use_standoff = case["use_standoff"]
         cfg.ik_parallel = case["ik_parallel"]
@@ -101,6 +108,8 @@ def main():
         target = env.objects[env.target_idx]
         target.pose = ns.util.pack_pose(target.pose_mat)
         target.compute_grasp = True
+        target.attached = bool(case.get("attached", False))
+        z_up = bool(case.get("z_upsample", False))
         target.seeds, target.grasp_potentials, target.grasp_vis_points = [], [], []
         for o in env.objects:
             o.compute_grasp = o is target
@@ -113,9 +122,9 @@ def main():
         _print = builtins.print
         builtins.print = lambda *a, **k: None
         try:
-            reach_raw, grasps_raw = p.solve_goal_set_ik(target, env, pose_grasp.copy(), z_upsample=False,
+            reach_raw, grasps_raw = p.solve_goal_set_ik(target, env, pose_grasp.copy(), z_upsample=z_up,
                                                         y_upsample=False, obj_coord=True)
-            p.solve_and_process_ik(target, pose_grasp.copy(), False)
+            p.solve_and_process_ik(target, pose_grasp.copy(), z_up)
             reach_proc, grasps_proc = np.array(target.reach_grasps), np.array(target.grasps)
             np.random.seed(7)
             p.setup_goal_set(env)
@@ -126,7 +135,7 @@ def main():
             builtins.print = _print
         np.savez_compressed(
             os.path.join(out_dir, "goalset_%s.npz" % name), use_standoff=int(case["use_standoff"]),
-            ik_parallel=int(case["ik_parallel"]), scene_args=np.array(repr(SCENE_ARGS)),
+            ik_parallel=int(case["ik_parallel"]), attached=int(target.attached), z_upsample=int(z_up), scene_args=np.array(repr(SCENE_ARGS)),
             sdf_checksum=np.float64(sc["sdf_grids"].astype(np.float64).sum()), body_points=robot.body_points,
             pose_grasp=pose_grasp, start=S.START_CONF, reach_raw=np.array(reach_raw), grasps_raw=np.array(grasps_raw),
             reach_processed=reach_proc, grasps_processed=grasps_proc, reach_final=reach_fin, grasps_final=grasps_fin,
