@@ -165,7 +165,9 @@ class ChompEngine(object):
         self._check64(xi, (B, n, 9), "xi"); self._check64(start, (B, 9), "start"); self._check64(end, (B, 9), "end")
         if c > 0:
             self._check64(goal_rows, (B, c, 9), "goal_rows")
-        info = torch.empty((B, _lib.INFO_STRIDE), dtype=torch.float64, device=xi.device)
+        # (rows of inactive trajectories are never written: keep them defined)
+        info = (torch.zeros if active is not None else torch.empty)((B, _lib.INFO_STRIDE), dtype=torch.float64,
+                                                                    device=xi.device)
         grad = torch.empty_like(xi) if want_grad else None
         p = self.points_per_link
         dpot = torch.zeros((B, n, 10, p), dtype=torch.float32, device=xi.device) if debug else None
