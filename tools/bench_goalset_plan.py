@@ -72,6 +72,12 @@ def main():
             torch.cuda.synchronize()
             ts.append(time.perf_counter() - t0)
         one[name] = {"plan_wall_ms": min(ts[1:]) * 1e3, "iterations": cfg.optim_steps + cfg.extra_smooth_steps}
+        # the plugin call the reference's own loop makes: Optimizer.optimize(traj, force_update=True), one trajectory
+        t0 = time.perf_counter()
+        for _ in range(50):
+            planner.optim.optimize(traj, force_update=True)
+        torch.cuda.synchronize()
+        one[name]["optimize_call_ms"] = (time.perf_counter() - t0) / 50 * 1e3
     res["single_trajectory_plan"] = one
     print(json.dumps(res))
 
