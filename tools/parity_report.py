@@ -1,0 +1,105 @@
+#!/usr/bin/env python
+"""SURVEY 8(d) parity check at scale: from identical state, trajectories after k in {1, 10, 70} fused iterations vs the
+oracle (pinned to the reference's own Python by tests/golden/), per mode: max |xi - xi_ref| over the arm DOFs, the
+fraction of trajectories within 1e-4 rad, and the first diverging iteration of any failure.
+
+  python tools/parity_report.py dump  OUT.npz     on the GPU box: runs the engine, records xi after every iteration
+  python tools/parity_report.py check OUT.npz     anywhere (CPU): replays the oracle (one process per core), compares,
+                                                  prints one JSON object
+"""
+import json
+import multiprocessing as mp
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+SCENE = dict(num_objects=10, grid=96, seed=0)
+N_TRAJ, N_WPT, ITERS = 64, 30, 70
+MODES = {
+    "fixed_topk": dict(goal_set_proj=False, use_standoff=True, top_k_collision=1000),
+    "fixed_full": dict(goal_set_proj=False, use_standoff=True, top_k_collision=0),
+    "goalset_standoff_topk": dict(goal_set_proj=True, use_standoff=True, top_k_collision=1000),
+    "goalset_single_full": dict(goal_set_proj=True, use_standoff=False, top_k_collision=0),
+    "goalset_standoff_topk200": dict(goal_set_proj=True, use_standoff=True, top_k_collision=200),
+    "goalset_standoff_topk_finger": dict(goal_set_proj=True, use_standoff=True, top_k_collision=1000, consider_finger=True),
+}
+
+
+def dump(path):
+    import torch
+
+    import helpers as H
+    from omg_planner_b200 import scene as S
+    from omg_planner_b200.config import ChompConfig
+    from omg_planner_b200.robot import PandaConstants
+
+    sc = S.make_scene(**SCENE)
+    robot = PandaConstants()
+    xi, st, en, tails = S.make_trajectories(N_TRAJ, N_WPT, robot.joint_lower_limit, robot.joint_upper_limit, seed=11)
+    out = {"xi0": xi, "start": st, "end": en, "tails": tails}
+    dev = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    for name, mode in MODES.items():
+        cfg = ChompConfig(**mode)
+        eng = H.engine_for(sc, cfg, robot)
+        rows = H.goal_rows_for(mode, tails, en)
+        x = dev(xi)
+        res = eng.plan(cfg, x, dev(st), dev(en), None if rows is None else dev(rows), iters=ITERS, history=True)
+        out["hist_" + name] = res["hist_xi"].cpu().numpy()
+    np.savez_compressed(path, **out)
+    print("wrote", path)
+
+
+def _oracle_worker(args):
+    name, mode, b, xi, st, en, rows = args
+    from omg_planner_b200 import scene as S
+    from oracle import chomp_ref as R
+
+    global _SC
+    try:
+        sc = _SC
+    except NameError:
+        sc = _SC = S.make_scene(**SCENE)
+    cfg = R.RefConfig(**mode)
+    opt = R.ChompRef(R.PandaRef(), sc, cfg, xi, st, en, rows)
+    hist = np.zeros((ITERS, N_WPT, 9))
+    for it in range(ITERS):
+        opt.step()
+        hist[it] = opt.xi
+    return name, b, hist
+
+
+def check(path):
+    import helpers as H
+
+    g = np.load(path)
+    jobs = []
+    for name, mode in MODES.items():
+        rows = H.goal_rows_for(mode, g["tails"], g["end"])
+        for b in range(N_TRAJ):
+            jobs.append((name, mode, b, g["xi0"][b], g["start"][b], g["end"][b], None if rows is None else rows[b]))
+    ref = {name: np.zeros((ITERS, N_TRAJ, N_WPT, 9)) for name in MODES}
+    with mp.get_context("fork").Pool(os.cpu_count() or 1) as pool:
+        for name, b, hist in pool.imap_unordered(_oracle_worker, jobs, chunksize=4):
+            ref[name][:, b] = hist
+    report = {"scene": SCENE, "trajectories": N_TRAJ, "waypoints": N_WPT, "tolerance_rad": 1e-4, "modes": {}}
+    for name, mode in MODES.items():
+        dofs = 9 if mode.get("consider_finger") else 7
+        err = np.abs(g["hist_" + name] - ref[name])[..., :dofs].max(axis=(2, 3))      # [iters, B]
+        entry = {}
+        for k in (1, 10, 70):
+            e = err[k - 1]
+            entry["after_%d" % k] = {"max_abs_rad": float(e.max()), "fraction_within_tolerance": float((e <= 1e-4).mean())}
+        bad = np.argwhere(err > 1e-4)
+        entry["first_divergence"] = None if bad.size == 0 else {"iteration": int(bad[:, 0].min()) + 1,
+                                                                "trajectories": sorted(set(bad[:, 1].tolist()))[:8]}
+        report["modes"][name] = entry
+    print(json.dumps(report))
+
+
+if __name__ == "__main__":
+    {"dump": dump, "check": check}[sys.argv[1]](sys.argv[2])
