@@ -23,7 +23,6 @@ namespace omgb {
 
 constexpr int LRN_EXPERTS = 5;
 constexpr int LRN_MAX_GOALS = 256;
-constexpr int LRN_PER_LANE = LRN_MAX_GOALS / 32;
 constexpr int LRN_THREADS = 32 * LRN_EXPERTS;
 
 struct LearnerArgs {
@@ -56,7 +55,10 @@ __device__ __forceinline__ double lrn_warp_max(double v) {
 }
 
 // omg/online_learner.py:32-58 for one expert: x (previous distribution), v = eta * cv, both in shared memory [G];
-// result written to out [G] (shared).  All 32 lanes of the calling warp participate.
+// result written to out [G] (shared).  All 32 lanes of the calling warp participate; LRN_PER_LANE = goals per lane
+// (a template parameter: 20 goals need one register set per lane, not eight -- occupancy is what hides the latency
+// of the bisection's dependent exp / reduce chain).
+template <int LRN_PER_LANE>
 __device__ void lrn_bregman_warp(const double *x, const double *cv, double eta, int G, double delta, double *out) {
     const int lane = threadIdx.x & 31;
     double sh[LRN_PER_LANE], v[LRN_PER_LANE], alpha[LRN_PER_LANE], y[LRN_PER_LANE];
@@ -116,7 +118,8 @@ __device__ void lrn_bregman_warp(const double *x, const double *cv, double eta, 
         if (lane + 32 * k < G) out[lane + 32 * k] = y[k] / ys;
 }
 
-__global__ void __launch_bounds__(LRN_THREADS) learner_update_kernel(const LearnerArgs a) {
+template <int PER_LANE>
+__global__ void __launch_bounds__(LRN_THREADS, PER_LANE <= 2 ? 4 : 2) learner_update_kernel(const LearnerArgs a) {
     __shared__ double s_cv[LRN_MAX_GOALS];
     __shared__ double s_p[LRN_MAX_GOALS];
     __shared__ double s_old[LRN_EXPERTS][LRN_MAX_GOALS];
@@ -172,7 +175,7 @@ __global__ void __launch_bounds__(LRN_THREADS) learner_update_kernel(const Learn
         for (int k = tid; k < LRN_EXPERTS * G; k += LRN_THREADS) s_old[k / G][k % G] = ep[k];
         __syncthreads();
         const double delta = 1.0 / (double)(4 * G + 1);
-        lrn_bregman_warp(s_old[warp], s_cv, P.etas[warp], G, delta, s_new[warp]);
+        lrn_bregman_warp<PER_LANE>(s_old[warp], s_cv, P.etas[warp], G, delta, s_new[warp]);
         __syncwarp();
         {   // experts_costs[i] = cv . p + weights . |p - p_old| (:222-224), weights = 1
             double c1 = 0.0, c2 = 0.0;

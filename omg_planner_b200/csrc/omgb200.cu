@@ -1252,7 +1252,12 @@ extern "C" int omgb_learner_update(const omgb_learner_params_t *prm, int batch, 
     a.p = p; a.sum_costs = sum_costs; a.experts_p = experts_p; a.experts_costs = experts_costs; a.q = q;
     a.done = done; a.goal_idx = goal_idx; a.end = end; a.goal_rows = goal_rows; a.cost_vector = cost_vector;
     a.selected_hist = selected; a.batch = batch;
-    learner_update_kernel<<<batch, LRN_THREADS, 0, (cudaStream_t)stream>>>(a);
+    const int G = prm->num_goals;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (G <= 32) learner_update_kernel<1><<<batch, LRN_THREADS, 0, st>>>(a);
+    else if (G <= 64) learner_update_kernel<2><<<batch, LRN_THREADS, 0, st>>>(a);
+    else if (G <= 128) learner_update_kernel<4><<<batch, LRN_THREADS, 0, st>>>(a);
+    else learner_update_kernel<8><<<batch, LRN_THREADS, 0, st>>>(a);
     ++g_launches;
     OMGB_CUDA(cudaGetLastError());
     return OMGB_OK;

@@ -76,6 +76,25 @@ def run_aux(hbm_peak_gbs=None, ik_oracle_sample=60):
     del dst, fields
     torch.cuda.empty_cache()
 
+    # ---- omgb_sdf_loss: the drop-in operator (omg_cuda.sdf_loss_forward) on config 2's point count --------------------
+    from omg_planner_b200 import scene as S
+    from omg_planner_b200.cost import se3_inverse_f32
+    from omg_planner_b200.engine import sdf_loss_forward
+
+    sc = S.make_scene(num_objects=10, grid=128, seed=0)
+    N = 1024 * 30 * 150
+    pts_op = torch.from_numpy(rng.uniform([0.2, -0.5, -0.1], [0.9, 0.5, 0.6], (N, 3)).astype(np.float32)).cuda()
+    args = [torch.from_numpy(np.stack([se3_inverse_f32(m) for m in sc["pose_mats"]])).cuda(),
+            torch.from_numpy(sc["sdf_grids"]).cuda(), torch.from_numpy(sc["sdf_limits"]).cuda(), pts_op,
+            torch.full((10,), 0.2).cuda(), torch.ones(10).cuda(), torch.full((10,), 0.01).cuda(), torch.zeros(10).cuda()]
+    ms = _time(lambda: sdf_loss_forward(*args), flush, reps=3, warm=1)
+    pot, grad, col = sdf_loss_forward(*args)
+    out["sdf_loss_operator"] = {"workload": "%d points (1024 x 30 x 150) x 10 objects @128^3, uniform in the workspace box" % N,
+                                "ms": ms, "points_per_s": N / (ms * 1e-3), "point_object_pairs_per_s": 10 * N / (ms * 1e-3),
+                                "nonzero_potentials": int((pot > 0).sum().item())}
+    del args, pts_op, pot, grad, col
+    torch.cuda.empty_cache()
+
     # ---- omgb_point_sdf: table-top cloud -----------------------------------------------------------------------
     pts = rng.uniform([0.2, -0.5, 0.0], [1.0, 0.5, 0.6], (20000, 3))
     f = C.compute_sdf_from_points(pts)

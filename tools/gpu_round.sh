@@ -19,9 +19,12 @@ for K in sdf_pack_entry point_sdf_kernel ik_chain_kernel; do
   rm -f gpurun_out/aux_${K}_$TAG.ncu-rep
 done
 python tools/bench_goalset_plan.py > gpurun_out/goalset_plan_$TAG.json 2> gpurun_out/goalset_plan_$TAG.err
-B=64 ncu --set full --clock-control none -k regex:"learner_update|goal_cost" -s 20 -c 2 -f -o gpurun_out/learner_$TAG \
-    python tools/bench_goalset_plan.py > gpurun_out/learner_ncu_$TAG.log 2>&1
-python tools/ncu_summary.py gpurun_out/learner_$TAG.ncu-rep "goal_cost_kernel + learner_update_kernel, B=64 tools/bench_goalset_plan.py ($TAG)" > gpurun_out/ncu_learner_$TAG.txt
-rm -f gpurun_out/learner_$TAG.ncu-rep
+for K in learner_update_kernel goal_cost_kernel; do
+  B=1024 ncu --set full --clock-control none -k regex:$K -s 10 -c 1 -f -o gpurun_out/gs_${K}_$TAG \
+      python tools/bench_goalset_plan.py > gpurun_out/gs_ncu_${K}_$TAG.log 2>&1
+  python tools/ncu_summary.py gpurun_out/gs_${K}_$TAG.ncu-rep "$K, B=1024 G=20 tools/bench_goalset_plan.py ($TAG)" > gpurun_out/ncu_${K}_$TAG.txt
+  rm -f gpurun_out/gs_${K}_$TAG.ncu-rep
+done
+python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke_$TAG.log 2>&1; tail -1 gpurun_out/smoke_$TAG.log
 du -sh gpurun_out
 ls -la gpurun_out | tail -12
