@@ -3,8 +3,10 @@
   * fixed goal, or a goal set without goal switching (ol_alg "Baseline"/"Proj"): the whole plan -- every iteration of
     every trajectory, early exit on terminate, history_trajectories and the info list -- is ONE persistent launch
     (omgb_chomp_plan_history) plus one info-only launch for the trajectories that did not terminate.
-  * goal set with the online learner: per iteration one fused goal-scoring launch (Learner.update_goal), the learner's
-    [B,G] update on the host (BASELINE north_star keeps goal reweighting on the host), one fused CHOMP launch.
+  * goal set with the online learner: per iteration omgb_goal_costs -> omgb_learner_update -> omgb_chomp_plan_step on
+    one stream, no host synchronisation until the plan is over (_plan_with_device_learner).  cfg.host_learner = True
+    (or more than 256 goals) keeps BASELINE north_star's split instead: goal scoring and the CHOMP step on the device,
+    the learner's [B,G] update on the host (_plan_with_learner).
 
 Same names and results as the reference: `Planner(env, traj)`, `.plan(traj) -> info list`, `.history_trajectories`,
 `.info`, `.selected_goals`, `.cost`, `.optim`, `.learner`, `.grasp_init(env)`.  Goal sets come in through
@@ -83,26 +85,29 @@ class Planner(GoalSetMixin):
         self.optim = Optimizer(env, self.cost)
         self.lazy = lazy
         if self.cfg.goal_set_proj:
-            # omg/planner.py:103-114.  Objects that carry grasp poses (compute_grasp) get their goal sets built here
-            # -- batched IK, flip augmentation, collision / diversity filters (goal_set.py); objects whose
-            # .grasps / .reach_grasps are already set are used as they are.
-            if getattr(self.cfg, "use_external_grasp", False):
-                self.load_goal_from_external(self.cfg.external_grasps)
-            if self.cfg.scene_file == "" or self.cfg.traj_init == "grasp":
-                self.load_grasp_set(env)
-                self.setup_goal_set(env)
-            else:
-                self.load_goal_from_scene()
-            self.grasp_init(env)
-            self.learner = Learner(env, traj, self.cost)
+            self._load_goals(env)
         else:
             self.traj.interpolate_waypoints()
         self.history_trajectories = []
         self.info = []
         self.selected_goals = []
 
+    def _load_goals(self, env):
+        """omg/planner.py:103-114 / 137-147.  Objects that carry grasp poses (compute_grasp) get their goal sets built
+        here -- batched IK, flip augmentation, collision / diversity filters (goal_set.py); objects whose .grasps /
+        .reach_grasps are already set are used as they are."""
+        if getattr(self.cfg, "use_external_grasp", False):
+            self.load_goal_from_external(self.cfg.external_grasps)
+        elif self.cfg.scene_file == "" or self.cfg.traj_init == "grasp":
+            self.load_grasp_set(env)
+            self.setup_goal_set(env)
+        else:
+            self.load_goal_from_scene()
+        self.grasp_init(env)
+        self.learner = Learner(env, self.traj, self.cost)
+
     def update(self, env, traj):
-        """omg/planner.py:121-152 without the grasp loading."""
+        """omg/planner.py:121-152: re-plan in a changed scene / for a new trajectory with the same Cost."""
         self.cfg = env.config
         self.env = env
         self.traj = traj
@@ -112,11 +117,10 @@ class Planner(GoalSetMixin):
             self.cost.target_obj = env.objects[env.target_idx]
         self.optim = Optimizer(env, self.cost)
         if self.cfg.goal_set_proj:
-            self.grasp_init(env)
-            self.learner = Learner(env, traj, self.cost)
+            self._load_goals(env)
         else:
             self.traj.interpolate_waypoints()
-        self.history_trajectories, self.info = [], []
+        self.history_trajectories, self.info, self.selected_goals = [], [], []
 
     def load_goal_from_scene(self):
         """omg/planner.py:154-174: goals saved with a scene file (<scene_path>/<scene_file>.mat: 'goals',
