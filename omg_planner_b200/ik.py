@@ -21,18 +21,24 @@ def mat2quat_xyzw(R):
     PyKDL: omg/util.py:105-127, 223-227).  KDL rebuilds the matrix from it with a formula that is even in q
     (frames.cpp:191-198), so only the rotation matters, not the sign convention."""
     R = np.asarray(R, dtype=np.float64)
-    flat = R.reshape(-1, 3, 3)
-    out = np.zeros((flat.shape[0], 4))
-    for i, m in enumerate(flat):
-        # Bar-Itzhack: eigenvector of the symmetric 4x4 K matrix (robust to slightly non-orthonormal input)
-        K = np.array([[m[0, 0] - m[1, 1] - m[2, 2], 0, 0, 0],
-                      [m[0, 1] + m[1, 0], m[1, 1] - m[0, 0] - m[2, 2], 0, 0],
-                      [m[0, 2] + m[2, 0], m[1, 2] + m[2, 1], m[2, 2] - m[0, 0] - m[1, 1], 0],
-                      [m[2, 1] - m[1, 2], m[0, 2] - m[2, 0], m[1, 0] - m[0, 1], m[0, 0] + m[1, 1] + m[2, 2]]]) / 3.0
-        vals, vecs = np.linalg.eigh(K)
-        q = vecs[:, np.argmax(vals)]          # x, y, z, w
-        out[i] = q if q[3] >= 0 else -q
-    return out.reshape(R.shape[:-2] + (4,))
+    m = R.reshape(-1, 3, 3)
+    # Bar-Itzhack: eigenvector of the symmetric 4x4 K matrix for the largest eigenvalue (robust to slightly
+    # non-orthonormal input); all poses in one stacked eigh
+    K = np.zeros((m.shape[0], 4, 4))
+    K[:, 0, 0] = m[:, 0, 0] - m[:, 1, 1] - m[:, 2, 2]
+    K[:, 1, 0] = m[:, 0, 1] + m[:, 1, 0]
+    K[:, 1, 1] = m[:, 1, 1] - m[:, 0, 0] - m[:, 2, 2]
+    K[:, 2, 0] = m[:, 0, 2] + m[:, 2, 0]
+    K[:, 2, 1] = m[:, 1, 2] + m[:, 2, 1]
+    K[:, 2, 2] = m[:, 2, 2] - m[:, 0, 0] - m[:, 1, 1]
+    K[:, 3, 0] = m[:, 2, 1] - m[:, 1, 2]
+    K[:, 3, 1] = m[:, 0, 2] - m[:, 2, 0]
+    K[:, 3, 2] = m[:, 1, 0] - m[:, 0, 1]
+    K[:, 3, 3] = m[:, 0, 0] + m[:, 1, 1] + m[:, 2, 2]
+    vals, vecs = np.linalg.eigh(K / 3.0)                 # (lower triangle is what eigh reads)
+    q = vecs[np.arange(m.shape[0]), :, np.argmax(vals, axis=1)]   # x, y, z, w
+    q = np.where(q[:, 3:4] >= 0, q, -q)
+    return q.reshape(R.shape[:-2] + (4,))
 
 
 def poses_to_targets(poses):
