@@ -9,7 +9,7 @@ ROOT = os.path.dirname(_HERE)
 LIB_PATH = os.environ.get("OMGB_LIB") or os.path.join(_HERE, "lib", "libomgb200.so")   # OMGB_LIB: A/B experiments
 SOURCES = [os.path.join(_HERE, "csrc", f) for f in ("omgb200.cu", "chomp_kernels.cuh", "goal_kernels.cuh",
                                                      "sdf_device.cuh", "sdf_asset_kernels.cuh", "traj_kernels.cuh", "learner_kernels.cuh",
-                                                     "ik_kernels.cu", "host_common.h")] + [
+                                                     "ik_kernels.cu", "ik_svd_reg.cuh", "host_common.h")] + [
     os.path.join(ROOT, "include", "omgb200.h")]
 
 INFO_STRIDE = 16

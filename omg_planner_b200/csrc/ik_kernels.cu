@@ -11,12 +11,14 @@
 // what remains different from the reference is the last bit of sin / cos / acos.
 #include <cuda_runtime.h>
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <string>
 
 #include "../../include/omgb200.h"
 #include "host_common.h"
+#include "ik_svd_reg.cuh"
 
 namespace omgb {
 
@@ -76,13 +78,18 @@ __device__ __forceinline__ void d_rot2(const double *v, double angle, double *R)
 // Forward kinematics and Jacobian in one walk of the chain (chainfksolverpos_recursive.cpp and
 // chainjnttojacsolver.cpp:49-95 compute the same frames with the same operations): tip frame `T`, J rows 0-2 linear /
 // 3-5 angular, reference point at the tip.
-__device__ void d_fk_jac(const IkChain &c, const double *q, Fr &T, double (*J)[IK_NJ], bool want_jac) {
+template <bool UNROLL>
+__device__ __forceinline__ void d_fk_jac(const IkChain &c, const double *q, Fr &T, double (*J)[IK_NJ], bool want_jac) {
 #pragma unroll
     for (int i = 0; i < 9; ++i) T.M[i] = (i % 4 == 0) ? 1.0 : 0.0;
     T.p[0] = T.p[1] = T.p[2] = 0.0;
-    if (want_jac)
+    if (want_jac) {
+#pragma unroll
         for (int r = 0; r < 6; ++r)
+#pragma unroll
             for (int k = 0; k < IK_NJ; ++k) J[r][k] = 0.0;
+    }
+#pragma unroll(UNROLL ? IK_NSEG : 1)
     for (int s = 0; s < IK_NSEG; ++s) {
         const bool mov = s < IK_NJ;
         double PM[9], Pp[3];
@@ -112,6 +119,7 @@ __device__ void d_fk_jac(const IkChain &c, const double *q, Fr &T, double (*J)[I
             double d[3];
 #pragma unroll
             for (int i = 0; i < 3; ++i) d[i] = total.p[i] - T.p[i];
+#pragma unroll
             for (int k = 0; k < IK_NJ; ++k) {                   // changeRefPoint of every column: vel += rot x d
                 const double r[3] = {J[3][k], J[4][k], J[5][k]};
                 double cr[3];
@@ -336,7 +344,10 @@ __device__ void d_get_rot(const double *d, double *out) {
 }
 
 // One ChainIkSolverPos_NR_JL::CartToJnt: q in/out.  Returns 0 (found), -5 (iteration limit) or -100 (SVD failure).
-__device__ int d_ik_solve(const IkChain &c, const double *target, double *q, int *steps) {
+// REG: the factorisation keeps U / w / tmp in registers and V in shared memory (ik_svd_reg.cuh); otherwise the generic
+// d_svd with everything in local memory.  Same operations in the same order either way.
+template <bool REG>
+__device__ int d_ik_solve(const IkChain &c, const double *target, double *q, int *steps, double *v_smem, int v_stride) {
     Fr goal;
     {
         const double x = target[3], y = target[4], z = target[5], w = target[6];
@@ -349,10 +360,12 @@ __device__ int d_ik_solve(const IkChain &c, const double *target, double *q, int
     const int maxiter = 100;
     const double eps = 1e-6, svd_eps = 0.00001;
     int i, status = 0;
-    double U[6][IK_NJ], V[IK_NJ][IK_NJ], S[IK_NJ], tmp[IK_NJ];
+    double U[6][IK_NJ], S[IK_NJ], tmp[IK_NJ];
+    double Vloc[REG ? 1 : IK_NJ][IK_NJ];
+    const VRef Vs{v_smem, v_stride};
     for (i = 0; i < maxiter; i++) {
         Fr f;
-        d_fk_jac(c, q, f, U, true);
+        d_fk_jac<REG>(c, q, f, U, true);
         double tw[6], Mi[9], Rrel[9], rv[3], rr[3];
 #pragma unroll
         for (int a = 0; a < 3; ++a) tw[a] = goal.p[a] - f.p[a];
@@ -368,20 +381,26 @@ __device__ int d_ik_solve(const IkChain &c, const double *target, double *q, int
 #pragma unroll
         for (int a = 0; a < 6; ++a) zero = zero && (eps > tw[a]) && (tw[a] > -eps);
         if (zero) break;
-        if (d_svd(U, S, V, tmp, 150) != 0) { status = -100; break; }
+        const int rc = REG ? r_svd(U, S, Vs, tmp, 150) : d_svd(U, S, Vloc, tmp, 150);
+        if (rc != 0) { status = -100; break; }
+#pragma unroll
         for (int a = 0; a < IK_NJ; ++a) {
             double sum = 0.0;
+#pragma unroll
             for (int b = 0; b < 6; ++b) sum += U[b][a] * tw[b];
             tmp[a] = fabs(S[a]) < svd_eps ? 0.0 : sum / S[a];
         }
+#pragma unroll
         for (int a = 0; a < IK_NJ; ++a) {
             double sum = 0.0;
-            for (int b = 0; b < IK_NJ; ++b) sum += V[a][b] * tmp[b];
+#pragma unroll
+            for (int b = 0; b < IK_NJ; ++b) sum += (REG ? Vs(a, b) : Vloc[REG ? 0 : a][b]) * tmp[b];
             double v = q[a] + sum;
             if (v < c.qmin[a]) v = c.qmin[a];
             if (v > c.qmax[a]) v = c.qmax[a];
             S[a] = v;   // (tmp is still being read; S is free)
         }
+#pragma unroll
         for (int a = 0; a < IK_NJ; ++a) q[a] = S[a];
     }
     *steps = i;
@@ -391,11 +410,13 @@ __device__ int d_ik_solve(const IkChain &c, const double *target, double *q, int
 
 // targets [P,T,7] (position xyz, quaternion xyzw), seeds [S,7] -> sols [P,S,T,7], solved [P,S] (solves that succeeded
 // before the first failure), steps [P,S,T] or null (Newton steps of every solve attempted).
+template <bool REG>
 __global__ void __launch_bounds__(64) ik_chain_kernel(const __grid_constant__ IkChain c,
                                                       const double *__restrict__ targets,
                                                       const double *__restrict__ seeds, int P, int T, int S,
                                                       double *__restrict__ sols, int *__restrict__ solved,
                                                       int *__restrict__ steps) {
+    __shared__ double s_v[REG ? 49 * 64 : 1];   // V of every thread, [element][thread]
     const long long total = (long long)P * S;
     for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
          idx += (long long)gridDim.x * blockDim.x) {
@@ -413,7 +434,7 @@ __global__ void __launch_bounds__(64) ik_chain_kernel(const __grid_constant__ Ik
 #pragma unroll
             for (int a = 0; a < IK_NJ; ++a) r[a] = q[a];
             int st = 0;
-            const int rc = d_ik_solve(c, tg, r, &st);
+            const int rc = d_ik_solve<REG>(c, tg, r, &st, s_v + (REG ? threadIdx.x : 0), 64);
             if (steps) steps[(size_t)idx * T + t] = st;
 #pragma unroll
             for (int a = 0; a < IK_NJ; ++a) sols[((size_t)idx * T + t) * IK_NJ + a] = r[a];
@@ -434,7 +455,7 @@ __global__ void __launch_bounds__(128) ik_fk_kernel(const __grid_constant__ IkCh
 #pragma unroll
     for (int a = 0; a < IK_NJ; ++a) q[a] = joints[(size_t)m * joint_stride + a];
     Fr f;
-    d_fk_jac(c, q, f, nullptr, false);
+    d_fk_jac<false>(c, q, f, nullptr, false);
     double *o = poses + (size_t)m * 16;
 #pragma unroll
     for (int r = 0; r < 3; ++r) {
@@ -496,8 +517,25 @@ extern "C" int omgb_ik_solve(const double *chain_frames, const double *q_min, co
     if (!d_targets || !d_seeds || !d_sols || !d_solved) return host_fail(OMGB_ERR_INVALID, "omgb_ik_solve: null buffer");
     long long blocks = (total + 63) / 64;
     if (blocks > 148LL * 64) blocks = 148LL * 64;
-    ik_chain_kernel<<<(int)blocks, 64, 0, (cudaStream_t)stream>>>(c, d_targets, d_seeds, num_poses, chain_length,
-                                                                 num_seeds, d_sols, d_solved, d_steps);
+    // Two builds of the same arithmetic (identical results, tests/test_cpu_ik_svd_reg.py): the register-resident
+    // factorisation has the shorter dependent chain but needs 255 registers and 25 KB of shared memory per 64 chains,
+    // the generic one keeps U / V in local memory at 168 registers.  Measured on B200: 3900 chains 40.8 vs 44.5 ms,
+    // 39000 chains 189 vs 78 ms -- so goal-set sized problems take the first, up-sampled sets the second.
+    // OMGB_IK_SVD=reg|local forces one.
+    static int forced = -2;
+    if (forced == -2) {
+        const char *e = getenv("OMGB_IK_SVD");
+        forced = !e ? -1 : (strcmp(e, "local") == 0 ? 0 : (strcmp(e, "reg") == 0 ? 1 : -1));
+    }
+    const int use_reg = forced >= 0 ? forced : (total <= 4096 ? 1 : 0);
+    if (use_reg)
+        ik_chain_kernel<true><<<(int)blocks, 64, 0, (cudaStream_t)stream>>>(c, d_targets, d_seeds, num_poses,
+                                                                           chain_length, num_seeds, d_sols, d_solved,
+                                                                           d_steps);
+    else
+        ik_chain_kernel<false><<<(int)blocks, 64, 0, (cudaStream_t)stream>>>(c, d_targets, d_seeds, num_poses,
+                                                                            chain_length, num_seeds, d_sols, d_solved,
+                                                                            d_steps);
     host_count_launch();
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return host_fail(OMGB_ERR_CUDA, std::string("ik_chain_kernel: ") + cudaGetErrorString(e));
