@@ -26,6 +26,22 @@ def test_library_loads_and_exports_every_declared_symbol():
         assert hasattr(L, name), name
 
 
+def test_header_is_plain_c(tmp_path):
+    """include/omgb200.h must compile as C99 (the boundary is a C ABI: no C++, no torch types) and its struct layouts
+    must match the ctypes mirrors."""
+    import ctypes
+    import subprocess
+
+    src = tmp_path / "h.c"
+    src.write_text('#include <stdio.h>\n#include "omgb200.h"\nint main(void){printf("%zu %zu %zu\\n", '
+                   'sizeof(omgb_step_params_t), sizeof(omgb_learner_params_t), sizeof(omgb_sdf_source_t));return 0;}\n')
+    exe = tmp_path / "h"
+    subprocess.check_call(["gcc", "-std=c99", "-pedantic", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"),
+                           "-o", str(exe), str(src)])
+    sizes = [int(v) for v in subprocess.check_output([str(exe)]).split()]
+    assert sizes == [ctypes.sizeof(_lib.StepParams), ctypes.sizeof(_lib.LearnerParams), ctypes.sizeof(_lib.SdfSource)]
+
+
 def test_argument_validation_without_gpu():
     L = _lib.lib()
     assert L.omgb_scene_set_robot(None, None, None, None, None, 0, None, None, 15, None, None) == -1
