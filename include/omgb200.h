@@ -306,7 +306,9 @@ int omgb_point_sdf(const double *d_points, int num_points, const double *d_gx, c
  *   T = 1 for a single solve.
  * d_seeds DEVICE [S, 7].  Outputs: d_sols DEVICE [P, S, T, 7]; d_solved DEVICE int32 [P, S] = number of solves that
  *   succeeded before the first failure (== T: the whole chain solved); d_steps DEVICE int32 [P, S, T] or NULL =
- *   Newton steps of each solve attempted. */
+ *   Newton steps of each solve attempted.
+ * Two builds of the same arithmetic exist (factorisation in registers / in local memory); the library picks by
+ * problem size, the environment variable OMGB_IK_SVD=reg|local forces one.  Results are identical. */
 int omgb_ik_solve(const double *chain_frames, const double *q_min, const double *q_max, const double *d_targets,
                   int num_poses, int chain_length, const double *d_seeds, int num_seeds, double *d_sols,
                   int *d_solved, int *d_steps, void *stream);
