@@ -8,6 +8,9 @@
     (or more than 256 goals) keeps BASELINE north_star's split instead: goal scoring and the CHOMP step on the device,
     the learner's [B,G] update on the host (_plan_with_learner).
 
+cfg.timeout (the reference's wall-clock stop, omg/planner.py:629, 3 s by default there) is honoured by the host-learner
+loop only: the fused paths finish a 70-iteration plan in milliseconds and cannot be interrupted from the host.
+
 Same names and results as the reference: `Planner(env, traj)`, `.plan(traj) -> info list`, `.history_trajectories`,
 `.info`, `.selected_goals`, `.cost`, `.optim`, `.learner`, `.grasp_init(env)`.  Goal sets come in through
 env.objects[target].grasps / .reach_grasps (built by goal_set.py from grasp poses, or given).
