@@ -50,7 +50,7 @@ __global__ void prep_objects_kernel(const float *__restrict__ pose, const float 
     const float *P = pose + 16 * o;
     float m[3][3] = {{P[0], P[1], P[2]}, {P[4], P[5], P[6]}, {P[8], P[9], P[10]}};
     float q[3], w;
-    float t = __fadd_rn(__fadd_rn(m[0][0], m[1][1]), m[2][2]);
+    float t = __fadd_rn(m[0][0], __fadd_rn(m[1][1], m[2][2]));   // trace(): Eigen's unrolled tree redux c0 + (c1 + c2)
     if (t > 0.0f) {
         t = __fsqrt_rn(__fadd_rn(t, 1.0f));
         w = __fmul_rn(0.5f, t);
@@ -73,13 +73,14 @@ __global__ void prep_objects_kernel(const float *__restrict__ pose, const float 
     ObjRec r;
     r.qw = w; r.qx = q[0]; r.qy = q[1]; r.qz = q[2];
     r.tx = P[3]; r.ty = P[7]; r.tz = P[11];
+    // toRotationMatrix with the multiply-adds fused exactly where nvcc fuses them in the reference kernel
+    // (oracle/sdf_ref: SASS of the reference source built for sm_100a; tests/test_gpu_ref_operator.py)
     const float tx = __fmul_rn(2.0f, q[0]), ty = __fmul_rn(2.0f, q[1]), tz = __fmul_rn(2.0f, q[2]);
-    const float twx = __fmul_rn(tx, w), twy = __fmul_rn(ty, w), twz = __fmul_rn(tz, w);
-    const float txx = __fmul_rn(tx, q[0]), txy = __fmul_rn(ty, q[0]), txz = __fmul_rn(tz, q[0]);
-    const float tyy = __fmul_rn(ty, q[1]), tyz = __fmul_rn(tz, q[1]), tzz = __fmul_rn(tz, q[2]);
-    r.r[0] = __fsub_rn(1.0f, __fadd_rn(tyy, tzz)); r.r[1] = __fsub_rn(txy, twz); r.r[2] = __fadd_rn(txz, twy);
-    r.r[3] = __fadd_rn(txy, twz); r.r[4] = __fsub_rn(1.0f, __fadd_rn(txx, tzz)); r.r[5] = __fsub_rn(tyz, twx);
-    r.r[6] = __fsub_rn(txz, twy); r.r[7] = __fadd_rn(tyz, twx); r.r[8] = __fsub_rn(1.0f, __fadd_rn(txx, tyy));
+    const float twx = __fmul_rn(tx, w), twz = __fmul_rn(tz, w), txz = __fmul_rn(tz, q[0]);
+    const float tyy = __fmul_rn(ty, q[1]), tzz = __fmul_rn(tz, q[2]);
+    r.r[0] = __fsub_rn(1.0f, __fadd_rn(tyy, tzz)); r.r[1] = __fmaf_rn(ty, q[0], -twz); r.r[2] = __fmaf_rn(ty, w, txz);
+    r.r[3] = __fmaf_rn(ty, q[0], twz); r.r[4] = __fsub_rn(1.0f, __fmaf_rn(tx, q[0], tzz)); r.r[5] = __fmaf_rn(tz, q[1], -twx);
+    r.r[6] = __fmaf_rn(-ty, w, txz); r.r[7] = __fmaf_rn(tz, q[1], twx); r.r[8] = __fsub_rn(1.0f, __fmaf_rn(tx, q[0], tyy));
     const float *lim = limits + 10 * o;
     r.minx = lim[0]; r.miny = lim[1]; r.minz = lim[2];
     r.ex = __fsub_rn(lim[3], lim[0]); r.ey = __fsub_rn(lim[4], lim[1]); r.ez = __fsub_rn(lim[5], lim[2]);

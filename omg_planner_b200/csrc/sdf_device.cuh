@@ -2,8 +2,10 @@
 //
 // Arithmetic contract (what "results identical to the reference" means for this operator): every fp32
 // operation of layers/sdf_matching_loss_kernel.cu:97-181 is reproduced as a separately rounded IEEE op,
-// with fused multiply-adds only where written as __fmaf_rn below (the lerp a + t*(b-a), the quaternion
-// cross products, w*uv + p, and the R^T*g accumulation).  The reference's double-precision steps
+// with fused multiply-adds exactly where nvcc 12.9 fuses them when it compiles the reference's own source for
+// sm_100a (oracle/sdf_ref builds that source; its SASS was read instruction by instruction and the result is
+// checked bit for bit on the B200, tests/test_gpu_ref_operator.py): the lerp a + t*(b-a), the quaternion cross
+// products, w*uv + p, the quaternion -> rotation matrix entries and the R^T*g accumulation.  The reference's double-precision steps
 // ((p - 0.5) in double, 0.5*(f+ - f-)/delta in double, -v + 0.5*eps in double) are evaluated in fp32 in a
 // way that is bit-identical to the double path (double rounding through binary64 is innocuous for +,-,/
 // of binary32 operands since 53 >= 2*24+2; the one value where (int)(p - 0.5) would differ is handled by
@@ -139,10 +141,10 @@ __device__ __forceinline__ void finish_pair(const ObjRec &o, float v, float fpx,
         vy = __fmul_rn(__fmul_rn(__fmul_rn(o.inveps, dgy), d), o.pad);
         vz = __fmul_rn(__fmul_rn(__fmul_rn(o.inveps, dgz), d), o.pad);
     }
-    // rotationMatrix.transpose() * vgrad   (kernel.cu:176)
-    gx = __fmaf_rn(o.r[6], vz, __fmaf_rn(o.r[3], vy, __fmul_rn(o.r[0], vx)));
-    gy = __fmaf_rn(o.r[7], vz, __fmaf_rn(o.r[4], vy, __fmul_rn(o.r[1], vx)));
-    gz = __fmaf_rn(o.r[8], vz, __fmaf_rn(o.r[5], vy, __fmul_rn(o.r[2], vx)));
+    // rotationMatrix.transpose() * vgrad   (kernel.cu:176): Eigen's 3-term tree sum c0 + (c1 + c2) as nvcc fuses it
+    gx = __fmaf_rn(o.r[0], vx, __fmaf_rn(o.r[3], vy, __fmul_rn(o.r[6], vz)));
+    gy = __fmaf_rn(o.r[1], vx, __fmaf_rn(o.r[4], vy, __fmul_rn(o.r[7], vz)));
+    gz = __fmaf_rn(o.r[2], vx, __fmaf_rn(o.r[5], vy, __fmul_rn(o.r[8], vz)));
 }
 
 // Full evaluation by one thread: potential, world-frame potential gradient, collide flag (kernel.cu:147-180).

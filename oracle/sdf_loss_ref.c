@@ -22,17 +22,26 @@
  * restated here from Eigen 3.3's published Quaternion.h algorithms (Shoemake matrix->quaternion;
  * v + w*(2 q x v) + q x (2 q x v); the standard 12-product quaternion->matrix).
  *
- * Floating-point contraction: the reference was compiled by nvcc, which fuses a*b+c into FMA wherever
- * its scheduler likes (unknowable without building it; it cannot be built here: Eigen is absent).  This
- * restatement fixes one explicit contraction pattern (fmaf() below marks every fused op; everything else
- * is a separately rounded IEEE op; compile with -ffp-contract=off).  The double-precision steps of the
+ * Floating-point contraction: the reference is compiled by nvcc, which fuses a*b+c into FMA where its
+ * optimiser likes.  The pattern restated here (fmaf() marks every fused op; everything else is a separately
+ * rounded IEEE op; compile with -ffp-contract=off) is the one nvcc 12.9 -- the toolchain of this image, and the
+ * oldest that targets sm_100 -- emits when it compiles the reference's own source for sm_100a with the flags of
+ * layers/setup.py: oracle/sdf_ref/ builds that source where it lies (over stand-ins for the absent
+ * ATen/Eigen/Sophus headers) and its SASS was read instruction by instruction.  The double-precision steps of the
  * reference ((p-0.5) in double; 0.5*(f+-f-)/delta in double; -v+0.5*eps in double) are evaluated in
  * double here exactly as written.
  *
- * PARITY STATUS: the reference ships no golden vectors for this operator and its
- * CUDA half cannot be compiled or run here => this file is pinned only by (a) analytic SDF fields
- * whose trilinear interpolant is known in closed form (tests/test_oracle_sdf.py) and (b) agreement of
- * the full CHOMP step built on it with the reference's own Python (tests/golden, tools/make_golden.py).
+ * PARITY STATUS: the reference ships no golden vectors for this operator.  Pinned by
+ * (a) the reference's own getValueInterpolated / getGradientInterpolated (kernel.cu:37-86) compiled from the
+ *     reference source for the host (oracle/_ref/libsdf_ref.so): bit-exact on random grid coordinates incl. the
+ *     (-0.5, 0.5) truncation band, border voxels and out-of-bounds taps (tests/test_oracle_sdf.py, fixture
+ *     tests/golden/sdf_interp.npz);
+ * (b) the reference's own device path (sdf_loss_cuda_forward with its kernels, same library) run on the B200
+ *     against the product operator, which is bit-identical to this file (tests/test_gpu_ref_operator.py);
+ * (c) analytic SDF fields whose trilinear interpolant is known in closed form;
+ * (d) agreement of the full CHOMP step built on it with the reference's own Python (tests/golden).
+ * Not pinnable here: Eigen itself (absent, unpinned upstream) -- its three quaternion routines and the order of
+ * its 3-term reductions are restated from Eigen 3.3's published code in oracle/sdf_ref/shim/Eigen/Core.
  */
 #include <math.h>
 #include <stddef.h>
@@ -84,7 +93,7 @@ static f3 grad_interp(f3 p, i3 dim, const float *g, float delta) {
 
 /* Eigen::Quaternion<float>(Matrix3f) -- QuaternionBase::operator=(MatrixBase), Eigen 3.3 Quaternion.h */
 static void mat_to_quat(const float m[3][3], float *qw, float qv[3]) {
-    float t = m[0][0] + m[1][1] + m[2][2];
+    float t = m[0][0] + (m[1][1] + m[2][2]);   /* trace() = diagonal().sum(): unrolled tree redux c0 + (c1 + c2) */
     if (t > 0.0f) {
         t = sqrtf(t + 1.0f);
         *qw = 0.5f * t;
@@ -106,15 +115,16 @@ static void mat_to_quat(const float m[3][3], float *qw, float qv[3]) {
     }
 }
 
-/* Eigen::QuaternionBase::toRotationMatrix */
+/* Eigen::QuaternionBase::toRotationMatrix (tx = 2x ...; twx = tx*w ...; res(0,1) = txy - twz ...), with the
+ * multiply-adds fused exactly where nvcc 12.9 fuses them when it compiles the reference source for sm_100a
+ * (oracle/sdf_ref: SASS of SDFdistanceForward; verified on the B200 by tests/test_gpu_ref_operator.py):
+ * rounded products twx, twz, txz, tyy, tzz; txx, txy, twy, tyz exist only inside an FMA. */
 static void quat_to_mat(float w, const float v[3], float R[3][3]) {
     const float tx = 2.0f * v[0], ty = 2.0f * v[1], tz = 2.0f * v[2];
-    const float twx = tx * w, twy = ty * w, twz = tz * w;
-    const float txx = tx * v[0], txy = ty * v[0], txz = tz * v[0];
-    const float tyy = ty * v[1], tyz = tz * v[1], tzz = tz * v[2];
-    R[0][0] = 1.0f - (tyy + tzz); R[0][1] = txy - twz;          R[0][2] = txz + twy;
-    R[1][0] = txy + twz;          R[1][1] = 1.0f - (txx + tzz); R[1][2] = tyz - twx;
-    R[2][0] = txz - twy;          R[2][1] = tyz + twx;          R[2][2] = 1.0f - (txx + tyy);
+    const float twx = tx * w, twz = tz * w, txz = tz * v[0], tyy = ty * v[1], tzz = tz * v[2];
+    R[0][0] = 1.0f - (tyy + tzz);            R[0][1] = fmaf(ty, v[0], -twz);          R[0][2] = fmaf(ty, w, txz);
+    R[1][0] = fmaf(ty, v[0], twz);           R[1][1] = 1.0f - fmaf(tx, v[0], tzz);    R[1][2] = fmaf(tz, v[1], -twx);
+    R[2][0] = fmaf(-ty, w, txz);             R[2][1] = fmaf(tz, v[1], twx);           R[2][2] = 1.0f - fmaf(tx, v[0], tyy);
 }
 
 static inline f3 cross_fma(const float a[3], f3 b) {
@@ -188,10 +198,11 @@ long long omg_oracle_sdf_loss(const float *pose_init, const float *sdf_grids, co
             } else {
                 continue;                                               /* kernel.cu:172-173 */
             }
-            /* rotationMatrix.transpose() * vgrad   kernel.cu:176 */
-            const float gx = fmaf(R[2][0], vg[2], fmaf(R[1][0], vg[1], R[0][0] * vg[0]));
-            const float gy = fmaf(R[2][1], vg[2], fmaf(R[1][1], vg[1], R[0][1] * vg[0]));
-            const float gz = fmaf(R[2][2], vg[2], fmaf(R[1][2], vg[1], R[0][2] * vg[0]));
+            /* rotationMatrix.transpose() * vgrad   kernel.cu:176: coefficient i = (row_i . v).sum() = c0 + (c1 + c2)
+             * (Eigen's unrolled tree redux), fused by nvcc as fma(R0i, v0, fma(R1i, v1, R2i*v2)) */
+            const float gx = fmaf(R[0][0], vg[0], fmaf(R[1][0], vg[1], R[2][0] * vg[2]));
+            const float gy = fmaf(R[0][1], vg[0], fmaf(R[1][1], vg[1], R[2][1] * vg[2]));
+            const float gz = fmaf(R[0][2], vg[0], fmaf(R[1][2], vg[1], R[2][2] * vg[2]));
             potentials[n] += pot;                                       /* kernel.cu:186-195, 250-258 */
             potential_grads[3 * n + 0] += gx;
             potential_grads[3 * n + 1] += gy;
@@ -199,4 +210,24 @@ long long omg_oracle_sdf_loss(const float *pose_init, const float *sdf_grids, co
         }
     }
     return p_in;
+}
+
+/* The two interpolation helpers on their own (grid coordinates in, value / gradient out), for the pin against the
+ * reference's own getValueInterpolated / getGradientInterpolated (tests/test_oracle_sdf.py). */
+void omg_oracle_value_interp(const float *pgrid, int n, const float *grid, int d0, int d1, int d2, float *out) {
+    const i3 dim = {d0, d1, d2};
+    for (int i = 0; i < n; ++i) {
+        const f3 p = {pgrid[3 * i], pgrid[3 * i + 1], pgrid[3 * i + 2]};
+        out[i] = value_interp(p, dim, grid, 0);
+    }
+}
+
+void omg_oracle_grad_interp(const float *pgrid, int n, const float *grid, int d0, int d1, int d2, float delta,
+                            float *out) {
+    const i3 dim = {d0, d1, d2};
+    for (int i = 0; i < n; ++i) {
+        const f3 p = {pgrid[3 * i], pgrid[3 * i + 1], pgrid[3 * i + 2]};
+        const f3 g = grad_interp(p, dim, grid, delta);
+        out[3 * i] = g.x; out[3 * i + 1] = g.y; out[3 * i + 2] = g.z;
+    }
 }

@@ -27,7 +27,23 @@ def _load():
         fp = ctypes.POINTER(ctypes.c_float)
         _lib.omg_oracle_sdf_loss.restype = ctypes.c_longlong
         _lib.omg_oracle_sdf_loss.argtypes = [fp] * 8 + [ctypes.c_int, ctypes.c_int] + [fp] * 3
+        _lib.omg_oracle_value_interp.argtypes = [fp, ctypes.c_int, fp] + [ctypes.c_int] * 3 + [fp]
+        _lib.omg_oracle_grad_interp.argtypes = [fp, ctypes.c_int, fp] + [ctypes.c_int] * 3 + [ctypes.c_float, fp]
     return _lib
+
+
+def interp(pgrid, grid, delta):
+    """The restatement's getValueInterpolated / getGradientInterpolated on grid coordinates pgrid [N,3] of one grid
+    [d0,d1,d2] -> (values [N], gradients [N,3])."""
+    lib = _load()
+    pgrid, grid = _f32(pgrid), _f32(grid)
+    n = pgrid.shape[0]
+    val, grad = np.empty(n, np.float32), np.empty((n, 3), np.float32)
+    fp = ctypes.POINTER(ctypes.c_float)
+    c = lambda a: a.ctypes.data_as(fp)
+    lib.omg_oracle_value_interp(c(pgrid), n, c(grid), grid.shape[0], grid.shape[1], grid.shape[2], c(val))
+    lib.omg_oracle_grad_interp(c(pgrid), n, c(grid), grid.shape[0], grid.shape[1], grid.shape[2], float(delta), c(grad))
+    return val, grad
 
 
 def _f32(a):

@@ -42,4 +42,9 @@ def _built_artifacts():
         kdl_ik_ref.build_ref()
     except Exception:   # noqa: BLE001 -- the prebuilt library (if any) is used as it is
         pass
+    try:
+        from oracle import sdf_ref_lib
+        sdf_ref_lib.build_ref()
+    except Exception:   # noqa: BLE001
+        pass
     yield

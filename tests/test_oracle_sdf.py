@@ -107,3 +107,42 @@ def test_trilinear_matches_manual_on_random_grid():
     assert pin == 50 and not pot.any()
     sure = np.abs(val - thr) > 1e-5
     np.testing.assert_array_equal(col[sure], (val < thr)[sure].astype(np.float32))
+
+
+# ---- pin against the reference's own interpolation helpers (layers/sdf_matching_loss_kernel.cu:15-86) ------------
+def _bits(a):
+    return np.ascontiguousarray(a, np.float32).view(np.uint32)
+
+
+def test_interp_equals_reference_fixture():
+    """oracle/sdf_loss_ref.c's value_interp / grad_interp == outputs of the reference's getValueInterpolated /
+    getGradientInterpolated (compiled from the reference source; tools/make_golden_sdf_interp.py), bit for bit."""
+    import os
+    fx = np.load(os.path.join(os.path.dirname(__file__), "golden", "sdf_interp.npz"))
+    val, grad = op.interp(fx["pgrid"], fx["grid"], float(fx["delta"]))
+    assert (fx["value"] == 1.0).sum() > 1000 and (fx["value"] != 1.0).sum() > 5000
+    np.testing.assert_array_equal(_bits(val), _bits(fx["value"]))
+    np.testing.assert_array_equal(_bits(grad), _bits(fx["grad"]))
+
+
+def test_interp_equals_reference_helpers():
+    """Live against oracle/_ref/libsdf_ref.so (the reference source compiled by oracle/sdf_ref/Makefile): 2 x 10^5
+    random grid coordinates on two grids, incl. the (-0.5, 0.5) truncation band, border voxels and OOB taps."""
+    import pytest
+    from oracle import sdf_ref_lib
+    if not sdf_ref_lib.have_ref():
+        pytest.skip("oracle/_ref/libsdf_ref.so not built (needs /root/reference)")
+    import sys, os
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    from make_golden_sdf_interp import coordinates
+    for seed, dims in ((1, (13, 9, 21)), (2, (40, 33, 17))):
+        rng = np.random.RandomState(seed)
+        grid = rng.normal(0.1, 0.3, dims).astype(np.float32)
+        pg = coordinates(dims, 100000, rng)
+        delta = np.float32(rng.uniform(0.002, 0.02))
+        v_ref, g_ref = sdf_ref_lib.interp(pg, grid, delta)
+        v, g = op.interp(pg, grid, delta)
+        np.testing.assert_array_equal(_bits(v), _bits(v_ref))
+        np.testing.assert_array_equal(_bits(g), _bits(g_ref))
+        band = ((pg > -0.5) & (pg < 0.5)).any(1)
+        assert band.sum() > 1000 and (v_ref[band] != 1.0).sum() > 100   # the truncation band is exercised in bounds

@@ -4,7 +4,8 @@
 set -e
 cd "$(dirname "$0")/.."
 make -s -C oracle            # CPU restatements
-make -s -C oracle ref        # the reference's KDL (oracle/_ref/libkdl_ik.so)
+make -s -C oracle ref        # the reference's KDL (oracle/_ref/libkdl_ik.so) and CUDA operator source (libsdf_ref.so)
+python tools/make_golden_sdf_interp.py # sdf_interp.npz : the reference's getValueInterpolated / getGradientInterpolated
 python tools/make_golden.py            # chomp_*.npz    : omg.cost.Cost + omg.optimizer.Optimizer, 7 modes
 python tools/make_golden_learner.py    # learner_*.npz  : omg.online_learner.Learner in Planner.plan's interleave
 python tools/make_golden_plan.py       # plan_*.npz     : omg.planner.Planner.plan
