@@ -2,9 +2,11 @@
 method of ycb_render/robotPose/robot_pykdl.py) from /root/reference under stubs, with `omg_cuda`
 bound to the CPU restatement of layers/sdf_matching_loss_kernel.cu (oracle/sdf_loss_ref.c).
 
-BUILD-CONTAINER ONLY.  /root/reference does not exist on the GPU box; nothing under tests/ -m gpu,
-bench.py or __graft_entry__ imports this file.  It exists to (1) pin oracle/chomp_ref.py against
-the reference's own code and (2) generate tests/golden/*.npz (tools/make_golden.py).
+It exists to (1) pin oracle/chomp_ref.py against the reference's own code, (2) generate tests/golden/*.npz
+(tools/make_golden.py) -- both BUILD-CONTAINER ONLY, /root/reference does not exist on the GPU box -- and (3) drive
+the reference's own classes on the B200 from the staged copy tests/_ref_snapshot/ (tools/stage_ref_snapshot.py;
+OMG_REFERENCE_ROOT points at it) with `omg_cuda` bound to the product operator
+(tests/test_gpu_reference_classes.py).  bench.py and __graft_entry__ never import this file.
 
 Stub list follows SURVEY.md section 8(c).
 """
