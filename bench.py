@@ -171,8 +171,16 @@ def run_b200(a):
     from omg_planner_b200.engine import ChompEngine
 
     torch.cuda.set_device(local)
+    nccl_log = None
     if world > 1:
-        os.environ["NCCL_DEBUG"] = os.environ.get("OMGB_NCCL_DEBUG", "WARN")   # keep stdout to the one JSON line
+        # NCCL's INFO log goes to a per-rank file (stdout carries the one JSON line); rank 0 copies its init lines to
+        # stderr and into the JSON line ("nccl") so that the communicator size is checkable.
+        os.environ.setdefault("NCCL_DEBUG", "INFO")
+        os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT,ENV")
+        if "NCCL_DEBUG_FILE" not in os.environ:
+            os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+            os.environ["NCCL_DEBUG_FILE"] = os.path.join(ROOT, "gpurun_out", "nccl_n%d_rank%%h_%%p.log" % world)
+        nccl_log = os.environ["NCCL_DEBUG_FILE"]
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     cfg = ChompConfig(timesteps=a.waypoints, **mode)
     robot = PandaConstants()
@@ -293,22 +301,53 @@ def run_b200(a):
         e2e_modes[mode_name] = float(t.item())
     e2e_ms_max = e2e_modes["default_zero_copy"]
 
-    # the one collective of the path: all-gather of the final per-trajectory costs
+    # the one collective of the path: all-gather of the final per-trajectory costs, timed on the device
     final_cost = out["info"][:, 2].contiguous()
+    allgather_ms = None
     if world > 1:
         from omg_planner_b200 import dist as D
+        D.all_gather_costs(final_cost)   # warm-up: communicator channels, buffers
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
         gathered = D.all_gather_costs(final_cost)
+        e1.record()
+        torch.cuda.synchronize()
         assert gathered.shape[0] == world * B
-    if rank != 0:
+        t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        allgather_ms = float(t.item())
+
+    # the reference's plugin call: Optimizer.optimize(traj, force_update=True) with a host numpy trajectory, one
+    # trajectory (the reference's own shape) and the whole batch; wall clock per call incl. H2D / D2H and Python
+    e2e_plugin = None
+    if not a.no_plugin:
+        e2e_plugin = run_plugin_e2e(a, scene, mode, xi0, st, en, tails, robot, steps=a.steps)
+        t = torch.tensor([e2e_plugin["batch"]["ms_per_call"]], dtype=torch.float64, device="cuda")
         if world > 1:
-            dist.destroy_process_group()
-        return
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_plugin["batch"]["ms_per_call_max_over_ranks"] = float(t.item())
+        e2e_plugin["batch"]["value"] = B * world / (float(t.item()) * 1e-3)
 
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(peaks_path):
         peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     else:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+
+    # BASELINE configs 3 / 4 / 5 at full size (every rank takes part: they shard over WORLD_SIZE)
+    configs = None
+    if a.configs:
+        del flush
+        torch.cuda.empty_cache()
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import bench_configs
+        which = tuple("config" + c.strip() for c in a.configs.split(",") if c.strip())
+        configs = bench_configs.run_all(rank, world, peak, peak_src, which, parity=not a.no_parity)
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
     bytes_per_launch = 128.0 * p_in_per_launch + B * (8.0 * n * 9 + 4.0 * (2 + c) * 9)
     kern_ms = dev_ms / a.steps
     achieved = bytes_per_launch / (kern_ms * 1e-3) / 1e9
@@ -338,6 +377,10 @@ def run_b200(a):
                        "rows from and writes xi/info to mapped pinned host memory over PCIe -- the H2D/D2H bytes move "
                        "inside the kernel; stream synchronised before return)",
                 "ms_per_step_by_transfer_mode": {k: v / a.steps for k, v in e2e_modes.items()}},
+        "e2e_plugin": e2e_plugin,
+        "allgather_ms": allgather_ms,
+        "allgather": None if allgather_ms is None else "NCCL all_gather_into_tensor of %d fp64 final costs per rank, "
+                                                       "CUDA events, max over ranks; outside the timed steps" % B,
         "gpu_launches": launches,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "peak_source": peak_src, "kernel": "chomp_step_kernel<%s>" % ("topk" if a.mode == "default" else "fullsum"),
@@ -349,6 +392,10 @@ def run_b200(a):
     }
     if cpu is not None:
         line["cpu_baseline"] = cpu
+    if configs is not None:
+        line["configs"] = configs
+    if nccl_log is not None:
+        line["nccl"] = nccl_summary(nccl_log, world)
     if world == 1 and not a.no_aux:
         # the kernels either side of the CHOMP loop (goal-set IK, SDF packing, point-cloud field, trajectory
         # initialisation): reported beside the headline, never part of it
@@ -361,6 +408,90 @@ def run_b200(a):
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def nccl_summary(pattern, world):
+    """Rank 0's view of the NCCL INFO log files: communicator size and the transport lines, echoed to stderr."""
+    import glob
+    import re
+    import socket
+
+    out = {"debug_file": pattern, "nranks": None, "lines": []}
+    path = pattern.replace("%h", socket.gethostname()).replace("%p", "*")
+    for f in sorted(glob.glob(path)):
+        try:
+            for ln in open(f, errors="replace"):
+                m = re.search(r"nranks (\d+)", ln)
+                if m and out["nranks"] is None:
+                    out["nranks"] = int(m.group(1))
+                if ("nranks" in ln or "NVLS" in ln or "NCCL version" in ln) and len(out["lines"]) < 12:
+                    out["lines"].append(ln.strip()[:200])
+        except OSError:
+            pass
+    for ln in out["lines"]:
+        print("NCCL:", ln, file=sys.stderr)
+    out["comm_nranks_ok"] = (out["nranks"] == world) if out["nranks"] is not None else None
+    return out
+
+
+def run_plugin_e2e(a, scene, mode, xi0, st, en, tails, robot, steps):
+    """Optimizer.optimize(traj, force_update=True) -- the call omg/planner.py:621 makes -- through the plugin classes:
+    host numpy trajectory in, updated trajectory + info out, every call (pinned staging, H2D, fused kernel, D2H)."""
+    import types
+
+    import torch
+
+    from omg_planner_b200.config import ChompConfig
+    from omg_planner_b200.cost import Cost
+    from omg_planner_b200.optimizer import Optimizer
+
+    cfg = ChompConfig(timesteps=a.waypoints, **mode)
+    env = types.SimpleNamespace()
+    env.config = cfg
+    env.target_idx = scene["target_idx"]
+    env.objects = [types.SimpleNamespace(name=nm, pose_mat=np.array(scene["pose_mats"][i]), attached=False,
+                                         reach_grasps=[], grasps=[]) for i, nm in enumerate(scene["names"])]
+    env.sdf_torch = torch.from_numpy(scene["sdf_grids"]).cuda()
+    env.sdf_limits = torch.from_numpy(scene["sdf_limits"]).cuda()
+    rk = types.SimpleNamespace(_pose_0=robot.pose_0, _tip2joint=robot.tip2joint, _joint_axis=robot.joint_axis,
+                               _joint_origin=robot.joint_axis, center_offset=robot.center_offset)
+    env.robot = types.SimpleNamespace(robot_kinematics=rk, collision_points=robot.collision_points,
+                                      joint_lower_limit=robot.joint_lower_limit, joint_upper_limit=robot.joint_upper_limit)
+
+    class Traj(object):   # omg/core.py:23-57 carrier
+        def __init__(self, data, start, end, goal_idx):
+            self.data, self.start, self.end, self.goal_set, self.goal_idx = data, start, end, [], goal_idx
+
+        def set(self, x):
+            self.data = x
+
+    cost = Cost(env)
+    target = env.objects[env.target_idx]
+    cost.target_obj = target
+    res = {}
+    B = xi0.shape[0]
+    for name, traj in (("single", Traj(xi0[0].copy(), st[0], en[0], 0)),
+                       ("batch", Traj(xi0.copy(), st, en, np.arange(B)))):
+        if mode["goal_set_proj"]:
+            target.reach_grasps = [tails[0]] if name == "single" else tails[:, None]
+        opt = Optimizer(env, cost)
+        calls = max(steps, 20) if name == "single" else steps
+        for _ in range(3):
+            opt.optimize(traj, force_update=True)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(calls):
+            info = opt.optimize(traj, force_update=True)
+        torch.cuda.synchronize()
+        ms = (time.perf_counter() - t0) / calls * 1e3
+        nb = 1 if name == "single" else B
+        res[name] = {"trajectories": nb, "ms_per_call": ms, "value": nb / (ms * 1e-3), "unit": "trajectory-iterations/s",
+                     "calls": calls}
+    res["api"] = ("omg_planner_b200.optimizer.Optimizer.optimize(traj, force_update=True) over Cost.evaluate: numpy "
+                  "trajectory -> pinned staging -> H2D -> ONE fused launch -> D2H of xi + the [B,16] info array; "
+                  "gradient / cost_traj / per-trajectory dicts fetched lazily for a batch; host wall clock per call")
+    res["reference_call"] = "omg/planner.py:621 self.optim.optimize(traj, force_update=True) (omg/optimizer.py:115-135)"
+    return res
 
 
 def run_reference(a):
@@ -406,6 +537,10 @@ def main():
     ap.add_argument("--cpu-steps", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-aux", action="store_true")
+    ap.add_argument("--no-plugin", action="store_true", help="skip the Optimizer.optimize plugin-call timing")
+    ap.add_argument("--configs", default="4,5,3", help="BASELINE configs to run beside the config-2 headline "
+                                                       "(comma list of 3,4,5; empty string: none)")
+    ap.add_argument("--no-parity", action="store_true", help="skip the oracle-checked subsamples of the config blocks")
     a = ap.parse_args()
     if a.impl == "reference":
         run_reference(a)

@@ -36,6 +36,52 @@ def se3_inverse_f32(rt):
     return out
 
 
+class BatchInfos(object):
+    """The per-trajectory info dicts of one batched Optimizer.optimize / Cost.compute_total_loss call: a read-only
+    sequence over one [B,16] info array.  Dicts (omg/cost.py:509-530 keys) are built when indexed; the gradient
+    [B,n,9] and the per-row obstacle costs stay on the device until the first dict is built.  `.rows` is the raw
+    array (columns: omg_planner_b200._lib.INFO_KEYS), `.terminate` etc. are vectorised views for batch callers."""
+
+    def __init__(self, cost, cfg, rows, n, grad_dev, rowobs_dev, xi_before, start, end):
+        self._cost, self._cfg, self.rows, self._n = cost, cfg, rows, n
+        self._grad_dev, self._rowobs_dev, self._host = grad_dev, rowobs_dev, None
+        self._before, self._start, self._end = xi_before, start, end
+        self._cache = {}
+
+    def __len__(self):
+        return self.rows.shape[0]
+
+    @property
+    def terminate(self):
+        return self.rows[:, 8] > 0
+
+    @property
+    def cost(self):
+        return self.rows[:, 2]
+
+    def gradient(self):
+        """[B,n,9] numpy (one D2H copy, cached)."""
+        if self._host is None:
+            self._host = (self._grad_dev.cpu().numpy(), self._rowobs_dev.cpu().numpy())
+        return self._host[0]
+
+    def __getitem__(self, b):
+        if isinstance(b, slice):
+            return [self[i] for i in range(*b.indices(len(self)))]
+        if b < 0:
+            b += len(self)
+        if not 0 <= b < len(self):
+            raise IndexError(b)
+        if b not in self._cache:
+            grad = self.gradient()
+            self._cache[b] = self._cost._info_dict(self._cfg, self.rows[b], self._n, grad[b], self._host[1][b],
+                                                   self._before[b], self._start[b], self._end[b])
+        return self._cache[b]
+
+    def __iter__(self):
+        return (self[i] for i in range(len(self)))
+
+
 class Cost(object):
     def __init__(self, env):
         self.env = env
@@ -44,6 +90,7 @@ class Cost(object):
         if len(self.env.objects) > 0:
             self.target_obj = self.env.objects[self.env.target_idx]
         self.engine = ChompEngine()
+        self._stage = {}
         self._robot_sig = None
         self._sdf_sig = None
         self._obj_sig = None
@@ -68,9 +115,21 @@ class Cost(object):
             clr[-1], eps[-1], pad[-1] = 0.0, 0.05, 0.5
         return poses, eps, pad, clr, dis
 
+    def _scene_signature(self):
+        """What the per-object operator parameters depend on, as one cheap comparable value: object poses, names,
+        the target, its attached flag, and the cfg scalars of omg/cost.py:303-328.  Rebuilding and hashing the
+        parameter arrays themselves on every call (round 1) cost more than the fused kernel for one trajectory."""
+        cfg, objs = self.cfg, self.env.objects
+        t = self.env.target_idx
+        poses = np.array([ob.pose_mat for ob in objs], dtype=np.float64)
+        return (poses.tobytes(), tuple(ob.name for ob in objs), t, bool(getattr(objs[t], "attached", False)),
+                float(cfg.epsilon), float(cfg.clearance), float(cfg.target_epsilon), float(cfg.target_clearance),
+                tuple(cfg.disable_collision_set))
+
     def sync(self):
         robot = self.env.robot
-        sig = (np.asarray(robot.collision_points, dtype=np.float64).tobytes(),
+        pts = robot.collision_points
+        sig = (id(pts), np.asarray(pts, dtype=np.float64).tobytes(),
                np.asarray(robot.joint_lower_limit).tobytes(), np.asarray(robot.joint_upper_limit).tobytes())
         if sig != self._robot_sig:
             self.engine.set_robot(_RobotView(robot), use_true_joint_origin=True)
@@ -80,10 +139,9 @@ class Cost(object):
         if ssig != self._sdf_sig:
             self.engine.set_sdf(grids, self.env.sdf_limits)
             self._sdf_sig, self._obj_sig = ssig, None
-        params = self.object_params()
-        osig = b"".join(p.tobytes() for p in params)
+        osig = self._scene_signature()
         if osig != self._obj_sig:
-            self.engine.set_objects(*params)
+            self.engine.set_objects(*self.object_params())
             self._obj_sig = osig
 
     # ---- reference API ----------------------------------------------------------------------------------
@@ -106,16 +164,28 @@ class Cost(object):
         normal = np.matmul(r, normals[None, ...])
         return np.concatenate([x, normal], 2).transpose([3, 1, 0, 2])
 
-    def _traj_tensors(self, traj):
+    def _staged(self, key, arr):
+        """numpy fp64 -> device through a cached pinned staging buffer (async H2D on the current stream; the buffer
+        is reused by the next call, which is ordered behind this copy on the same stream)."""
         dev = self.engine.device
+        arr = np.asarray(arr, dtype=np.float64)
+        slot = self._stage.get(key)
+        if slot is None or slot[0].shape != arr.shape:
+            slot = (torch.empty(arr.shape, dtype=torch.float64).pin_memory(),
+                    torch.empty(arr.shape, dtype=torch.float64, device=dev))
+            self._stage[key] = slot
+        np.copyto(slot[0].numpy(), arr)
+        slot[1].copy_(slot[0], non_blocking=True)
+        return slot[1]
+
+    def _traj_tensors(self, traj):
         data = np.asarray(traj.data, dtype=np.float64)
         batched = data.ndim == 3
-        xi = torch.from_numpy(np.ascontiguousarray(data if batched else data[None])).to(dev)
+        xi = self._staged("xi", data if batched else data[None])
         B = xi.shape[0]
-        bc = lambda a: torch.from_numpy(np.array(
-            np.broadcast_to(np.asarray(a, dtype=np.float64).reshape((-1, 9))[-B:] if np.ndim(a) > 1
-                            else np.asarray(a, dtype=np.float64)[None], (B, 9)))).to(dev)
-        start, end = bc(traj.start), bc(traj.end)
+        bc = lambda a: np.broadcast_to(np.asarray(a, dtype=np.float64).reshape((-1, 9))[-B:] if np.ndim(a) > 1
+                                       else np.asarray(a, dtype=np.float64)[None], (B, 9))
+        start, end = self._staged("start", bc(traj.start)), self._staged("end", bc(traj.end))
         rows = None
         if self.cfg.goal_set_proj:
             c = self.engine_cfg().constraint_rows
@@ -126,7 +196,7 @@ class Cost(object):
             else:
                 gs = np.asarray(traj.goal_set)
                 goal = (gs[np.arange(B), idx] if gs.ndim == 3 else gs[idx])[:, None]
-            rows = torch.from_numpy(np.array(np.broadcast_to(goal, (B, c, 9)), dtype=np.float64)).to(dev)
+            rows = self._staged("rows", np.broadcast_to(goal, (B, c, 9)))
         return xi, start, end, rows, batched
 
     def engine_cfg(self):
@@ -150,27 +220,19 @@ class Cost(object):
             return v
         return cfg
 
-    def _info_dicts(self, cfg, out, xi_before, update_mode):
-        info_t = out["info"].cpu().numpy()
-        grad = out["grad"].cpu().numpy()
-        rows = out["row_obs"].cpu().numpy()
-        infos = []
-        n = xi_before.shape[1]
-        for b in range(info_t.shape[0]):
-            r = info_t[b]
-            smooth_rows = self._smooth_rows(cfg, xi_before[b], self._last_start[b], self._last_end[b])
-            info = {
-                "collision_pts": None, "obs": r[0], "smooth": r[1], "grasp": 0, "weighted_obs": cfg.obstacle_weight * r[0],
-                "weighted_smooth": cfg.smoothness_weight * r[1], "weighted_smooth_grad": r[7], "weighted_obs_grad": r[6],
-                "weighted_grasp_grad": 0, "weighted_grasp": 0, "gradient": grad[b], "failure_terminate": bool(r[11]),
-                "cost": r[2], "grad": r[5], "terminate": bool(r[8]), "collide": r[3],
-                "standoff_idx": n - cfg.reach_tail_length if cfg.use_standoff else n - 1, "reach": r[4],
-                "execute": bool(r[10]), "violate_limit": bool(r[9]),
-                "cost_traj": cfg.obstacle_weight * rows[b] + cfg.smoothness_weight * smooth_rows[:-1],
-                "p_in": r[12],
-            }
-            infos.append(info)
-        return infos
+    def _info_dict(self, cfg, r, n, grad, rows, xi_before, start, end):
+        """One info dict (omg/cost.py:509-530) from one omgb info row."""
+        smooth_rows = self._smooth_rows(cfg, xi_before, start, end)
+        return {
+            "collision_pts": None, "obs": r[0], "smooth": r[1], "grasp": 0, "weighted_obs": cfg.obstacle_weight * r[0],
+            "weighted_smooth": cfg.smoothness_weight * r[1], "weighted_smooth_grad": r[7], "weighted_obs_grad": r[6],
+            "weighted_grasp_grad": 0, "weighted_grasp": 0, "gradient": grad, "failure_terminate": bool(r[11]),
+            "cost": r[2], "grad": r[5], "terminate": bool(r[8]), "collide": r[3],
+            "standoff_idx": n - cfg.reach_tail_length if cfg.use_standoff else n - 1, "reach": r[4],
+            "execute": bool(r[10]), "violate_limit": bool(r[9]),
+            "cost_traj": cfg.obstacle_weight * rows + cfg.smoothness_weight * smooth_rows[:-1],
+            "p_in": r[12], "text": [],
+        }
 
     @staticmethod
     def _smooth_rows(cfg, xi, start, end):
@@ -183,19 +245,34 @@ class Cost(object):
         return 0.5 * np.linalg.norm(vel * w, axis=1) ** 2
 
     def evaluate(self, traj, update_mode=0):
-        """One fused iteration; update_mode as omgb_step_params_t.update.  Returns (infos, new_xi, batched)."""
+        """One fused iteration; update_mode as omgb_step_params_t.update.  Returns (infos, new_xi, batched).
+        One trajectory (the reference's shape): a plain info dict, everything on the host when the call returns.
+        A batch: `infos` is a BatchInfos -- one [B,16] info array copied back with xi; the per-trajectory dicts, the
+        gradient [B,n,9] and cost_traj are fetched from the device only if somebody looks at them."""
         self.sync()
         cfg = self.engine_cfg()
         xi, start, end, rows, batched = self._traj_tensors(traj)
-        before = xi.cpu().numpy()
-        self._last_start, self._last_end = start.cpu().numpy(), end.cpu().numpy()
         want_dbg = bool(getattr(self.cfg, "vis", False))
+        before = np.array(traj.data, dtype=np.float64, copy=True)
+        before = before if batched else before[None]
         out = self.engine.step(cfg, xi, start, end, rows, update=update_mode, want_grad=True, debug=want_dbg,
                                want_row_obs=True)
-        infos = self._info_dicts(cfg, out, before, update_mode)
+        B, n = xi.shape[0], xi.shape[1]
+        host = self._stage.get(("host", B, n))
+        if host is None:
+            host = (torch.empty((B, n, 9), dtype=torch.float64).pin_memory(),
+                    torch.empty((B, out["info"].shape[1]), dtype=torch.float64).pin_memory())
+            self._stage[("host", B, n)] = host
+        host[0].copy_(xi, non_blocking=True)
+        host[1].copy_(out["info"], non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        new_xi, info_rows = host[0].numpy().copy(), host[1].numpy().copy()
+        st_h, en_h = self._stage["start"][0].numpy().copy(), self._stage["end"][0].numpy().copy()
+        self._last_start, self._last_end = st_h, en_h
+        infos = BatchInfos(self, cfg, info_rows, n, out["grad"].clone(), out["row_obs"].clone(), before, st_h, en_h)
         if want_dbg:
             self._fill_collision_pts(infos, out)
-        return infos, xi.cpu().numpy(), batched
+        return (infos if batched else [infos[0]]), new_xi, batched
 
     def _fill_collision_pts(self, infos, out):
         """info['collision_pts'] [n,10,p,12] (omg/cost.py:355-358): xyz, potential, potential gradient."""
@@ -214,7 +291,7 @@ class Cost(object):
         """(cost, grad, info) like omg/cost.py:451-532 (no update)."""
         infos, _, batched = self.evaluate(traj, update_mode=0)
         if batched:
-            return (np.array([i["cost"] for i in infos]), np.stack([i["gradient"] for i in infos]), infos)
+            return (np.array(infos.cost), infos.gradient(), infos)
         return infos[0]["cost"], infos[0]["gradient"], infos[0]
 
     def compute_obstacle_cost_layer(self, ws_positions, vis_pts=None, special_check_id=0,

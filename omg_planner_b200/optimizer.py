@@ -47,8 +47,9 @@ class Optimizer(object):
         self.update()
         mode = 0 if info_only else (1 if force_update else 2)
         infos, new_xi, batched = self.cost.evaluate(traj, update_mode=mode)
-        for info in infos:
-            info["text"] = self.report(traj.data, info)
+        if not batched or getattr(self.cfg, "report_cost", False):   # (a batch keeps its dicts lazy: Cost.BatchInfos)
+            for info in infos:
+                info["text"] = self.report(traj.data, info)
         if mode != 0:
             # Trajectory.update mutates in place, Trajectory.set replaces (omg/core.py:43-57): the net effect of
             # optimize() is a replaced .data

@@ -157,9 +157,11 @@ class Planner(GoalSetMixin):
         if cfg.scene_file == "" or cfg.traj_init == "grasp":
             if len(env.objects) > 0:
                 target = env.objects[env.target_idx]
-                if len(target.grasps) > 0:
-                    traj.goal_set = target.grasps
-                    traj.goal_potentials = getattr(target, "grasp_potentials", [])
+                # unconditional, as the reference (planner.py:192-194): a target whose IK / collision filter left no
+                # goals must leave an EMPTY goal set (plan() then returns "planning not run"), not the previous
+                # target's goals -- PlanningScene reuses one Trajectory across update_planner()/reset()
+                traj.goal_set = target.grasps
+                traj.goal_potentials = getattr(target, "grasp_potentials", [])
                 if cfg.goal_set_proj and cfg.use_standoff and len(target.reach_grasps) > 0:
                     traj.goal_set = np.asarray(target.reach_grasps)[..., -1, :]
         if len(traj.goal_set) == 0:
@@ -314,7 +316,8 @@ class Planner(GoalSetMixin):
             info = self.optim.optimize(traj, force_update=True)
             infos.append(info)
             hist.append(np.copy(traj.data))
-            term = np.array([i["terminate"] for i in (info if batched else [info])])
+            term = (np.asarray(info.terminate) if hasattr(info, "terminate")
+                    else np.array([i["terminate"] for i in (info if batched else [info])]))
             if t > 0:
                 stop[(stop < 0) & term] = t
             if (stop >= 0).all():

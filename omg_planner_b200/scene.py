@@ -52,15 +52,47 @@ def _sample_grid(kind, params, dims, delta, origin):
     return out
 
 
+def _sample_grid_torch(kind, params, dims, delta, origin, device):
+    """_sample_grid on a CUDA device (torch, fp64, the same IEEE operations in the same order; elementwise torch
+    kernels do not fuse multiply-adds) -> fp32 torch tensor [X,Y,Z].  256^3 grids take milliseconds instead of
+    seconds of numpy; tests/test_gpu_fullsize.py checks it is bit-identical to the numpy generator."""
+    import torch
+
+    X, Y, Z = dims
+    f64 = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64)).to(device)
+    ys = f64((np.arange(Y) + 0.5) * delta + origin[1])[None, :, None]
+    zs = f64((np.arange(Z) + 0.5) * delta + origin[2])[None, None, :]
+    out = torch.empty((X, Y, Z), dtype=torch.float32, device=device)
+    step = max(1, (1 << 24) // (Y * Z))
+    for x0 in range(0, X, step):
+        xs = f64((np.arange(x0, min(X, x0 + step)) + 0.5) * delta + origin[0])[:, None, None]
+        shape = (xs.shape[0], Y, Z)
+        px, py, pz = xs.expand(shape), ys.expand(shape), zs.expand(shape)
+        if kind == "sphere":
+            v = torch.sqrt(px * px + py * py + pz * pz) - params[0]
+        elif kind == "box":
+            qx, qy, qz = px.abs() - float(params[0]), py.abs() - float(params[1]), pz.abs() - float(params[2])
+            cx, cy, cz = qx.clamp_min(0.0), qy.clamp_min(0.0), qz.clamp_min(0.0)
+            outside = torch.sqrt(cx * cx + cy * cy + cz * cz)
+            v = outside + torch.maximum(torch.maximum(qx, qy), qz).clamp_max(0.0)
+        else:
+            dz = pz - pz.clamp(-params[1], params[1])
+            v = torch.sqrt(px * px + py * py + dz * dz) - params[0]
+        out[x0:x0 + xs.shape[0]] = v.to(torch.float32)
+    return out
+
+
 def _yaw(a):
     c, s = np.cos(a), np.sin(a)
     return np.array([[c, -s, 0], [s, c, 0], [0, 0, 1.0]])
 
 
-def make_scene(num_objects=10, grid=128, seed=0, table=True, grid_choices=None):
+def make_scene(num_objects=10, grid=128, seed=0, table=True, grid_choices=None, device=None):
     """One table-top scene.  Object 0 is the grasp target; the last object is the table.
     grid_choices: optional list of per-object cubic grid sizes to draw from (mixed sizes exercise the
-    pad-to-max path of combine_sdfs); default: every object is grid^3."""
+    pad-to-max path of combine_sdfs); default: every object is grid^3.
+    device: a CUDA device -> the fields are sampled there and "sdf_grids" is a torch tensor on it (same values)."""
+    sample = _sample_grid if device is None else (lambda *a: _sample_grid_torch(*a, device))
     rng = np.random.RandomState(1000 + seed)
     names, poses, grids, origins, deltas, dims = [], [], [], [], [], []
     n_free = num_objects - (1 if table else 0)
@@ -82,7 +114,7 @@ def make_scene(num_objects=10, grid=128, seed=0, table=True, grid_choices=None):
         pose[:3, :3] = _yaw(rng.uniform(-np.pi, np.pi))
         pose[:3, 3] = [rng.uniform(0.3, 0.8), rng.uniform(-0.4, 0.4), rng.uniform(0.0, 0.5)]
         names.append("%03d_%s" % (o, kind)); poses.append(pose)
-        grids.append(_sample_grid(kind, params, (g, g, g), delta, origin))
+        grids.append(sample(kind, params, (g, g, g), delta, origin))
         origins.append(origin); deltas.append(delta); dims.append((g, g, g))
     if table:
         # bullet/panda_scene.py:582: table at (0.55, 0, -0.17), model y-up (quat 0.707,0.707,0,0 = Rx(90deg))
@@ -94,7 +126,7 @@ def make_scene(num_objects=10, grid=128, seed=0, table=True, grid_choices=None):
         pose[:3, :3] = np.array([[1, 0, 0], [0, 0, -1], [0, 1, 0.0]])
         pose[:3, 3] = [0.55, 0.0, -0.17]
         names.append("table"); poses.append(pose)
-        grids.append(_sample_grid("box", tuple(half), (g, g, g), delta, origin))
+        grids.append(sample("box", tuple(half), (g, g, g), delta, origin))
         origins.append(origin); deltas.append(delta); dims.append((g, g, g))
     return pack_scene(names, poses, grids, origins, deltas, target_idx=0)
 
@@ -102,12 +134,16 @@ def make_scene(num_objects=10, grid=128, seed=0, table=True, grid_choices=None):
 def pack_scene(names, poses, grids, origins, deltas, target_idx=0):
     """Same packing as omg/core.py:366-411: pad to the max shape with 1.0, stretch max' accordingly."""
     num = len(names)
-    shapes = np.array([g.shape for g in grids])
+    shapes = np.array([tuple(g.shape) for g in grids])
     mx = shapes.max(0)
-    sdf = np.ones((num, mx[0], mx[1], mx[2]), np.float32)
+    if isinstance(grids[0], np.ndarray):
+        sdf = np.ones((num, mx[0], mx[1], mx[2]), np.float32)
+    else:
+        import torch
+        sdf = torch.ones((num, int(mx[0]), int(mx[1]), int(mx[2])), dtype=torch.float32, device=grids[0].device)
     lim = np.zeros((num, 10), np.float32)
     for i in range(num):
-        s = grids[i].shape
+        s = tuple(grids[i].shape)
         sdf[i, :s[0], :s[1], :s[2]] = grids[i]
         mn = np.asarray(origins[i], dtype=np.float64)
         mxc = mn + deltas[i] * np.array(s)

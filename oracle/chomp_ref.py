@@ -399,7 +399,10 @@ class ChompRef(object):
         cfg, robot = self.cfg, self.robot
         self.schedule()
         goal = self.goal if cfg.goal_set_proj else None
+        pin0 = self.stats.get("p_in", 0)
         cost, grad, info = total_cost(robot, self.scene, cfg, self.xi, self.start, self.end, goal, self.stats)
+        # in-bounds (body point, enabled object) pairs of this iteration -- the numerator of the roofline
+        info["p_in"] = self.stats.get("p_in", 0) - pin0
         low = (self.xi < robot.lower - 5e-3).any()          # omg/optimizer.py:166-174 (sic)
         high = self.xi > robot.upper + 5e-3
         info["violate_limit"] = bool((low * high).any())

@@ -82,3 +82,25 @@ def test_dynamic_timesteps_and_initial_goal_choice():
         p.grasp_init(env)
         assert traj.goal_idx == want
         np.testing.assert_array_equal(traj.end, goals[want])
+
+
+def test_target_without_grasps_leaves_an_empty_goal_set_and_plan_does_not_run():
+    """omg/planner.py:192-197 assigns traj.goal_set = target.grasps unconditionally: after a target switch whose IK /
+    collision filter yields no goals, the (reused) Trajectory must not keep the previous target's goals, and plan()
+    returns the empty info list ("planning not run", planner.py:650-652)."""
+    goals = np.stack([np.full(9, v) for v in (1.0, 0.2, 0.5)])
+    cfg = ChompConfig(goal_set_proj=True, use_standoff=True, goal_idx=0)
+    with_goals = types.SimpleNamespace(grasps=goals, reach_grasps=[], grasp_potentials=[0.0, 0.0, 0.0])
+    without = types.SimpleNamespace(grasps=[], reach_grasps=[], grasp_potentials=[])
+    env = types.SimpleNamespace(objects=[with_goals, without], target_idx=0, config=cfg)
+    calls = []
+    traj = types.SimpleNamespace(start=np.zeros(9), goal_set=[], end=np.zeros(9), data=np.zeros((30, 9)),
+                                 interpolate_waypoints=lambda: calls.append(1))
+    p = _planner(cfg)
+    p.env, p.traj = env, traj
+    p.grasp_init(env)
+    assert len(traj.goal_set) == 3 and traj.goal_idx == 0 and len(calls) == 1
+    env.target_idx = 1                       # PlanningScene.update_planner() with a new target, same Trajectory
+    p.grasp_init(env)
+    assert len(traj.goal_set) == 0 and len(traj.goal_potentials) == 0 and len(calls) == 1
+    assert p.plan(traj) == []                # no device work is attempted

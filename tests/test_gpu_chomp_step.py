@@ -91,6 +91,9 @@ def test_single_iteration_vs_oracle_denser_scene(name):
                 slack = ref_infos[b][it]["tie_slack"] * (1 + 1e-9) if key in ("obs", "cost") else 0.0
                 assert abs(infos[b, it, INFO_COLS[key]] - ref) <= 1e-6 * max(1.0, abs(ref)) + slack, (key, b, it)
             assert bool(infos[b, it, 8]) == ref_infos[b][it]["terminate"]
+            # P_in -- the numerator of the roofline's algorithmic bytes -- is the oracle's count of
+            # in-bounds (body point, enabled object) pairs, exactly (pairs the cull proves far are still counted)
+            assert int(infos[b, it, 12]) == int(ref_infos[b][it]["p_in"]), (b, it)
     assert infos[:, 0, 12].sum() > 0
 
 
