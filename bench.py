@@ -471,7 +471,7 @@ def run_plugin_e2e(a, scene, mode, xi0, st, en, tails, robot, steps):
     res = {}
     B = xi0.shape[0]
     for name, traj in (("single", Traj(xi0[0].copy(), st[0], en[0], 0)),
-                       ("batch", Traj(xi0.copy(), st, en, np.arange(B)))):
+                       ("batch", Traj(xi0.copy(), st, en, np.zeros(B, dtype=int)))):
         if mode["goal_set_proj"]:
             target.reach_grasps = [tails[0]] if name == "single" else tails[:, None]
         opt = Optimizer(env, cost)

@@ -37,21 +37,7 @@ def test_device_scene_generator_equals_numpy():
         np.testing.assert_array_equal(a["sdf_limits"], b["sdf_limits"])
 
 
-def _per_iteration_oracle(b):
-    from oracle import chomp_ref as R
-    sc, mode, n, xi, st, en, rows, iters = BC._PAR["trace_args"]
-    opt = R.ChompRef(R.PandaRef(), sc, R.RefConfig(timesteps=n, **mode), xi[b], st[b], en[b], rows[b])
-    out, pin = [], []
-    for _ in range(iters):
-        info = opt.step()
-        out.append(opt.xi.copy())
-        pin.append(info["p_in"])
-    return b, np.stack(out), pin
-
-
 def test_config4_true_shape_1_10_70_iterations():
-    import multiprocessing as mp
-
     n, objects, grid, Sn, iters = 60, 20, 256, 16, 70
     dev = torch.device("cuda", torch.cuda.current_device())
     sc = S.make_scene(num_objects=objects, grid=grid, seed=4, device=dev)
@@ -65,10 +51,7 @@ def test_config4_true_shape_1_10_70_iterations():
     out = eng.plan(cfg, x, to(st), to(en), to(tails), iters=iters, history=True)
     hist = out["hist_xi"].cpu().numpy()          # [iters, S, n, 9]
     pin_dev = out["hist_info"][:, :, 12].cpu().numpy()
-    BC._PAR["trace_args"] = (BC._host_scene(sc), BC.DEFAULT_MODE, n, xi0, st, en, tails, iters)
-    workers = max(1, min(Sn, len(os.sched_getaffinity(0))))
-    with mp.get_context("fork").Pool(workers) as pool:
-        res = pool.map(_per_iteration_oracle, range(Sn))
+    res, _ = BC._pool_map(BC._oracle_trace_worker, Sn, (BC._host_scene(sc), BC.DEFAULT_MODE, n, xi0, st, en, tails, iters))
     err = np.zeros((Sn, iters))
     for b, ref, pin in res:
         err[b] = np.abs(hist[:, b] - ref)[..., :7].max(axis=(1, 2))

@@ -73,6 +73,37 @@ def _host_scene(sc):
 _PAR = {}
 
 
+def _pool_init(d):
+    """spawned worker: arguments from a pickle, the (possibly 1.34 GB) SDF tensor memory-mapped from a .npy file"""
+    import pickle
+    with open(os.path.join(d, "args.pkl"), "rb") as f:
+        sc, rest = pickle.load(f)
+    sc["sdf_grids"] = np.load(os.path.join(d, "grid.npy"), mmap_mode="r")
+    _PAR["args"] = (sc,) + tuple(rest)
+
+
+def _pool_map(fn, count, args):
+    """Run the CPU oracle for `count` trajectories on the host cores.  The workers are SPAWNED (this process holds a
+    CUDA context and NCCL threads; they only ever run numpy + the C operator) and get args[0], the scene, through a
+    temporary directory: the big grid as a memory-mapped file shared by all of them."""
+    import pickle
+    import shutil
+    import tempfile
+
+    workers = max(1, min(count, (len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else 4)))
+    d = tempfile.mkdtemp(prefix="omgb_oracle_")
+    try:
+        sc = dict(args[0])
+        np.save(os.path.join(d, "grid.npy"), np.ascontiguousarray(sc.pop("sdf_grids"), dtype=np.float32))
+        with open(os.path.join(d, "args.pkl"), "wb") as f:
+            pickle.dump((sc, tuple(args[1:])), f)
+        with mp.get_context("spawn").Pool(workers, initializer=_pool_init, initargs=(d,)) as pool:
+            res = pool.map(fn, range(count))
+    finally:
+        shutil.rmtree(d, ignore_errors=True)
+    return res, workers
+
+
 def _oracle_steps_worker(b):
     from oracle import chomp_ref as R
     sc, mode, n, xi, st, en, rows, checkpoints = _PAR["args"]
@@ -87,15 +118,25 @@ def _oracle_steps_worker(b):
     return b, np.stack(out), p_in
 
 
+def _oracle_trace_worker(b):
+    """xi after EVERY iteration (tests/test_gpu_configs_fullsize.py)."""
+    from oracle import chomp_ref as R
+    sc, mode, n, xi, st, en, rows, iters = _PAR["args"]
+    opt = R.ChompRef(R.PandaRef(), sc, R.RefConfig(timesteps=n, **mode), xi[b], st[b], en[b], rows[b])
+    out, pin = [], []
+    for _ in range(iters):
+        info = opt.step()
+        out.append(opt.xi.copy())
+        pin.append(info["p_in"])
+    return b, np.stack(out), pin
+
+
 def _oracle_parity_steps(sc_host, mode, n, xi, st, en, rows, dev_states, checkpoints=(1, 10)):
-    """dev_states[k]: device xi [S,n,9] after checkpoints[k] iterations from the same state.  Oracle per trajectory in
-    a fork pool (the children only run numpy + the C operator; the 1.34 GB grid is shared copy-on-write)."""
+    """dev_states[k]: device xi [S,n,9] after checkpoints[k] iterations from the same state."""
     S = xi.shape[0]
-    _PAR["args"] = (sc_host, mode, n, xi, st, en, rows, tuple(checkpoints))
-    workers = max(1, min(S, (len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else 4)))
     t0 = time.perf_counter()
-    with mp.get_context("fork").Pool(workers) as pool:
-        res = dict((b, h) for b, h, _ in pool.map(_oracle_steps_worker, range(S)))
+    out, workers = _pool_map(_oracle_steps_worker, S, (sc_host, mode, n, xi, st, en, rows, tuple(checkpoints)))
+    res = dict((b, h) for b, h, _ in out)
     err = np.zeros((len(checkpoints), S))
     for b in range(S):
         for k in range(len(checkpoints)):
@@ -290,7 +331,7 @@ def _oracle_plan_worker(b):
     from oracle import learner_ref as LR
     from oracle import planner_ref as P
 
-    sc, cfg_kw, n, xi0, g0, goals, reach = _PAR["plan_args"]
+    sc, cfg_kw, n, xi0, g0, goals, reach = _PAR["args"]
     cfg = R.RefConfig(timesteps=n, top_k_collision=1000, **cfg_kw)
     G = goals.shape[1]
     learner = LR.LearnerRef(cfg, G)
@@ -304,11 +345,8 @@ def _oracle_plan_worker(b):
 
 def _oracle_parity_plan(sc_host, cfg_kw, n, xi0, g0, goals, reach, dev_hist, dev_sel):
     S = xi0.shape[0]
-    _PAR["plan_args"] = (sc_host, cfg_kw, n, xi0, g0, goals, reach)
-    workers = max(1, min(S, (len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else 4)))
     t0 = time.perf_counter()
-    with mp.get_context("fork").Pool(workers) as pool:
-        res = pool.map(_oracle_plan_worker, range(S))
+    res, workers = _pool_map(_oracle_plan_worker, S, (sc_host, cfg_kw, n, xi0, g0, goals, reach))
     err, same = np.zeros(S), 0
     for b, hist, sel in res:
         m = min(len(hist), len(dev_hist[b]))
