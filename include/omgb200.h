@@ -124,9 +124,10 @@ int omgb_scene_set_robot(omgb_scene_t *scene, const double *pose_0, const double
                          const double *lower, const double *upper);
 
 /* Packed SDFs exactly as Env.combine_sdfs leaves them: d_sdf_grids DEVICE [O,X,Y,Z] fp32 (borrowed, not
- * copied: zero-copy on env.sdf_torch), h_sdf_limits HOST [O,10] fp32. */
+ * copied: zero-copy on env.sdf_torch), h_sdf_limits HOST [O,10] fp32.  The grid preprocessing (lower-bound grid)
+ * runs on `stream` -- the stream the grid was produced on -- and only that stream is waited for. */
 int omgb_scene_set_sdf(omgb_scene_t *scene, const float *d_sdf_grids, const float *h_sdf_limits,
-                       int num_objects, int dim_x, int dim_y, int dim_z);
+                       int num_objects, int dim_x, int dim_y, int dim_z, void *stream);
 
 /* Per-object parameters built by Cost.compute_obstacle_cost_layer (omg/cost.py:303-335), HOST arrays:
  * pose_inv [O,4,4] fp32 (world->object), epsilons, padding_scales, clearances, disables [O] fp32. */

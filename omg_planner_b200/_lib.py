@@ -109,7 +109,7 @@ def lib():
     L.omgb_scene_create.argtypes = [ctypes.POINTER(vp), ci]
     L.omgb_scene_destroy.argtypes = [vp]
     L.omgb_scene_set_robot.argtypes = [vp, vp, vp, vp, vp, ci, vp, vp, ci, vp, vp]
-    L.omgb_scene_set_sdf.argtypes = [vp, vp, vp, ci, ci, ci, ci]
+    L.omgb_scene_set_sdf.argtypes = [vp, vp, vp, ci, ci, ci, ci, vp]
     L.omgb_scene_set_profile.argtypes = [vp, vp]
     L.omgb_scene_set_options.argtypes = [vp, ci, ci]
     L.omgb_scene_set_host_mode.argtypes = [vp, ci]

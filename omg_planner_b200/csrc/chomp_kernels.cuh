@@ -52,43 +52,54 @@ struct DilDesc {
 };
 
 struct SmemLayout {
-    unsigned off_xi, off_start, off_end, off_goal, off_frames, off_lg, off_grad, off_u, off_viol, off_red, off_pts,
-        off_mask, off_best, off_bestp, off_act, off_win, off_objs, off_hist, total;
+    unsigned off_xi, off_start, off_end, off_goal, off_frames, off_lg, off_grad, off_u, off_viol, off_red,
+        off_mask, off_mask_hi, off_best, off_bestp, off_act, off_win, off_objs, off_hist, total;
+    int nlu;        // links that own gradient rows: 8 in top-k mode without consider_finger (cost.py:401-402), else 10
+    int red_max;    // index of the block-argmax slot inside the reduction scratch
+    int mask_hi;    // 1: more than 32 objects, the object masks are two 32-bit words
 };
 
 __host__ __device__ inline unsigned align_up(unsigned v, unsigned a) { return (v + a - 1) / a * a; }
 
-__host__ __device__ inline SmemLayout make_layout(int n, int c, int lpi, int nobj, int p) {
+// Shared memory of one CTA (one trajectory).  Sized so that a 30-waypoint trajectory fits four times and a
+// 60-waypoint one twice into an SM's 228 KB: the per-point potentials of the top-k path live in a global scratch
+// (written and read once by the same CTA, L2-resident), link gradients only for the links that can own a winner,
+// 32-bit object masks unless there are more than 32 objects, byte / short indices.
+__host__ __device__ inline SmemLayout make_layout(int n, int c, int lpi, int nobj, int p, int nwarps, bool topk,
+                                                  bool consider_finger) {
     SmemLayout L;
     unsigned o = 0;
+    L.nlu = (topk && !consider_finger) ? NL - 2 : NL;
+    L.mask_hi = nobj > 32 ? 1 : 0;
     L.off_xi = o; o += sizeof(double) * n * ND;
     L.off_start = o; o += sizeof(double) * ND;
     L.off_end = o; o += sizeof(double) * ND;
     L.off_goal = o; o += sizeof(double) * (c > 0 ? c : 1) * ND;
     L.off_frames = o; o += sizeof(double) * (n + 2) * NL * 12;
-    // link gradients [n*10][8] fp64; aliased with (a) the sin/cos table of the FK phase and (b) the fp32
-    // potential array [n*10][lpi] of the top-k path
-    unsigned lg = sizeof(double) * n * NL * NS, pot = sizeof(float) * n * NL * lpi, sc = sizeof(double2) * (n + 2) * 7;
-    unsigned u = lg > pot ? lg : pot;
-    u = u > sc ? u : sc;
+    // link gradients [n*nlu][8] fp64; aliased with the sin/cos table of the FK phase
+    unsigned lg = sizeof(double) * n * L.nlu * NS, sc = sizeof(double2) * (n + 2) * 7;
+    unsigned u = lg > sc ? lg : sc;
     o = align_up(o, 16);   // double2 sin/cos table
     L.off_lg = o; o += align_up(u, 16);
-    // grad / u / viol live in the frames region: the link frames are dead once the obstacle gradient is assembled
+    // grad / u / viol (+ the scan scratch of metric_apply) live in the frames region: the link frames are dead once
+    // the obstacle gradient is assembled; 5 * n * 9 doubles <= (n + 2) * 120
     L.off_grad = L.off_frames;
     L.off_u = L.off_grad + sizeof(double) * n * ND;
     L.off_viol = L.off_u + sizeof(double) * n * ND;
-    L.off_red = o; o += sizeof(double) * (33 * 8);
-    L.off_pts = o;   // (body points are read from global memory)
-    L.off_mask = o; o += sizeof(unsigned long long) * n * NL;
+    // reduction scratch: (nwarps + 1) x 8 partial sums, then the argmax slot; never less than the 16-double info row
+    L.red_max = (nwarps + 1) * 8;
+    L.off_red = o; o += sizeof(double) * (L.red_max + 8 < 24 ? 24 : L.red_max + 8);
+    L.off_mask = o; o += sizeof(unsigned) * n * NL;
+    L.off_mask_hi = o; o += L.mask_hi ? sizeof(unsigned) * n * NL : 0;
     L.off_best = o; o += sizeof(float) * n * NL;
-    L.off_bestp = o; o += sizeof(int) * n * NL;
-    L.off_act = o; o += sizeof(int) * (n * NL + 40);
-    L.off_win = o; o += sizeof(unsigned short) * (n * NL + 8);
+    L.off_act = o; o += align_up(sizeof(unsigned short) * (n * NL + 40), 4);
+    L.off_win = o; o += align_up(sizeof(unsigned short) * (n * NL + 8), 4);
+    L.off_bestp = o; o += align_up(n * NL, 16);
     o = align_up(o, 16);
     L.off_objs = o; o += sizeof(ObjRec) * nobj;
     L.off_hist = o; o += sizeof(int) * 264;
     L.total = align_up(o, 16);
-    (void)p;
+    (void)p; (void)lpi;
     return L;
 }
 
@@ -123,6 +134,8 @@ struct StepArgs {
     long long *prof;         // [B,16] or null: clock64() at phase boundaries (diagnostic)
     double *hist_xi;         // [iters,B,n,9] or null: xi after every iteration (Planner.history_trajectories[1:])
     double *hist_info;       // [iters,B,16] or null: the info row of every iteration (Planner.info)
+    float *pot_scratch;      // [B,n*10,LPI] fp32: per-point potentials of the top-k path (global, written and read by
+                             // the trajectory's own CTA within one iteration)
     DilDesc dil;
     SmemLayout lay;          // computed on the host (make_layout)
     RobotParams rp;
@@ -144,7 +157,7 @@ __device__ __forceinline__ double warp_sum(double v) {
     return v;
 }
 
-// Block-wide sum of K values at once; every thread gets the results.  scratch: >= 32*K + K doubles.
+// Block-wide sum of K values at once; every thread gets the results.  scratch: >= (warps + 1) * K doubles.
 template <int K>
 __device__ __forceinline__ void block_sum_n(double (&v)[K], double *scratch) {
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
@@ -159,11 +172,11 @@ __device__ __forceinline__ void block_sum_n(double (&v)[K], double *scratch) {
     if (threadIdx.x < K) {
         double t = 0.0;
         for (int q = 0; q < nw; ++q) t += scratch[q * K + threadIdx.x];
-        scratch[32 * K + threadIdx.x] = t;
+        scratch[nw * K + threadIdx.x] = t;
     }
     __syncthreads();
 #pragma unroll
-    for (int k = 0; k < K; ++k) v[k] = scratch[32 * K + k];
+    for (int k = 0; k < K; ++k) v[k] = scratch[nw * K + k];
 }
 
 __device__ __forceinline__ void xform(const double *F, double px, double py, double pz, double &x, double &y,
@@ -386,15 +399,15 @@ __device__ __forceinline__ int classify_pair(const ObjRec &ob, const DilDesc &dd
 struct WinCtx {
     const RobotConst *rc;
     const double *frames;
-    const unsigned long long *mask;
-    const int *bestp;
+    const unsigned *mask_lo, *mask_hi;   // (mask_hi null: at most 32 objects)
+    const unsigned char *bestp;
     const unsigned short *win;
     const ObjRec *objs;
     const float *grids;
     const DilDesc *dil;
     double *lg;
     double inv_dt;
-    int n, n_win;
+    int n, n_win, nlu;
     bool finger_soft, use_dil;
 };
 
@@ -421,10 +434,9 @@ __device__ __forceinline__ void winners_pass(const WinCtx &c) {
         xform(Fn, b0, b1, b2, xn, yn, zn);
         const float x = (float)X, y = (float)Y, z = (float)Z;
         float pot = 0.0f, gx = 0.0f, gy = 0.0f, gz = 0.0f;
-        const unsigned long long m64 = c.mask[li];
 #pragma unroll 1
-        for (int half = 0; half < 2; ++half) {   // 64-bit object mask walked as two 32-bit words (cheaper bit ops)
-            unsigned m = half ? (unsigned)(m64 >> 32) : (unsigned)m64;
+        for (int half = 0; half < (c.mask_hi ? 2 : 1); ++half) {   // object mask: one or two 32-bit words
+            unsigned m = half ? c.mask_hi[li] : c.mask_lo[li];
             while (m) {
                 const int o = __ffs(m) - 1 + 32 * half;
                 m &= m - 1;
@@ -442,7 +454,7 @@ __device__ __forceinline__ void winners_pass(const WinCtx &c) {
         fg_weight(X, Y, Z, xp, yp, zp, xn, yn, zn, (double)pot, (double)gx, (double)gy, (double)gz, c.inv_dt, wx, wy, wz);
 #pragma unroll 1
         for (int s = l; s < NS; s += G)
-            c.lg[(size_t)li * NS + s] = fg_slot(c.rc, c.frames + (size_t)i * NL * 12, j, s, X, Y, Z, wx, wy, wz);
+            c.lg[((size_t)i * c.nlu + j) * NS + s] = fg_slot(c.rc, c.frames + (size_t)i * NL * 12, j, s, X, Y, Z, wx, wy, wz);
     }
 }
 
@@ -519,16 +531,16 @@ __device__ __forceinline__ void chomp_iteration(const StepArgs &a, unsigned char
     double *s_goal = reinterpret_cast<double *>(smem + L.off_goal);
     double *s_frames = reinterpret_cast<double *>(smem + L.off_frames);
     double *s_lg = reinterpret_cast<double *>(smem + L.off_lg);
-    float *s_pot = reinterpret_cast<float *>(smem + L.off_lg);
     double2 *s_sc = reinterpret_cast<double2 *>(smem + L.off_lg);
     double *s_grad = reinterpret_cast<double *>(smem + L.off_grad);
     double *s_u = reinterpret_cast<double *>(smem + L.off_u);
     double *s_viol = reinterpret_cast<double *>(smem + L.off_viol);
     double *s_red = reinterpret_cast<double *>(smem + L.off_red);
-    unsigned long long *s_mask = reinterpret_cast<unsigned long long *>(smem + L.off_mask);
+    unsigned *s_mlo = reinterpret_cast<unsigned *>(smem + L.off_mask);
+    unsigned *s_mhi = L.mask_hi ? reinterpret_cast<unsigned *>(smem + L.off_mask_hi) : nullptr;
     float *s_best = reinterpret_cast<float *>(smem + L.off_best);
-    int *s_bestp = reinterpret_cast<int *>(smem + L.off_bestp);
-    int *s_act = reinterpret_cast<int *>(smem + L.off_act);
+    unsigned char *s_bestp = smem + L.off_bestp;
+    unsigned short *s_act = reinterpret_cast<unsigned short *>(smem + L.off_act);
     unsigned short *s_win = reinterpret_cast<unsigned short *>(smem + L.off_win);
     ObjRec *s_objs = reinterpret_cast<ObjRec *>(smem + L.off_objs);
     int *s_hist = reinterpret_cast<int *>(smem + L.off_hist);
@@ -540,6 +552,8 @@ __device__ __forceinline__ void chomp_iteration(const StepArgs &a, unsigned char
     constexpr bool topk_mode = TOPK;   // prm.top_k_collision > 0
     const bool goal_set = prm.goal_set_proj != 0;
     const int n_li = n * NL;
+    const int NLU = L.nlu;
+    float *g_pot = a.pot_scratch + (size_t)b * n_li * LPI;   // this trajectory's slice of the potential scratch
 
 #define OMGB_PROF(slot) do { if (a.prof && tid == 0) a.prof[(size_t)b * 16 + (slot)] = clock64(); } while (0)
     OMGB_PROF(0);
@@ -640,7 +654,8 @@ __device__ __forceinline__ void chomp_iteration(const StepArgs &a, unsigned char
             }
             m |= 1ull << o;
         }
-        s_mask[li] = m;
+        s_mlo[li] = (unsigned)m;
+        if (s_mhi) s_mhi[li] = (unsigned)(m >> 32);
     }
     __syncthreads();
     OMGB_PROF(3);
@@ -649,7 +664,7 @@ __device__ __forceinline__ void chomp_iteration(const StepArgs &a, unsigned char
         int n_act = 0;   // running count (uniform)
         for (int base = 0; base < n_li; base += nthr) {
             const int li = base + tid;
-            const bool on = (li < n_li) && (s_mask[li] != 0ull || a.dbg_pts != nullptr);
+            const bool on = (li < n_li) && (s_mlo[li] != 0u || (s_mhi && s_mhi[li] != 0u) || a.dbg_pts != nullptr);
             const unsigned bal = __ballot_sync(0xffffffffu, on);
             if (lane == 0) s_hist[warp] = __popc(bal);
             __syncthreads();
@@ -659,16 +674,14 @@ __device__ __forceinline__ void chomp_iteration(const StepArgs &a, unsigned char
                 if (w < warp) before += cnt;
                 total += cnt;
             }
-            if (on) s_act[n_act + before + __popc(bal & ((1u << lane) - 1u))] = li;
+            if (on) s_act[n_act + before + __popc(bal & ((1u << lane) - 1u))] = (unsigned short)li;
             n_act += total;
             __syncthreads();
         }
         if (tid == 0) s_hist[263] = n_act;
     }
-    if (topk_mode)
-        for (int k = tid; k < n_li * LPI; k += nthr) s_pot[k] = 0.0f;   // (the sin/cos table is dead now)
-    else
-        for (int k = tid; k < n_li * NS; k += nthr) s_lg[k] = 0.0;
+    if (!topk_mode)
+        for (int k = tid; k < n_li * NS; k += nthr) s_lg[k] = 0.0;   // (the sin/cos table is dead now)
     __syncthreads();
     const int n_act = s_hist[263];
 
@@ -691,11 +704,10 @@ __device__ __forceinline__ void chomp_iteration(const StepArgs &a, unsigned char
         double X, Y, Z;
         xform(F, bp[0], bp[1], bp[2], X, Y, Z);
         const float x = (float)X, y = (float)Y, z = (float)Z;   // omg/cost.py:136 .float()
-        const unsigned long long m64 = live ? s_mask[li] : 0ull;
         float pot = 0.0f, col = 0.0f, gx = 0.0f, gy = 0.0f, gz = 0.0f;
 #pragma unroll 1
-        for (int half = 0; half < 2; ++half) {   // 64-bit object mask walked as two 32-bit words (cheaper bit ops)
-            unsigned m = half ? (unsigned)(m64 >> 32) : (unsigned)m64;
+        for (int half = 0; half < (s_mhi ? 2 : 1); ++half) {   // object mask: one or two 32-bit words
+            unsigned m = live ? (half ? s_mhi[li] : s_mlo[li]) : 0u;
             while (m) {
                 const int o = __ffs(m) - 1 + 32 * half;
                 m &= m - 1;
@@ -735,7 +747,7 @@ __device__ __forceinline__ void chomp_iteration(const StepArgs &a, unsigned char
             }
         }
         if (topk_mode) {
-            if (live) s_pot[(size_t)li * LPI + pl] = pot;
+            if (live) __stcg(g_pot + (size_t)li * LPI + pl, pot);
             // argmax over the body points of this link instance (potentials are >= 0, so their bit patterns
             // order like the values); ties -> highest point index
             const unsigned bits = live ? __float_as_uint(pot) : 0u;
@@ -743,7 +755,7 @@ __device__ __forceinline__ void chomp_iteration(const StepArgs &a, unsigned char
             const unsigned bal = __ballot_sync(gmask, live && bits == mx) & gmask;
             if (have && pl == 0 && mx != 0u) {
                 s_best[li] = __uint_as_float(mx);
-                s_bestp[li] = (31 - __clz(bal)) - sub * LPI;
+                s_bestp[li] = (unsigned char)((31 - __clz(bal)) - sub * LPI);
             }
         } else {
             // full-sum mode: functional gradient of every point with non-zero potential, reduced over
@@ -803,7 +815,7 @@ __device__ __forceinline__ void chomp_iteration(const StepArgs &a, unsigned char
 #pragma unroll
             for (int q = 0; q < RC; ++q) {
                 const int k = tid + q * nthr;
-                cache[q] = (k < n_as) ? __float_as_uint(s_pot[(size_t)s_act[k / LPI] * LPI + (k % LPI)]) : 0u;
+                cache[q] = (k < n_as && (k % LPI) < P) ? __float_as_uint(__ldcg(g_pot + (size_t)s_act[k / LPI] * LPI + (k % LPI))) : 0u;
             }
             for (int shift = 24; shift >= 0; shift -= 8) {
                 for (int k = tid; k < 256; k += nthr) s_hist[k] = 0;
@@ -814,7 +826,8 @@ __device__ __forceinline__ void chomp_iteration(const StepArgs &a, unsigned char
                     if (u != 0u && (u & pmask) == prefix) atomicAdd(&s_hist[(u >> shift) & 255u], 1);
                 }
                 for (int k = tid + RC * nthr; k < n_as; k += nthr) {   // (only when n_as > 16 * blockDim)
-                    const uint32_t u = __float_as_uint(s_pot[(size_t)s_act[k / LPI] * LPI + (k % LPI)]);
+                    if ((k % LPI) >= P) continue;
+                    const uint32_t u = __float_as_uint(__ldcg(g_pot + (size_t)s_act[k / LPI] * LPI + (k % LPI)));
                     if (u != 0u && (u & pmask) == prefix) atomicAdd(&s_hist[(u >> shift) & 255u], 1);
                 }
                 __syncthreads();
@@ -857,9 +870,10 @@ __device__ __forceinline__ void chomp_iteration(const StepArgs &a, unsigned char
         if (nnz > 0) {
             for (int k = tid; k < n_act * LPI; k += nthr) {
                 const int li = s_act[k / LPI], p = k % LPI;
-                const float pv = s_pot[(size_t)li * LPI + p];
                 const int i = li / NL, j = li - i * NL;
-                if (p < P && j < jmax && pv > 0.0f && __float_as_uint(pv) >= tau) {
+                if (p >= P || j >= jmax) continue;
+                const float pv = __ldcg(g_pot + (size_t)li * LPI + p);
+                if (pv > 0.0f && __float_as_uint(pv) >= tau) {
                     const double *F = s_frames + (size_t)li * 12;
                     const double *Fp = (i > 0) ? (F - NL * 12) : (s_frames + ((size_t)n * NL + j) * 12);
                     const double *bp = rc->pts[j][p];
@@ -891,16 +905,17 @@ __device__ __forceinline__ void chomp_iteration(const StepArgs &a, unsigned char
             if (win) s_win[wbase + __popc(bal & ((1u << lane) - 1u))] = (unsigned short)li;
         }
         double red1[1] = {acc};
-        block_sum_n<1>(red1, s_red);   // (also the barrier after which s_pot is dead and s_lg may be written)
+        block_sum_n<1>(red1, s_red);
         obs_sum = red1[0] * (double)n;   // added to every waypoint row (SURVEY A-3)
-        for (int k = tid; k < n_li * NS; k += nthr) s_lg[k] = 0.0;
+        for (int k = tid; k < n * NLU * NS; k += nthr) s_lg[k] = 0.0;
         __syncthreads();
         OMGB_PROF(7);
         // ---- phase 4b: one winner per (waypoint, link) (SURVEY A-1).  The winner list was compacted in phase 4a;
         // the lanes per winner adapt to how many there are (few winners: low latency; many: no redundancy) ----
         {
             WinCtx wc;
-            wc.rc = rc; wc.frames = s_frames; wc.mask = s_mask; wc.bestp = s_bestp; wc.win = s_win; wc.objs = s_objs;
+            wc.rc = rc; wc.frames = s_frames; wc.mask_lo = s_mlo; wc.mask_hi = s_mhi; wc.bestp = s_bestp; wc.win = s_win;
+            wc.objs = s_objs; wc.nlu = NLU;
             wc.grids = a.grids; wc.dil = &a.dil; wc.lg = s_lg; wc.inv_dt = inv_dt; wc.n = n; wc.n_win = s_hist[261];
             wc.finger_soft = finger_soft; wc.use_dil = use_dil;
             if (wc.n_win * 8 <= nthr) winners_pass<8>(wc);
@@ -921,9 +936,9 @@ __device__ __forceinline__ void chomp_iteration(const StepArgs &a, unsigned char
         const int i = k / ND, d = k - i * ND;
         double og = 0.0;
         if (d < 7) {
-            for (int j = d; j <= jlast; ++j) og += s_lg[((size_t)i * NL + j) * NS + d];
+            for (int j = d; j <= jlast; ++j) og += s_lg[((size_t)i * NLU + j) * NS + d];
         } else if (jlast == 9) {
-            og = s_lg[((size_t)i * NL + (d + 1)) * NS + 7];   // dof 7 <- link 8, dof 8 <- link 9
+            og = s_lg[((size_t)i * NLU + (d + 1)) * NS + 7];   // dof 7 <- link 8, dof 8 <- link 9
         }
         const double xc = s_xi[k];
         const double xprev = (i > 0) ? s_xi[k - ND] : s_start[d];
@@ -1025,11 +1040,11 @@ __device__ __forceinline__ void chomp_iteration(const StepArgs &a, unsigned char
                 int fk = s_hist[0];
                 for (int w = 1; w < nwarps; ++w)
                     if (s_red[w] > fm || (s_red[w] == fm && s_hist[w] < fk)) { fm = s_red[w]; fk = s_hist[w]; }
-                s_red[40] = fm;
+                s_red[L.red_max] = fm;
                 s_hist[260] = fk;
             }
             __syncthreads();
-            const double vmax = s_red[40];
+            const double vmax = s_red[L.red_max];
             const int kmax = s_hist[260];
             metric_apply(a, n, s_viol, s_u, s_viol + n * ND);
             const double scale = vmax / (fabs(s_u[kmax]) + 1e-8);

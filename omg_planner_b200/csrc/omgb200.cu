@@ -5,6 +5,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <atomic>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -20,7 +22,8 @@
 namespace omgb {
 
 static thread_local std::string g_err;
-static unsigned long long g_launches = 0;   // kernels launched by this library (bench.py's gpu_launches)
+static std::atomic<unsigned long long> g_launches{0};   // kernels launched by this library (bench.py's gpu_launches)
+static std::mutex g_attr_mutex;                          // guards the per-instantiation function-attribute caches
 
 static int fail(int code, const std::string &msg) {
     g_err = msg;
@@ -412,7 +415,36 @@ struct omgb_scene {
     double *d_stage = nullptr;
     size_t stage_bytes = 0;
     int smem_optin = 0;
+    // per-point potentials of the top-k path: [trajectories][n*10][LPI] fp32, grown on demand (launch_step)
+    float *d_pot = nullptr;
+    size_t pot_floats = 0;
+    // One engine is one stream's worth of mutable state (CTA order slots, plan counters, the potential scratch).
+    // Every launch records `last_done` on its stream; a launch arriving on ANOTHER stream waits for it first, so
+    // driving one engine from several streams is serialised instead of racing (use one engine per stream to overlap).
+    cudaEvent_t last_done = nullptr;
+    cudaStream_t last_stream = nullptr;
+    bool has_last = false;
 };
+
+// Orders a launch on `st` behind the previous launch of this scene when that ran on a different stream.
+static int stream_enter(omgb_scene *s, cudaStream_t st) {
+    if (s->has_last && s->last_stream != st) {
+        cudaError_t e = cudaStreamWaitEvent(st, s->last_done, 0);
+        if (e != cudaSuccess) return host_fail(OMGB_ERR_CUDA, std::string("cudaStreamWaitEvent: ") + cudaGetErrorString(e));
+    }
+    return OMGB_OK;
+}
+static int stream_leave(omgb_scene *s, cudaStream_t st) {
+    if (!s->last_done) {
+        cudaError_t e = cudaEventCreateWithFlags(&s->last_done, cudaEventDisableTiming);
+        if (e != cudaSuccess) return host_fail(OMGB_ERR_CUDA, std::string("cudaEventCreate: ") + cudaGetErrorString(e));
+    }
+    cudaError_t e = cudaEventRecord(s->last_done, st);
+    if (e != cudaSuccess) return host_fail(OMGB_ERR_CUDA, std::string("cudaEventRecord: ") + cudaGetErrorString(e));
+    s->last_stream = st;
+    s->has_last = true;
+    return OMGB_OK;
+}
 
 extern "C" int omgb_version(void) { return OMGB_VERSION; }
 extern "C" const char *omgb_last_error(void) { return g_err.c_str(); }
@@ -437,7 +469,8 @@ extern "C" int omgb_scene_destroy(omgb_scene_t *s) {
     cudaFree(s->d_robot); cudaFree(s->d_limits); cudaFree(s->d_objparams); cudaFree(s->d_objs);
     cudaFree(s->d_Ainv); cudaFree(s->d_proj); cudaFree(s->d_stage); cudaFree(s->d_dil); cudaFree(s->d_bounds);
     for (int k = 0; k < ORDER_SLOTS; ++k) { cudaFree(s->order[k].d_order); cudaFree(s->order[k].d_cost); }
-    cudaFree(s->d_plan_sched); cudaFree(s->d_plan_progress); cudaFree(s->d_plan_counter);
+    cudaFree(s->d_plan_sched); cudaFree(s->d_plan_progress); cudaFree(s->d_plan_counter); cudaFree(s->d_pot);
+    if (s->last_done) cudaEventDestroy(s->last_done);
     for (int k = 0; k < PIPE_CHUNKS; ++k) {
         if (s->pipe_stream[k]) cudaStreamDestroy(s->pipe_stream[k]);
         if (s->pipe_done[k]) cudaEventDestroy(s->pipe_done[k]);
@@ -516,7 +549,7 @@ extern "C" int omgb_scene_set_robot(omgb_scene_t *s, const double *pose_0, const
     return OMGB_OK;
 }
 
-extern "C" unsigned long long omgb_launch_count(void) { return g_launches; }
+extern "C" unsigned long long omgb_launch_count(void) { return g_launches.load(); }
 
 extern "C" int omgb_scene_set_options(omgb_scene_t *s, int use_lower_bound, int use_longest_first) {
     if (!s) return fail(OMGB_ERR_INVALID, "omgb_scene_set_options: null scene");
@@ -541,7 +574,7 @@ extern "C" int omgb_scene_set_profile(omgb_scene_t *s, long long *d_phase_clocks
 }
 
 extern "C" int omgb_scene_set_sdf(omgb_scene_t *s, const float *d_sdf_grids, const float *h_sdf_limits,
-                                  int num_objects, int dx, int dy, int dz) {
+                                  int num_objects, int dx, int dy, int dz, void *stream) {
     if (!s || !d_sdf_grids || !h_sdf_limits) return fail(OMGB_ERR_INVALID, "omgb_scene_set_sdf: null argument");
     if (num_objects < 1 || num_objects > OMGB_MAX_OBJECTS)
         return fail(OMGB_ERR_INVALID, "num_objects must be in [1, OMGB_MAX_OBJECTS]");
@@ -574,9 +607,11 @@ extern "C" int omgb_scene_set_sdf(omgb_scene_t *s, const float *d_sdf_grids, con
         OMGB_CUDA(cudaMalloc(&s->d_dil, sizeof(float) * (size_t)total));
         OMGB_CUDA(cudaMalloc(&tmp, sizeof(float) * (size_t)total));
         const int blocks = (int)((total + 255) / 256 > 148 * 64 ? 148 * 64 : (total + 255) / 256);
-        brick_min_kernel<<<blocks, 256>>>(d_sdf_grids, num_objects, dx, dy, dz, tmp, dd.bx, dd.by, dd.bz);
-        brick_dilate_kernel<<<blocks, 256>>>(tmp, num_objects, dd.bx, dd.by, dd.bz, s->d_dil);
-        cudaError_t e1 = cudaGetLastError(), e2 = cudaDeviceSynchronize();
+        // on the caller's stream: the grid was produced there (omgb_sdf_pack, torch ops); only that stream is waited for
+        cudaStream_t st = (cudaStream_t)stream;
+        brick_min_kernel<<<blocks, 256, 0, st>>>(d_sdf_grids, num_objects, dx, dy, dz, tmp, dd.bx, dd.by, dd.bz);
+        brick_dilate_kernel<<<blocks, 256, 0, st>>>(tmp, num_objects, dd.bx, dd.by, dd.bz, s->d_dil);
+        cudaError_t e1 = cudaGetLastError(), e2 = cudaStreamSynchronize(st);
         cudaFree(tmp);
         if (e1 != cudaSuccess || e2 != cudaSuccess)
             return fail(OMGB_ERR_CUDA, std::string("lower-bound grid build: ") + cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
@@ -733,6 +768,7 @@ static int launch_one(const StepArgs &a, size_t smem, cudaStream_t st, const Pla
     int dev = 0;
     cudaGetDevice(&dev);
     const int which = plan ? 1 : 0;
+    std::lock_guard<std::mutex> lock(g_attr_mutex);
     if (dev < 0 || dev >= 64 || cached_smem[which][dev] != smem) {
         if (plan) {
             OMGB_CUDA(cudaFuncSetAttribute(chomp_plan_kernel<LPI, THREADS, MINB, TOPK>,
@@ -764,27 +800,67 @@ static int launch_cfg(const StepArgs &a, size_t smem, cudaStream_t st, const Pla
                                      : launch_one<LPI, THREADS, MINB, false>(a, smem, st, plan, num_sms);
 }
 
-static int step_config() {   // OMGB_STEP_CONFIG: 1 = 512 threads x 2 CTAs/SM, 2 = 1024 x 1, else chosen by footprint
-    static int cfg = -1;
-    if (cfg < 0) {
+static int step_config() {   // OMGB_STEP_CONFIG: 0 = 320 threads x 3 CTAs/SM, 1 = 512 x 2, 2 = 1024 x 1, 3 = 256 x 4; else by footprint
+    static int cfg = -2;
+    if (cfg == -2) {
         const char *e = getenv("OMGB_STEP_CONFIG");
-        cfg = e ? atoi(e) : 5;
+        cfg = e ? atoi(e) : -1;
     }
     return cfg;
 }
 
 // plan == nullptr: one iteration, CTA per trajectory; else the persistent plan kernel.
-static int launch_step(omgb_scene *s, const StepArgs &a_in, cudaStream_t st, const PlanArgs *plan = nullptr) {
+// pot_first: index of this launch's first trajectory inside the scene's potential scratch (the chunks of the pipelined
+// host entry point run concurrently on their own streams, each on its own slice).
+static int launch_step(omgb_scene *s, const StepArgs &a_in, cudaStream_t st, const PlanArgs *plan = nullptr,
+                       size_t pot_first = 0, bool guard_stream = true) {
     const StepArgs &a0 = a_in;
     const int lpi = s->p <= 16 ? 16 : 32;
-    const SmemLayout L = make_layout(a0.prm.n_waypoints, a0.prm.constraint_rows, lpi, s->num_objects, s->p);
+    const int n = a0.prm.n_waypoints, c = a0.prm.constraint_rows;
+    const bool topk = a0.prm.top_k_collision > 0, fing = a0.prm.consider_finger != 0;
+    if (a0.batch == 0) return OMGB_OK;
+    // CTA shape by how many CTAs of this footprint fit in an SM's 228 KB (+1 KB reserved each): three 320-thread CTAs
+    // for the usual 30-waypoint trajectory, two of 512 threads for 50-60 waypoints, one of 1024 beyond, so that ~30
+    // warps stay resident per SM either way.  OMGB_STEP_CONFIG = 0 / 1 / 2 / 3 forces 320x3 / 512x2 / 1024x1 / 256x4.
+    static const int shape_threads[4] = {320, 512, 1024, 256}, shape_ctas[4] = {3, 2, 1, 4};
+    auto layout_for = [&](int cfg) {
+        return make_layout(n, c, lpi, s->num_objects, s->p, shape_threads[cfg] / 32, topk, fing);
+    };
+    auto fits = [&](int cfg) {
+        const SmemLayout L = layout_for(cfg);
+        return L.total <= (size_t)s->smem_optin && (size_t)shape_ctas[cfg] * (L.total + 1024u) <= 228u * 1024u;
+    };
+    int cfg = step_config();
+    if (cfg < 0 || cfg > 3 || !fits(cfg)) {
+        // (256x4 fits a 30-waypoint trajectory too; measured with a cold L2 it is slower than 320x3 -- 0.121 vs 0.117 ms
+        // per step of 1024 trajectories: the per-trajectory critical path grows -- and faster with a warm one)
+        cfg = (lpi == 16 && fits(0)) ? 0 : fits(1) ? 1 : 2;
+        // small batches leave SMs under-filled: spend the idle warps on wider CTAs (lower latency per trajectory)
+        if (a0.batch <= s->num_sms) cfg = 2;
+        else if (a0.batch <= 2 * s->num_sms && (cfg == 0 || cfg == 3)) cfg = 1;
+    }
+    if (lpi == 32 && (cfg == 0 || cfg == 3)) cfg = 1;
+    const SmemLayout L = layout_for(cfg);
     if (L.total > (size_t)s->smem_optin)
         return fail(OMGB_ERR_UNSUPPORTED, "trajectory too long for one CTA's shared memory");
-    if (a0.batch == 0) return OMGB_OK;
-    // longest-first order from the previous launch on the same batch (same xi buffer and size)
     StepArgs a = a_in;
     a.lay = L;
     a.rp = s->rp;
+    if (topk) {   // the potential scratch covers pot_first + batch trajectories
+        const size_t need = (pot_first + (size_t)a.batch) * (size_t)n * NL * lpi;
+        if (need > s->pot_floats) {
+            if (pot_first != 0) return fail(OMGB_ERR_STATE, "potential scratch not sized before a chunked launch");
+            OMGB_CUDA(cudaStreamSynchronize(st));   // (earlier launches may still use the old buffer)
+            if (s->has_last) OMGB_CUDA(cudaEventSynchronize(s->last_done));
+            cudaFree(s->d_pot);
+            s->d_pot = nullptr; s->pot_floats = 0;
+            OMGB_CUDA(cudaMalloc(&s->d_pot, sizeof(float) * need));
+            s->pot_floats = need;
+        }
+        a.pot_scratch = s->d_pot + pot_first * (size_t)n * NL * lpi;
+    }
+    if (guard_stream) { int g_ = stream_enter(s, st); if (g_) return g_; }
+    // longest-first order from the previous launch on the same batch (same xi buffer and size)
     static int env_lpt = -1;
     if (env_lpt < 0) { const char *e = getenv("OMGB_NO_LPT"); env_lpt = (e && atoi(e)) ? 0 : 1; }
     OrderSlot *os = nullptr;
@@ -810,20 +886,10 @@ static int launch_step(omgb_scene *s, const StepArgs &a_in, cudaStream_t st, con
         a.order = os->valid ? os->d_order : nullptr;
         a.cta_cost = os->d_cost;
     }
-    // CTA shape by how many CTAs of this footprint fit in an SM's 228 KB (+1 KB reserved each): three 320-thread
-    // CTAs for the usual 30-waypoint trajectory, two of 512 or one of 1024 threads for long trajectories, so that
-    // ~30 warps stay resident per SM either way.  OMGB_STEP_CONFIG=1/2 forces 512x2 / 1024x1.
-    const int fit = (int)((228u * 1024u) / (L.total + 1024u));
-    int cfg = step_config();
-    if (cfg != 1 && cfg != 2) {
-        cfg = fit >= 3 ? 0 : (fit == 2 ? 1 : 2);
-        // small batches leave SMs under-filled: spend the idle warps on wider CTAs (lower latency per trajectory)
-        if (a.batch <= s->num_sms) cfg = 2;
-        else if (a.batch <= 2 * s->num_sms && cfg == 0) cfg = 1;
-    }
     int rc_ = OMGB_OK;
     if (lpi == 16) {
-        if (cfg == 0) rc_ = launch_cfg<16, 320, 3>(a, L.total, st, plan, s->num_sms);
+        if (cfg == 3) rc_ = launch_cfg<16, 256, 4>(a, L.total, st, plan, s->num_sms);
+        else if (cfg == 0) rc_ = launch_cfg<16, 320, 3>(a, L.total, st, plan, s->num_sms);
         else if (cfg == 1) rc_ = launch_cfg<16, 512, 2>(a, L.total, st, plan, s->num_sms);
         else rc_ = launch_cfg<16, 1024, 1>(a, L.total, st, plan, s->num_sms);
     } else {
@@ -838,6 +904,7 @@ static int launch_step(omgb_scene *s, const StepArgs &a_in, cudaStream_t st, con
         OMGB_CUDA(cudaGetLastError());
         os->valid = true;
     }
+    if (guard_stream) return stream_leave(s, st);
     return OMGB_OK;
 }
 
@@ -1004,7 +1071,21 @@ extern "C" int omgb_chomp_step_host(omgb_scene_t *s, const omgb_step_params_t *p
         }
         OMGB_CUDA(cudaEventCreateWithFlags(&s->pipe_begin, cudaEventDisableTiming));
     }
-    if (chunks > 1) OMGB_CUDA(cudaEventRecord(s->pipe_begin, st));
+    if (chunks > 1) {
+        // size the potential scratch for the whole batch before the chunks start (they run concurrently)
+        const size_t need = (size_t)batch * n * NL * (s->p <= 16 ? 16 : 32);
+        if (prm->top_k_collision > 0 && need > s->pot_floats) {
+            OMGB_CUDA(cudaStreamSynchronize(st));
+            if (s->has_last) OMGB_CUDA(cudaEventSynchronize(s->last_done));
+            cudaFree(s->d_pot);
+            s->d_pot = nullptr; s->pot_floats = 0;
+            OMGB_CUDA(cudaMalloc(&s->d_pot, sizeof(float) * need));
+            s->pot_floats = need;
+        }
+        rc_ = stream_enter(s, st);
+        if (rc_) return rc_;
+        OMGB_CUDA(cudaEventRecord(s->pipe_begin, st));
+    }
     for (int k = 0; k < chunks; ++k) {
         const int b0 = (int)((long long)batch * k / chunks), b1 = (int)((long long)batch * (k + 1) / chunks);
         const size_t nb = (size_t)(b1 - b0);
@@ -1022,7 +1103,7 @@ extern "C" int omgb_chomp_step_host(omgb_scene_t *s, const omgb_step_params_t *p
         StepArgs a = make_args(s, prm, (int)nb, d_xi + (size_t)b0 * n * ND, d_start + (size_t)b0 * ND,
                                d_end + (size_t)b0 * ND, c > 0 ? d_goal + (size_t)b0 * c * ND : nullptr, nullptr, nullptr,
                                d_info + (size_t)b0 * OMGB_INFO_STRIDE, nullptr, nullptr);
-        rc_ = launch_step(s, a, cs);
+        rc_ = chunks > 1 ? launch_step(s, a, cs, nullptr, (size_t)b0, false) : launch_step(s, a, cs);
         if (rc_) return rc_;
         OMGB_CUDA(cudaMemcpyAsync(h_xi + (size_t)b0 * n * ND, d_xi + (size_t)b0 * n * ND, sizeof(double) * nb * n * ND,
                                   cudaMemcpyDeviceToHost, cs));

@@ -68,7 +68,8 @@ class ChompEngine(object):
                                    dtype=np.float32)
         o, x, y, z = sdf_grids.shape
         self._keep["grids"] = sdf_grids
-        _lib.check(self.L.omgb_scene_set_sdf(self._h, _dp(sdf_grids), _hp(lim), o, x, y, z), "omgb_scene_set_sdf")
+        _lib.check(self.L.omgb_scene_set_sdf(self._h, _dp(sdf_grids), _hp(lim), o, x, y, z, _stream()),
+                   "omgb_scene_set_sdf")
         self.num_objects = o
 
     def set_objects(self, pose_inv, epsilons, padding_scales, clearances, disables):
