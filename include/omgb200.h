@@ -129,6 +129,14 @@ int omgb_scene_set_robot(omgb_scene_t *scene, const double *pose_0, const double
 int omgb_scene_set_sdf(omgb_scene_t *scene, const float *d_sdf_grids, const float *h_sdf_limits,
                        int num_objects, int dim_x, int dim_y, int dim_z, void *stream);
 
+/* Optional data layout for the exact-evaluation path of the fused kernels (the layout of
+ * omg/core.py:366-411 being replaced).  layout 0: read the reference [O,X,Y,Z] tensor as it is (default, zero-copy).
+ * layout 1: additionally keep a bricked copy -- 8^3-cell bricks of 8 KB, one float4 per cell holding the cell's four
+ * (y, z) taps -- so that a trilinear sample is two aligned 128-bit loads instead of eight scalar taps.  Same tap
+ * values and interpolation order: results are bit-identical.  Costs 4x the grid bytes; call after omgb_scene_set_sdf
+ * (which drops a stale copy) and before omgb_scene_set_objects.  Environment OMGB_SDF_LAYOUT=1 selects it by default. */
+int omgb_scene_set_sdf_layout(omgb_scene_t *scene, int layout, void *stream);
+
 /* Per-object parameters built by Cost.compute_obstacle_cost_layer (omg/cost.py:303-335), HOST arrays:
  * pose_inv [O,4,4] fp32 (world->object), epsilons, padding_scales, clearances, disables [O] fp32. */
 int omgb_scene_set_objects(omgb_scene_t *scene, const float *pose_inv, const float *epsilons,

@@ -18,7 +18,7 @@ INFO_KEYS = ["obs", "smooth", "cost", "collide", "reach", "grad", "weighted_obs_
              "reserved"]
 
 EXPORTS = ["omgb_version", "omgb_last_error", "omgb_scene_create", "omgb_scene_destroy", "omgb_scene_set_robot",
-           "omgb_scene_set_sdf", "omgb_scene_set_profile", "omgb_scene_set_options", "omgb_scene_set_host_mode", "omgb_launch_count", "omgb_scene_set_objects", "omgb_scene_set_metric",
+           "omgb_scene_set_sdf", "omgb_scene_set_sdf_layout", "omgb_scene_set_profile", "omgb_scene_set_options", "omgb_scene_set_host_mode", "omgb_launch_count", "omgb_scene_set_objects", "omgb_scene_set_metric",
            "omgb_sdf_loss_workspace_bytes", "omgb_sdf_loss", "omgb_chomp_step", "omgb_chomp_plan",
            "omgb_chomp_step_host", "omgb_batch_obstacle_cost", "omgb_goal_costs", "omgb_chomp_plan_history",
            "omgb_traj_interpolate", "omgb_sdf_pack", "omgb_point_sdf", "omgb_ik_solve", "omgb_hand_poses", "omgb_chomp_plan_step",
@@ -110,6 +110,7 @@ def lib():
     L.omgb_scene_destroy.argtypes = [vp]
     L.omgb_scene_set_robot.argtypes = [vp, vp, vp, vp, vp, ci, vp, vp, ci, vp, vp]
     L.omgb_scene_set_sdf.argtypes = [vp, vp, vp, ci, ci, ci, ci, vp]
+    L.omgb_scene_set_sdf_layout.argtypes = [vp, ci, vp]
     L.omgb_scene_set_profile.argtypes = [vp, vp]
     L.omgb_scene_set_options.argtypes = [vp, ci, ci]
     L.omgb_scene_set_host_mode.argtypes = [vp, ci]

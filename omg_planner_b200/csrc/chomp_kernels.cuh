@@ -53,7 +53,7 @@ struct DilDesc {
 
 struct SmemLayout {
     unsigned off_xi, off_start, off_end, off_goal, off_frames, off_lg, off_grad, off_u, off_viol, off_red,
-        off_mask, off_mask_hi, off_best, off_bestp, off_act, off_win, off_objs, off_hist, total;
+        off_mask, off_mask_hi, off_best, off_bestp, off_act, off_win, off_objs, off_hist, off_mbar, total;
     int nlu;        // links that own gradient rows: 8 in top-k mode without consider_finger (cost.py:401-402), else 10
     int red_max;    // index of the block-argmax slot inside the reduction scratch
     int mask_hi;    // 1: more than 32 objects, the object masks are two 32-bit words
@@ -98,6 +98,7 @@ __host__ __device__ inline SmemLayout make_layout(int n, int c, int lpi, int nob
     o = align_up(o, 16);
     L.off_objs = o; o += sizeof(ObjRec) * nobj;
     L.off_hist = o; o += sizeof(int) * 264;
+    L.off_mbar = o; o += 8;   // mbarrier of the bulk (TMA) staging copies
     L.total = align_up(o, 16);
     (void)p; (void)lpi;
     return L;
@@ -134,6 +135,7 @@ struct StepArgs {
     long long *prof;         // [B,16] or null: clock64() at phase boundaries (diagnostic)
     double *hist_xi;         // [iters,B,n,9] or null: xi after every iteration (Planner.history_trajectories[1:])
     double *hist_info;       // [iters,B,16] or null: the info row of every iteration (Planner.info)
+    QuadDesc quad;           // bricked quad copy of the grids for the exact path (data == null: reference layout)
     float *pot_scratch;      // [B,n*10,LPI] fp32: per-point potentials of the top-k path (global, written and read by
                              // the trajectory's own CTA within one iteration)
     DilDesc dil;
@@ -143,6 +145,7 @@ struct StepArgs {
     int batch;
     int metric_kind;         // 0: dense Ainv; 1: Ainv = s*min(i,j) (goal-set, free end); 2: s*min(i,j)(n+1-max(i,j))/(n+1)
     double metric_scale;     // s (= dt^2)
+    int bulk_stage;          // 1: xi and the object records are device memory -> staged by cp.async.bulk (TMA)
     int iteration;           // index inside a plan (for the t > 0 rule of planner.py:627)
     int stop_on_terminate;
     omgb_step_params_t prm;
@@ -151,6 +154,29 @@ struct StepArgs {
 // ----------------------------------------------------------------------------------------------------
 // small helpers
 // ----------------------------------------------------------------------------------------------------
+// TMA bulk copy global -> shared (cp.async.bulk, no tensor map: a contiguous run of 16-byte units) completing on an
+// mbarrier: one thread moves a trajectory's xi rows and the scene's object records while the others stage the rest.
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init_one(unsigned bar) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // earlier generic accesses to the destination, too
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(unsigned dst, const void *src, unsigned bytes, unsigned bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+    unsigned ok = 0;
+    while (!ok) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    }
+}
+
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -404,6 +430,7 @@ struct WinCtx {
     const unsigned short *win;
     const ObjRec *objs;
     const float *grids;
+    const QuadDesc *quad;
     const DilDesc *dil;
     double *lg;
     double inv_dt;
@@ -442,7 +469,7 @@ __device__ __forceinline__ void winners_pass(const WinCtx &c) {
                 m &= m - 1;
                 if (c.use_dil && classify_pair(c.objs[o], *c.dil, o, x, y, z) != PAIR_EXACT) continue;
                 float po, ax, ay, az, co;
-                pair_full_group<G>(c.objs[o], c.grids, gm, l, x, y, z, po, ax, ay, az, co);
+                pair_full_group<G>(c.objs[o], c.grids, *c.quad, gm, l, x, y, z, po, ax, ay, az, co);
                 pot = __fadd_rn(pot, po);
                 gx = __fadd_rn(gx, ax); gy = __fadd_rn(gy, ay); gz = __fadd_rn(gz, az);
             }
@@ -579,20 +606,35 @@ __device__ __forceinline__ void chomp_iteration(const StepArgs &a, unsigned char
         if (k < n_x + 2 * ND) return a.end + (size_t)b * ND + (k - n_x - ND);
         return a.goal_rows + (size_t)b * c * ND + (k - n_x - 2 * ND);
     };
+    // Device-resident state: the xi rows (n*72 bytes) and the object records (288 bytes each) are contiguous runs of
+    // 16-byte units -> ONE thread issues two TMA bulk copies that complete on an mbarrier (they read through L2, which
+    // is where another SM's previous iteration of this trajectory left xi); start / end / goal rows (72-byte rows,
+    // not 16-byte aligned for odd b) and everything in mapped host memory take the per-thread path.
+    const unsigned mbar = smem_u32(smem + L.off_mbar);
+    const bool bulk = a.bulk_stage && ((((size_t)g_xi) | ((size_t)n_x * 8u)) & 15u) == 0;
+    if (bulk && tid == 0) {
+        const unsigned bytes_xi = (unsigned)n_x * 8u, bytes_obj = (unsigned)sizeof(ObjRec) * (unsigned)O;
+        mbar_init_one(mbar);
+        mbar_expect_tx(mbar, bytes_xi + bytes_obj);
+        bulk_g2s(smem_u32(s_xi), g_xi, bytes_xi, mbar);
+        bulk_g2s(smem_u32(s_objs), a.objs, bytes_obj, mbar);
+    }
+    const int k0 = bulk ? n_x : 0;
     double stg0 = 0.0, stg1 = 0.0;
-    if (tid < n_in) stg0 = __ldcg(stage_src(tid));
-    if (tid + nthr < n_in) stg1 = __ldcg(stage_src(tid + nthr));
-    {
+    if (k0 + tid < n_in) stg0 = __ldcg(stage_src(k0 + tid));
+    if (k0 + tid + nthr < n_in) stg1 = __ldcg(stage_src(k0 + tid + nthr));
+    if (!bulk) {
         const int words = (int)(sizeof(ObjRec) / 4) * O;
         const uint32_t *src = reinterpret_cast<const uint32_t *>(a.objs);
         uint32_t *dst = reinterpret_cast<uint32_t *>(s_objs);
         for (int k = tid; k < words; k += nthr) dst[k] = src[k];
     }
     for (int k = tid; k < n_li; k += nthr) { s_best[k] = 0.0f; s_bestp[k] = 0; }
-    if (tid < n_in) s_xi[tid] = stg0;
-    if (tid + nthr < n_in) s_xi[tid + nthr] = stg1;
-    for (int k = tid + 2 * nthr; k < n_in; k += nthr) s_xi[k] = __ldcg(stage_src(k));   // (long trajectories)
+    if (k0 + tid < n_in) s_xi[k0 + tid] = stg0;
+    if (k0 + tid + nthr < n_in) s_xi[k0 + tid + nthr] = stg1;
+    for (int k = k0 + tid + 2 * nthr; k < n_in; k += nthr) s_xi[k] = __ldcg(stage_src(k));   // (long trajectories)
     __syncthreads();
+    if (bulk) mbar_wait(mbar, 0u);
 
     OMGB_PROF(1);
     // ---- phase 1: forward kinematics (n waypoints, then start, then end) ---------------------------
@@ -722,10 +764,10 @@ __device__ __forceinline__ void chomp_iteration(const StepArgs &a, unsigned char
                 }
                 t_exact += 1;
                 if (topk_mode) {
-                    inb = pair_potential(s_objs[o], a.grids, x, y, z, po, co);
+                    inb = pair_potential(s_objs[o], a.grids, a.quad, x, y, z, po, co);
                 } else {
                     float ax, ay, az;
-                    inb = pair_full(s_objs[o], a.grids, x, y, z, po, ax, ay, az, co);
+                    inb = pair_full(s_objs[o], a.grids, a.quad, x, y, z, po, ax, ay, az, co);
                     gx = __fadd_rn(gx, ax); gy = __fadd_rn(gy, ay); gz = __fadd_rn(gz, az);
                 }
                 pot = __fadd_rn(pot, po);
@@ -916,7 +958,7 @@ __device__ __forceinline__ void chomp_iteration(const StepArgs &a, unsigned char
             WinCtx wc;
             wc.rc = rc; wc.frames = s_frames; wc.mask_lo = s_mlo; wc.mask_hi = s_mhi; wc.bestp = s_bestp; wc.win = s_win;
             wc.objs = s_objs; wc.nlu = NLU;
-            wc.grids = a.grids; wc.dil = &a.dil; wc.lg = s_lg; wc.inv_dt = inv_dt; wc.n = n; wc.n_win = s_hist[261];
+            wc.grids = a.grids; wc.quad = &a.quad; wc.dil = &a.dil; wc.lg = s_lg; wc.inv_dt = inv_dt; wc.n = n; wc.n_win = s_hist[261];
             wc.finger_soft = finger_soft; wc.use_dil = use_dil;
             if (wc.n_win * 8 <= nthr) winners_pass<8>(wc);
             else if (wc.n_win * 4 <= nthr) winners_pass<4>(wc);

@@ -16,6 +16,7 @@ namespace omgb {
 struct GoalArgs {
     const ObjRec *objs;
     const float *grids;
+    QuadDesc quad;
     const RobotConst *robot;
     const double *from;        // [B] rows of 9, row stride from_stride doubles (traj.data[start] of every trajectory)
     long long from_stride;
@@ -164,7 +165,7 @@ __global__ void __launch_bounds__(THREADS) goal_cost_kernel(const GoalArgs a) {
                 mm &= mm - 1;
                 if (use_dil && classify_pair(s_objs[o], a.dil, o, x, y, z) != PAIR_EXACT) continue;
                 float po, co;
-                pair_potential(s_objs[o], a.grids, x, y, z, po, co);
+                pair_potential(s_objs[o], a.grids, a.quad, x, y, z, po, co);
                 pot = __fadd_rn(pot, po);
             }
         }

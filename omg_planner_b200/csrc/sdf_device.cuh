@@ -37,8 +37,24 @@ struct __align__(16) ObjRec {
     long long grid_offset;       // o * d0*d1*d2
     float ga[12];                // world -> APPROXIMATE grid coordinates, g = ga[4k..4k+2] . x + ga[4k+3] (cull/classify only)
     float wsx, wsy, wsz, wsr;    // WORLD-frame sphere enclosing the padded in-bounds box (first-level cull); wsr < 0: never cull
-    float pad1_[2];
+    long long quad_offset;       // o * QuadDesc::obj_stride (float4 units) into the bricked quad copy of the grids
 };
+
+// Optional second copy of the packed SDFs for the exact-evaluation path ("bricked quads", omgb_scene_set_sdf_layout):
+// one float4 per voxel cell (x, y, z) = the four taps (x,y,z) (x,y,z+1) (x,y+1,z) (x,y+1,z+1), cells grouped in 8^3
+// bricks of 8 KB, x fastest inside a brick.  A trilinear sample is then TWO aligned 128-bit loads (cells x0 and x0+1,
+// usually one 32-byte sector) instead of eight scalar taps over four (x, y) rows; same tap values, same lerp order,
+// so results are bit-identical.  4x the bytes of the reference layout, which stays in place for the raw operator.
+struct QuadDesc {
+    const float4 *data;          // null: read the reference [O,X,Y,Z] layout
+    long long obj_stride;        // float4s per object = nb0 * nb1 * nb2 * 512
+    int nb1, nb2;                // bricks along y and z
+};
+
+__host__ __device__ __forceinline__ long long quad_index(int x, int y, int z, int nb1, int nb2) {
+    const long long brick = ((long long)(x >> 3) * nb1 + (y >> 3)) * nb2 + (z >> 3);
+    return (brick << 9) + ((((y & 7) << 3) + (z & 7)) << 3) + (x & 7);
+}
 
 __device__ __forceinline__ float lerp_ref(float a, float b, float t) {   // kernel.cu:15-18
     return __fmaf_rn(t, __fsub_rn(b, a), a);
@@ -56,9 +72,10 @@ __device__ __forceinline__ void cell_of(float p, int &c0, float &f) {
     }
 }
 
-// kernel.cu:37-64.  Returns 1.0f when any of the 8 taps is out of bounds.
-__device__ __forceinline__ float value_interp(const float *__restrict__ g, int d0, int d1, int d2, float px,
-                                              float py, float pz, bool &inb) {
+// kernel.cu:37-64.  Returns 1.0f when any of the 8 taps is out of bounds.  q != null: the object's bricked quads.
+__device__ __forceinline__ float value_interp(const float *__restrict__ g, const float4 *__restrict__ q, int nb1,
+                                              int nb2, int d0, int d1, int d2, float px, float py, float pz,
+                                              bool &inb) {
     int x0, y0, z0;
     float fx, fy, fz;
     cell_of(px, x0, fx);
@@ -66,12 +83,20 @@ __device__ __forceinline__ float value_interp(const float *__restrict__ g, int d
     cell_of(pz, z0, fz);
     inb = (x0 >= 0) & (x0 + 1 < d0) & (y0 >= 0) & (y0 + 1 < d1) & (z0 >= 0) & (z0 + 1 < d2);
     if (!inb) return 1.0f;
-    const float *b = g + ((size_t)x0 * d1 + y0) * d2 + z0;
-    const size_t sx = (size_t)d1 * d2;
-    const float v000 = __ldg(b), v001 = __ldg(b + 1);
-    const float v010 = __ldg(b + d2), v011 = __ldg(b + d2 + 1);
-    const float v100 = __ldg(b + sx), v101 = __ldg(b + sx + 1);
-    const float v110 = __ldg(b + sx + d2), v111 = __ldg(b + sx + d2 + 1);
+    float v000, v001, v010, v011, v100, v101, v110, v111;
+    if (q) {   // two LDG.E.128
+        const float4 a = __ldg(q + quad_index(x0, y0, z0, nb1, nb2));
+        const float4 c = __ldg(q + quad_index(x0 + 1, y0, z0, nb1, nb2));
+        v000 = a.x; v001 = a.y; v010 = a.z; v011 = a.w;
+        v100 = c.x; v101 = c.y; v110 = c.z; v111 = c.w;
+    } else {
+        const float *b = g + ((size_t)x0 * d1 + y0) * d2 + z0;
+        const size_t sx = (size_t)d1 * d2;
+        v000 = __ldg(b); v001 = __ldg(b + 1);
+        v010 = __ldg(b + d2); v011 = __ldg(b + d2 + 1);
+        v100 = __ldg(b + sx); v101 = __ldg(b + sx + 1);
+        v110 = __ldg(b + sx + d2); v111 = __ldg(b + sx + d2 + 1);
+    }
     const float dx00 = lerp_ref(v000, v100, fx);
     const float dx01 = lerp_ref(v001, v101, fx);
     const float dx10 = lerp_ref(v010, v110, fx);
@@ -101,12 +126,13 @@ __device__ __forceinline__ void to_grid(const ObjRec &o, float x, float y, float
 
 // Value-only evaluation of one (point, object) pair: potential + collide flag (kernel.cu:147-171 without
 // the gradient).  Returns true if the 8-tap cell is in bounds.
-__device__ __forceinline__ bool pair_potential(const ObjRec &o, const float *__restrict__ grids, float x,
-                                               float y, float z, float &pot, float &col) {
+__device__ __forceinline__ bool pair_potential(const ObjRec &o, const float *__restrict__ grids, const QuadDesc &qd,
+                                               float x, float y, float z, float &pot, float &col) {
     float px, py, pz;
     to_grid(o, x, y, z, px, py, pz);
     bool inb;
-    const float v = value_interp(grids + o.grid_offset, o.d0, o.d1, o.d2, px, py, pz, inb);
+    const float v = value_interp(grids + o.grid_offset, qd.data ? qd.data + o.quad_offset : nullptr, qd.nb1, qd.nb2,
+                                 o.d0, o.d1, o.d2, px, py, pz, inb);
     col = (v < o.clr) ? 1.0f : 0.0f;
     if (v <= 0.0f) {
         pot = __fadd_rn(-v, __fmul_rn(0.5f, o.eps));
@@ -148,21 +174,24 @@ __device__ __forceinline__ void finish_pair(const ObjRec &o, float v, float fpx,
 }
 
 // Full evaluation by one thread: potential, world-frame potential gradient, collide flag (kernel.cu:147-180).
-__device__ __forceinline__ bool pair_full(const ObjRec &o, const float *__restrict__ grids, float x, float y,
-                                          float z, float &pot, float &gx, float &gy, float &gz, float &col) {
+__device__ __forceinline__ bool pair_full(const ObjRec &o, const float *__restrict__ grids, const QuadDesc &qd,
+                                          float x, float y, float z, float &pot, float &gx, float &gy, float &gz,
+                                          float &col) {
     float px, py, pz;
     to_grid(o, x, y, z, px, py, pz);
     const float *g = grids + o.grid_offset;
+    const float4 *q = qd.data ? qd.data + o.quad_offset : nullptr;
+    const int n1 = qd.nb1, n2 = qd.nb2;
     bool inb, dummy;
-    const float v = value_interp(g, o.d0, o.d1, o.d2, px, py, pz, inb);
+    const float v = value_interp(g, q, n1, n2, o.d0, o.d1, o.d2, px, py, pz, inb);
     float fpx = 0.f, fpy = 0.f, fpz = 0.f, fmx = 0.f, fmy = 0.f, fmz = 0.f;
     if (v <= o.eps) {   // kernel.cu:67-86: six re-interpolations (their result is unused when value > eps)
-        fpx = value_interp(g, o.d0, o.d1, o.d2, __fadd_rn(px, 1.0f), py, pz, dummy);
-        fpy = value_interp(g, o.d0, o.d1, o.d2, px, __fadd_rn(py, 1.0f), pz, dummy);
-        fpz = value_interp(g, o.d0, o.d1, o.d2, px, py, __fadd_rn(pz, 1.0f), dummy);
-        fmx = value_interp(g, o.d0, o.d1, o.d2, __fsub_rn(px, 1.0f), py, pz, dummy);
-        fmy = value_interp(g, o.d0, o.d1, o.d2, px, __fsub_rn(py, 1.0f), pz, dummy);
-        fmz = value_interp(g, o.d0, o.d1, o.d2, px, py, __fsub_rn(pz, 1.0f), dummy);
+        fpx = value_interp(g, q, n1, n2, o.d0, o.d1, o.d2, __fadd_rn(px, 1.0f), py, pz, dummy);
+        fpy = value_interp(g, q, n1, n2, o.d0, o.d1, o.d2, px, __fadd_rn(py, 1.0f), pz, dummy);
+        fpz = value_interp(g, q, n1, n2, o.d0, o.d1, o.d2, px, py, __fadd_rn(pz, 1.0f), dummy);
+        fmx = value_interp(g, q, n1, n2, o.d0, o.d1, o.d2, __fsub_rn(px, 1.0f), py, pz, dummy);
+        fmy = value_interp(g, q, n1, n2, o.d0, o.d1, o.d2, px, __fsub_rn(py, 1.0f), pz, dummy);
+        fmz = value_interp(g, q, n1, n2, o.d0, o.d1, o.d2, px, py, __fsub_rn(pz, 1.0f), dummy);
     }
     finish_pair(o, v, fpx, fpy, fpz, fmx, fmy, fmz, pot, gx, gy, gz, col);
     return inb;
@@ -172,11 +201,11 @@ __device__ __forceinline__ bool pair_full(const ObjRec &o, const float *__restri
 // within the group): lane l takes samples l, l+G, ... of the seven, the values are exchanged with shuffles and
 // every lane finishes redundantly.  G == 1 evaluates the six gradient samples only when value <= eps.
 template <int G>
-__device__ __forceinline__ void pair_full_group(const ObjRec &o, const float *__restrict__ grids, unsigned gm, int l,
-                                                float x, float y, float z, float &pot, float &gx, float &gy,
-                                                float &gz, float &col) {
+__device__ __forceinline__ void pair_full_group(const ObjRec &o, const float *__restrict__ grids, const QuadDesc &qd,
+                                                unsigned gm, int l, float x, float y, float z, float &pot, float &gx,
+                                                float &gy, float &gz, float &col) {
     if (G == 1) {
-        pair_full(o, grids, x, y, z, pot, gx, gy, gz, col);
+        pair_full(o, grids, qd, x, y, z, pot, gx, gy, gz, col);
         return;
     }
     float px, py, pz;
@@ -193,8 +222,8 @@ __device__ __forceinline__ void pair_full_group(const ObjRec &o, const float *__
             const float sy = (k == 2) ? 1.0f : ((k == 5) ? -1.0f : 0.0f);
             const float sz = (k == 3) ? 1.0f : ((k == 6) ? -1.0f : 0.0f);
             bool inb;
-            v[q] = value_interp(grids + o.grid_offset, o.d0, o.d1, o.d2, __fadd_rn(px, sx), __fadd_rn(py, sy),
-                                __fadd_rn(pz, sz), inb);
+            v[q] = value_interp(grids + o.grid_offset, qd.data ? qd.data + o.quad_offset : nullptr, qd.nb1, qd.nb2, o.d0,
+                                o.d1, o.d2, __fadd_rn(px, sx), __fadd_rn(py, sy), __fadd_rn(pz, sz), inb);
         }
     }
     float f[7];

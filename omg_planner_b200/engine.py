@@ -72,6 +72,12 @@ class ChompEngine(object):
                    "omgb_scene_set_sdf")
         self.num_objects = o
 
+    def set_sdf_layout(self, layout):
+        """0: the reference [O,X,Y,Z] layout (zero-copy); 1 / "quad": also keep the bricked quad copy (two 128-bit loads
+        per trilinear sample; bit-identical results; 4x the grid bytes).  Call between set_sdf and set_objects."""
+        code = {"plain": 0, "quad": 1}.get(layout, layout)
+        _lib.check(self.L.omgb_scene_set_sdf_layout(self._h, int(code), _stream()), "omgb_scene_set_sdf_layout")
+
     def set_objects(self, pose_inv, epsilons, padding_scales, clearances, disables):
         f = lambda a: np.ascontiguousarray(a, dtype=np.float32)
         pose_inv, epsilons, padding_scales, clearances, disables = map(
@@ -98,7 +104,7 @@ class ChompEngine(object):
         _lib.check(self.L.omgb_scene_set_options(self._h, int(use_lower_bound), int(use_longest_first)),
                    "omgb_scene_set_options")
 
-    def load_scene(self, scene, cfg):
+    def load_scene(self, scene, cfg, sdf_layout=None):
         """Upload a scene dict (omg_planner_b200.scene.make_scene layout) with the per-object parameters
         Cost.compute_obstacle_cost_layer would build (omg/cost.py:303-328)."""
         from .cost import se3_inverse_f32
@@ -106,6 +112,8 @@ class ChompEngine(object):
         grids = scene["sdf_grids"]
         grids = grids if torch.is_tensor(grids) else torch.from_numpy(grids)
         self.set_sdf(grids.to(self.device).contiguous(), scene["sdf_limits"])
+        if sdf_layout is not None:
+            self.set_sdf_layout(sdf_layout)
         num = len(scene["names"])
         poses = np.stack([se3_inverse_f32(scene["pose_mats"][i]) for i in range(num)])
         eps = np.full(num, cfg.epsilon, np.float32)

@@ -138,3 +138,30 @@ def test_persistent_plan_kernel_equals_per_iteration_launches(big):
     eng.plan(cfg, x3, _dev(st[sel]), _dev(en[sel]), _dev(tails[sel]), iters=iters)
     torch.cuda.synchronize()
     assert torch.equal(x3, x1[sel])
+
+
+@pytest.mark.parametrize("name", ["goalset_standoff_topk", "fixed_full"])
+def test_bricked_quad_layout_is_bit_identical(big, name):
+    """omgb_scene_set_sdf_layout(1): the exact path reads the bricked quad copy of the grids (two 128-bit loads per
+    trilinear sample) instead of the reference [O,X,Y,Z] layout; same taps, same lerps -> identical bits, in the
+    per-point phase (value only), the winners (7 samples) and the full-sum path, and in the goal-scoring kernel."""
+    sc, robot, xi, st, en, tails = big
+    mode = H.MODES[name]
+    outs = []
+    for layout in ("plain", "quad"):
+        cfg = ChompConfig(**mode)
+        from omg_planner_b200.engine import ChompEngine
+        eng = ChompEngine(robot=robot).load_scene(sc, cfg, sdf_layout=layout)
+        x = _dev(xi[:300])
+        rows = _dev(H.goal_rows_for(mode, tails[:300], en[:300])) if mode["goal_set_proj"] else None
+        infos = []
+        for it in range(4):
+            cfg.obstacle_weight, cfg.smoothness_weight, cfg.step_size = cfg.schedule(it + 1)
+            infos.append(eng.step(cfg, x, _dev(st[:300]), _dev(en[:300]), rows, want_grad=True))
+        goals = _dev(en[:7])
+        gc = eng.goal_costs(_dev(xi[:64]), 3, goals)
+        torch.cuda.synchronize()
+        outs.append((x.clone(), torch.stack([i["info"] for i in infos]), infos[-1]["grad"].clone(), gc.clone()))
+    for a, b in zip(outs[0], outs[1]):
+        assert torch.equal(a, b)
+    assert float(outs[0][1][..., 13].sum()) > 0    # non-zero potentials were evaluated
