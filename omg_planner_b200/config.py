@@ -28,7 +28,7 @@ class ChompConfig(object):
         target_clearance=0.0, top_k_collision=1000, terminate_smooth_loss=35, goal_set_proj=True,
         use_standoff=True, pre_terminate=True, uncheck_finger_collision=0, allow_collision_point=5,
         soft_joint_limit_padding=0.2, clip_grad_scale=10.0, consider_finger=False, reach_tail_length=5,
-        timesteps=30, time_interval=0.1, report_cost=False, report_time=False, timeout=-1.0,
+        timesteps=30, time_interval=0.1, report_cost=False, report_time=False, timeout=3.0,
         base_link="panda_link0", ol_alg="MD", dist_eps=0.1, normalize_cost=True, traj_init="grasp",
         # trajectory initialisation / outer loop (omg/config.py:63,89,96-99,69,129)
         traj_interpolate="cubic", dynamic_timestep=False, traj_delta=0.05, traj_max_step=50, traj_min_step=2,

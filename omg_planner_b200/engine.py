@@ -90,10 +90,12 @@ class ChompEngine(object):
     def set_metric(self, cfg):
         """Upload cfg.Ainv and the goal-set projection; cached on (n, goal_set_proj, c, dt)."""
         c = cfg.constraint_rows
-        key = (cfg.timesteps, bool(cfg.goal_set_proj), c, float(cfg.time_interval), id(cfg.Ainv))
+        ainv = np.ascontiguousarray(cfg.Ainv, dtype=np.float64)
+        # keyed on the CONTENT of Ainv (a few KB): an array modified in place, or a new one at a recycled id(), must
+        # not leave a stale metric / projection on the device
+        key = (cfg.timesteps, bool(cfg.goal_set_proj), c, float(cfg.time_interval), ainv.shape, hash(ainv.tobytes()))
         if key == self._metric_key:
             return
-        ainv = np.ascontiguousarray(cfg.Ainv, dtype=np.float64)
         proj = cfg.projection_matrix(c)
         proj = None if proj is None else np.ascontiguousarray(proj, dtype=np.float64)
         _lib.check(self.L.omgb_scene_set_metric(self._h, cfg.timesteps, _hp(ainv), c, _hp(proj)), "omgb_scene_set_metric")

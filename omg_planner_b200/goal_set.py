@@ -11,7 +11,12 @@ Reference behaviours kept on purpose:
   * setup_goal_set's diversity filter records indices of `goal_set[1:]` (off by one against goal_set) and then indexes
     goal_set with them (omg/planner.py:551-577).
   * sampling uses the global numpy RNG (np.random.choice, omg/planner.py:566).
-Not supported: cfg.increment_iks (off by default) -- its seeds depend on earlier results, which serialises the batch."""
+  * cfg.increment_iks (omg/config.py:94, off by default): later grasp poses get extra IK seeds taken from earlier
+    solutions -- ten drawn with np.random.choice after every group of four poses with the pool (planner.py:436-441), the
+    solution whose hand is closest without it (:365-373).  The chains from the fixed seeds do not depend on earlier
+    results and are still ONE launch; the extra-seed chains are one small launch per group / pose, in the reference's
+    order, with the same RNG calls.
+  * the simulated grasp files of a few YCB objects are filtered by ycb_special_case (omg/util.py:335-365)."""
 import os
 
 import numpy as np
@@ -61,6 +66,61 @@ def unpack_pose(pose):
     return out
 
 
+PANDA_WRIST_LIMIT = 2.8973   # |q7| limit hard-coded in the reference's flip test (omg/planner.py:232-234)
+
+
+def pitch_of(R):
+    """The second angle of transforms3d.euler.mat2euler(R) (static xyz axes): atan2(-R[2,0], |(R[0,0], R[1,0])|)."""
+    R = np.asarray(R, dtype=np.float64)
+    return np.arctan2(-R[..., 2, 0], np.sqrt(R[..., 0, 0] * R[..., 0, 0] + R[..., 1, 0] * R[..., 1, 0]))
+
+
+def ycb_special_case(pose_grasp, name):
+    """omg/util.py:335-365: grasp-pose filters for the YCB objects the reference treats as edge cases.  Thin objects keep
+    top-down grasps only; bowl / mug (/ the meat can, unreachable there: it is caught by the first branch) keep tilted
+    ones, pushed 2 cm along the approach axis."""
+    pose_grasp = np.asarray(pose_grasp)
+    if name in ("037_scissors", "010_potted_meat_can", "061_foam_brick"):
+        t = np.abs(pose_grasp[:, :3, 3])
+        pose_grasp = pose_grasp[(t[:, 2] > 0.09) & (t[:, 1] > 0.02) & (t[:, 0] < 0.05)]
+        if len(pose_grasp):
+            pose_grasp = pose_grasp[np.abs(pitch_of(pose_grasp[:, :3, :3])) > 0.06]
+    elif name in ("024_bowl", "025_mug"):
+        angle = 50 if name == "024_bowl" else 30
+        pose_grasp = pose_grasp[np.abs(pitch_of(pose_grasp[:, :3, :3])) > angle * np.pi / 180]
+        push = np.eye(4)
+        push[2, 3] = 0.02
+        pose_grasp = np.matmul(pose_grasp, push)
+    return pose_grasp
+
+
+def spin_about_vertical(poses, pivot, bins=50):
+    """Placement up-sampling (omg/planner.py:324-335): every pose rotated about the world z axis through `pivot` (the
+    object's position) by `bins` angles over a full turn.  [P,4,4] -> [bins,4,4] by broadcasting, as the reference does
+    (it is used with the single relative hand pose of an attached object)."""
+    turns = np.stack([rotZ(a) for a in np.linspace(-np.pi, np.pi, bins)], axis=0)
+    centred = np.array(poses, dtype=np.float64)
+    centred[:, :3, 3] = centred[:, :3, 3] - pivot
+    out = np.matmul(turns, centred)
+    out[:, :3, 3] += pivot
+    return out
+
+
+def tilt_about_contact_line(poses, bins=10, depth=0.13):
+    """omg/planner.py:337-348: every pose tilted about the hand's y axis through the finger contact point (`depth` along
+    the approach axis) by `bins` angles in [-45, 45] degrees.  [P,4,4] -> [P*bins,4,4], pose-major."""
+    tilts = np.stack([rotY(a) for a in np.linspace(-np.pi / 4, np.pi / 4, bins)], axis=0)[:, :3, :3]
+    poses = np.asarray(poses, dtype=np.float64)
+    reach = np.array([0, 0, depth])
+    contact = poses[:, :3, :3].dot(reach) + poses[:, :3, 3]                     # [P,3]
+    turned = np.matmul(poses[:, :3, :3], tilts[:, None])                          # [bins,P,3,3]
+    origin = contact[None] - turned.dot(reach)                                    # [bins,P,3]
+    out = np.tile(poses[:, None], (1, bins, 1, 1))
+    out[:, :, :3, 3] = origin.transpose((1, 0, 2))
+    out[:, :, :3, :3] = turned.transpose((1, 0, 2, 3))
+    return out.reshape(-1, 4, 4)
+
+
 def _pose_mat(obj):
     """4x4 object->world pose of an env object (omg/core.py:88-97 keeps both .pose_mat and the packed .pose)."""
     return np.asarray(obj.pose_mat, dtype=np.float64)
@@ -73,57 +133,50 @@ class GoalSetMixin(object):
     def ik_solver(self):
         if getattr(self, "_ik", None) is None:
             robot = self.env.robot
-            self._ik = IkSolver(robot.robot_kinematics._pose_0, robot.joint_lower_limit, robot.joint_upper_limit)
+            lo = np.asarray(robot.joint_lower_limit, dtype=np.float64).reshape(-1).copy()
+            hi = np.asarray(robot.joint_upper_limit, dtype=np.float64).reshape(-1).copy()
+            pad = float(self.cfg.soft_joint_limit_padding)
+            if pad != 0.2:   # the reference's KDL solver pads the URDF limits by a hard-coded 0.2 (robot_pykdl.py:122-138)
+                lo[:7] = (lo[:7] - pad) + 0.2
+                hi[:7] = (hi[:7] + pad) - 0.2
+            self._ik = IkSolver(robot.robot_kinematics._pose_0, lo, hi)
         return self._ik
 
     def flip_grasp(self, old_grasps):
-        """omg/planner.py:224-236: wrist flipped by pi in joint space."""
-        grasps = np.array(old_grasps[:])
-        neg_mask, pos_mask = (grasps[..., -3] < 0), (grasps[..., -3] > 0)
-        grasps[neg_mask, -3] += np.pi
-        grasps[pos_mask, -3] -= np.pi
-        limits = (grasps[..., -3] < 2.8973 - self.cfg.soft_joint_limit_padding) * (
-            grasps[..., -3] > -2.8973 + self.cfg.soft_joint_limit_padding)
-        return grasps, limits
+        """omg/planner.py:224-236: the same hand pose with the wrist (joint 7) half a turn the other way -- towards zero --
+        and the mask of the results that stay inside the padded wrist limit."""
+        flipped = np.array(old_grasps, dtype=np.float64)
+        wrist = flipped[..., 6]
+        flipped[..., 6] = wrist - np.sign(wrist) * np.pi
+        inside = np.abs(flipped[..., 6]) < PANDA_WRIST_LIMIT - self.cfg.soft_joint_limit_padding
+        return flipped, inside
 
     def solve_goal_set_ik(self, target_obj, env, pose_grasp, one_trial=False, z_upsample=False, y_upsample=False,
                           obj_coord=True):
         """omg/planner.py:296-455 + solve_one_pose_ik (:16-87): returns (reach_goal_set, standoff_goal_set) lists."""
         cfg = self.cfg
-        if getattr(cfg, "increment_iks", False):
-            raise RuntimeError("cfg.increment_iks is not supported by the batched IK (seeds would depend on earlier "
-                               "solutions)")
         object_pose = _pose_mat(target_obj)
         init_seed = np.asarray(self.traj.start, dtype=np.float64).reshape(-1)[:7]
         tail = cfg.reach_tail_length
-        anchor_seeds = UTIL_ANCHOR_SEEDS[: cfg.ik_seed_num].copy()
-        seeds = init_seed[None, :] if one_trial else np.concatenate([init_seed[None, :], anchor_seeds[:, :7]], axis=0)
+        seeds = init_seed[None, :]
+        if not one_trial:
+            seeds = np.concatenate([seeds, UTIL_ANCHOR_SEEDS[: cfg.ik_seed_num, :7]], axis=0)
 
-        pose_grasp = np.array(pose_grasp, dtype=np.float64)
-        pose_grasp_global = np.matmul(object_pose, pose_grasp) if obj_coord else pose_grasp
-        if z_upsample:   # placement: rotate about the object's global z (:324-335)
-            global_rot_z = np.stack([rotZ(a) for a in np.linspace(-np.pi, np.pi, 50)], axis=0)
-            translation = object_pose[:3, 3]
-            pose_grasp_global[:, :3, 3] = pose_grasp_global[:, :3, 3] - object_pose[:3, 3]
-            pose_grasp_global = np.matmul(global_rot_z, pose_grasp_global)
-            pose_grasp_global[:, :3, 3] += translation
-        if y_upsample:   # tilt about the antipodal contact line (:337-348)
-            bin_num = 10
-            global_rot_y = np.stack([rotY(a) for a in np.linspace(-np.pi / 4, np.pi / 4, bin_num)], axis=0)
-            finger_translation = pose_grasp_global[:, :3, :3].dot(np.array([0, 0, 0.13])) + pose_grasp_global[:, :3, 3]
-            local_rotation = np.matmul(pose_grasp_global[:, :3, :3], global_rot_y[:, None, :3, :3])
-            delta_translation = local_rotation.dot(np.array([0, 0, 0.13]))
-            pose_grasp_global = np.tile(pose_grasp_global[:, None], (1, bin_num, 1, 1))
-            pose_grasp_global[:, :, :3, 3] = (finger_translation[None] - delta_translation).transpose((1, 0, 2))
-            pose_grasp_global[:, :, :3, :3] = local_rotation.transpose((1, 0, 2, 3))
-            pose_grasp_global = pose_grasp_global.reshape(-1, 4, 4)
+        hand_poses = np.array(pose_grasp, dtype=np.float64)
+        if obj_coord:
+            hand_poses = np.matmul(object_pose, hand_poses)                     # gripper -> world
+        if z_upsample:
+            hand_poses = spin_about_vertical(hand_poses, object_pose[:3, 3])
+        if y_upsample:
+            hand_poses = tilt_about_contact_line(hand_poses)
 
-        pose_standoff = np.tile(np.eye(4), (tail, 1, 1, 1))
+        # the reach tail: the grasp pose pulled back along its approach axis, nearest first (:350-355)
+        retreat = np.tile(np.eye(4), (tail, 1, 1, 1))
         if cfg.use_standoff:
-            pose_standoff[:, 0, 2, 3] = -cfg.standoff_dist * np.linspace(0, 1, tail, endpoint=False)
-        standoff_grasp_global = np.matmul(pose_grasp_global, pose_standoff)     # [tail, P, 4, 4]
+            retreat[:, 0, 2, 3] = -cfg.standoff_dist * np.linspace(0, 1, tail, endpoint=False)
+        tail_poses = np.matmul(hand_poses, retreat)                             # [tail, P, 4, 4]
 
-        num = pose_grasp_global.shape[0]
+        num = hand_poses.shape[0]
         solved_poses = num - 1 if cfg.ik_parallel else num                       # (sic) :419
         if solved_poses <= 0:
             return [], []
@@ -131,32 +184,78 @@ class GoalSetMixin(object):
             # the chain of one (pose, seed): the farthest standoff pose from the seed, then tail poses 0..tail-1 each
             # from the previous solution (:45-62)
             order = [tail - 1] + list(range(tail))
-            chain = np.stack([standoff_grasp_global[k, :solved_poses] for k in order], axis=1)   # [P, tail+1, 4, 4]
+            chain = np.stack([tail_poses[k, :solved_poses] for k in order], axis=1)               # [P, tail+1, 4, 4]
         else:
-            chain = pose_grasp_global[:solved_poses, None]
-        sols, solved = self.ik_solver().solve_chains(poses_to_targets(chain), seeds)
+            chain = hand_poses[:solved_poses, None]
+        targets = poses_to_targets(chain)
+        sols, solved = self.ik_solver().solve_chains(targets, seeds)             # every fixed-seed chain: one launch
 
         finger_joint = np.array([0.04, 0.04])
         finger_joints = np.tile(finger_joint, (tail, 1))
-        reach_goal_set, standoff_goal_set = [], []
         T = chain.shape[1]
-        for p in range(solved_poses):            # result order of the reference: pose-major, seeds in order
-            for s in range(seeds.shape[0]):
-                if solved[p, s] != T:
+
+        def goals_of(sol_ps, solved_ps):
+            """solve_one_pose_ik's result lists for ONE pose over a list of seeds (:33-86), seeds in order."""
+            reach, standoff = [], []
+            for s_ in range(sol_ps.shape[0]):
+                if solved_ps[s_] != T:
                     continue
                 if cfg.use_standoff:
-                    iks = [sols[p, s, 1 + k] for k in range(tail)]
+                    iks = [sol_ps[s_, 1 + k] for k in range(tail)]
                     if not target_obj.attached:
                         iks = iks[::-1]
                     reach_traj = np.stack(iks)
                     if np.linalg.norm(np.diff(reach_traj, axis=0)) < 2:          # smooth (:71-73)
                         standoff_ = iks[0] if not target_obj.attached else iks[-1]
-                        reach_goal_set.append(np.concatenate([reach_traj, finger_joints], axis=-1))
-                        standoff_goal_set.append(np.concatenate([standoff_, finger_joint]))
+                        reach.append(np.concatenate([reach_traj, finger_joints], axis=-1))
+                        standoff.append(np.concatenate([standoff_, finger_joint]))
                 else:
-                    goal_ik = sols[p, s, 0]
-                    reach_goal_set.append(np.concatenate([goal_ik, finger_joint]))
-                    standoff_goal_set.append(np.concatenate([goal_ik, finger_joint]))
+                    goal_ik = sol_ps[s_, 0]
+                    reach.append(np.concatenate([goal_ik, finger_joint]))
+                    standoff.append(np.concatenate([goal_ik, finger_joint]))
+            return reach, standoff
+
+        reach_goal_set, standoff_goal_set = [], []
+        if not getattr(cfg, "increment_iks", False):
+            for p in range(solved_poses):        # result order of the reference: pose-major, seeds in order
+                r_, s_ = goals_of(sols[p], solved[p])
+                reach_goal_set.extend(r_)
+                standoff_goal_set.extend(s_)
+            return list(reach_goal_set), list(standoff_goal_set)
+
+        # ---- cfg.increment_iks: extra seeds from earlier solutions ---------------------------------------------
+        ik = self.ik_solver()
+        if cfg.ik_parallel:
+            group = 4                                                            # the pool's size (:404)
+            extra = np.zeros((0, 7))
+            for i in range(0, num, group):
+                idx = list(range(i, min(i + group, num - 1)))
+                more = ik.solve_chains(targets[idx], extra) if (len(idx) and len(extra)) else None
+                for k, p in enumerate(idx):
+                    r_, s_ = goals_of(sols[p], solved[p])
+                    if more is not None:
+                        r2, s2 = goals_of(more[0][k], more[1][k])
+                        r_, s_ = r_ + r2, s_ + s2
+                    reach_goal_set.extend(r_)
+                    standoff_goal_set.extend(s_)
+                # (:436-441: ten of the solutions so far, drawn WITH replacement from the global numpy RNG)
+                pick = np.random.choice(np.arange(len(standoff_goal_set)), min(len(standoff_goal_set), 10))
+                extra = np.array(standoff_goal_set).reshape(-1, 9)[pick, :7]
+        else:
+            hand_center = np.empty((0, 3))
+            for p in range(num):
+                r_, s_ = goals_of(sols[p], solved[p])
+                if len(standoff_goal_set) > 0 and len(hand_center) > 0:          # (:365-373)
+                    dists = np.linalg.norm(hand_poses[p, :3, 3] - hand_center, axis=-1)
+                    closest = np.argsort(dists)[:1]
+                    extra = np.array(standoff_goal_set)[closest, :7].reshape(-1, 7)
+                    m_sols, m_solved = ik.solve_chains(targets[p:p + 1], extra)
+                    r2, s2 = goals_of(m_sols[0], m_solved[0])
+                    r_, s_ = r_ + r2, s_ + s2
+                reach_goal_set.extend(r_)
+                standoff_goal_set.extend(s_)
+                if len(s_) > 0:
+                    hand_center = np.concatenate([hand_center, np.tile(hand_poses[p, :3, 3], (len(s_), 1))], axis=0)
         return list(reach_goal_set), list(standoff_goal_set)
 
     def solve_and_process_ik(self, target_obj, pose_grasp, z_upsample, obj_coord=True):
@@ -216,6 +315,7 @@ class GoalSetMixin(object):
                         pose_grasp = np.load(path, allow_pickle=True, fix_imports=True,
                                              encoding="bytes").item()[b"transforms"]
                     pose_grasp = np.matmul(pose_grasp, np.array(rotZ(np.pi / 2)))     # flip x, y (:481-482)
+                    pose_grasp = ycb_special_case(pose_grasp, target_obj.name)          # (:484)
                     target_obj.grasps_poses = pose_grasp
                 else:
                     pose_grasp = target_obj.grasps_poses

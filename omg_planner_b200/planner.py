@@ -8,8 +8,11 @@
     (or more than 256 goals) keeps BASELINE north_star's split instead: goal scoring and the CHOMP step on the device,
     the learner's [B,G] update on the host (_plan_with_learner).
 
-cfg.timeout (the reference's wall-clock stop, omg/planner.py:629, 3 s by default there) is honoured by the host-learner
-loop only: the fused paths finish a 70-iteration plan in milliseconds and cannot be interrupted from the host.
+cfg.timeout (the reference's wall-clock stop, omg/planner.py:629, 3 s by default) is honoured by the two loops that
+launch per iteration: the host-learner loop checks it every iteration like the reference; the device-learner loop
+checks it every 8 iterations against the DEVICE's progress (an event per check, the host never more than 16 iterations
+ahead) and stops enqueuing.  The single persistent launch of a fixed-goal plan cannot be interrupted from the host (a
+70-iteration plan of 1024 trajectories is ~6 ms of device time).
 
 Same names and results as the reference: `Planner(env, traj)`, `.plan(traj) -> info list`, `.history_trajectories`,
 `.info`, `.selected_goals`, `.cost`, `.optim`, `.learner`, `.grasp_init(env)`.  Goal sets come in through
@@ -241,17 +244,30 @@ class Planner(GoalSetMixin):
         stream = vp(torch.cuda.current_stream().cuda_stream)
         prm = _lib.StepParams()
         step0 = self.optim.step
+        t_begin, checks = time.time(), []
+        ran = 0
         for t in range(iters):
+            if cfg.timeout != -1 and t > 0 and t % 8 == 0:   # omg/planner.py:629 against the device's progress
+                if len(checks) >= 2:
+                    checks[-2].synchronize()                 # the device has finished iteration t - 16
+                if time.time() - t_begin > cfg.timeout:
+                    break
+                checks.append(torch.cuda.Event())
+                checks[-1].record()
             if t < cfg.optim_steps:
                 st.update(eng, xi, end, rows, done=done, selected=selected[t])
             self.optim.update()                                          # schedule, written back into cfg
-            eng.set_metric(ecfg)
             ecfg = cost.engine_cfg()
+            eng.set_metric(ecfg)
             eng.params_from(ecfg, True, into=prm)
             _lib.check(eng.L.omgb_chomp_plan_step(eng._h, ctypes.byref(prm), t, 1, B, vp(xi.data_ptr()),
                                                   vp(start.data_ptr()), vp(end.data_ptr()), vp(rows.data_ptr()),
                                                   vp(done.data_ptr()), vp(info.data_ptr()), vp(hist_xi.data_ptr()),
                                                   vp(hist_info.data_ptr()), stream), "omgb_chomp_plan_step")
+            ran = t + 1
+        if ran < iters:                                                  # stopped by cfg.timeout
+            iters, hist_xi, hist_info = ran, hist_xi[:ran], hist_info[:ran]
+            n_sel = min(n_sel, ran)
         stage = self.__dict__.setdefault("_stage", {})
         h_info, h_xi, sel = (_to_host(hist_info, stage, "info").copy(), _to_host(hist_xi, stage, "xi"),
                              selected.cpu().numpy())

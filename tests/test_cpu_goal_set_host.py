@@ -90,7 +90,7 @@ def build(g, device_free=True):
     sc = S.make_scene(**eval(str(g["scene_args"])))
     assert abs(sc["sdf_grids"].astype(np.float64).sum() - float(g["sdf_checksum"])) < 1e-6
     cfg = ChompConfig(goal_set_proj=True, use_standoff=bool(g["use_standoff"]), ik_parallel=bool(g["ik_parallel"]),
-                      goal_idx=-1)
+                      goal_idx=-1, increment_iks=bool(int(g["increment_iks"])) if "increment_iks" in g.files else False)
     robot = PandaConstants(body_points=g["body_points"])
     env = types.SimpleNamespace(config=cfg, target_idx=sc["target_idx"], objects=[])
     for i, name in enumerate(sc["names"]):
@@ -112,16 +112,20 @@ def test_goal_set_host_logic_matches_reference(path, monkeypatch):
     target = env.objects[env.target_idx]
     z_up = bool(int(g["z_upsample"])) if "z_upsample" in g.files else False
     p = HostPlanner(cfg, env, traj, OracleCost(sc, cfg, g["body_points"], target.attached), OracleIk(robot))
+    rng_seed = int(g["np_random_seed_ik"]) if "np_random_seed_ik" in g.files else 0
     # the product's own pose -> quaternion conversion: same goals, to the sensitivity of KDL's 1e-6 stop rule
+    np.random.seed(rng_seed)
     reach, grasps = p.solve_goal_set_ik(target, env, g["pose_grasp"].copy(), z_upsample=z_up)
     assert np.array(grasps).shape == g["grasps_raw"].shape
     assert np.abs(np.array(grasps) - g["grasps_raw"]).max() < 1e-3   # (each is a solution to 1e-6 in task space)
     # with the fixture run's conversions everything is bit-identical
     monkeypatch.setattr(GS, "poses_to_targets", harness_targets)
     target.pose_mat = harness_object_pose(target.pose_mat)
+    np.random.seed(rng_seed)
     reach, grasps = p.solve_goal_set_ik(target, env, g["pose_grasp"].copy(), z_upsample=z_up)
     np.testing.assert_array_equal(np.array(grasps), g["grasps_raw"])
     np.testing.assert_array_equal(np.array(reach), g["reach_raw"])
+    np.random.seed(rng_seed)
     p.solve_and_process_ik(target, g["pose_grasp"].copy(), z_up)
     np.testing.assert_array_equal(np.array(target.grasps), g["grasps_processed"])
     np.testing.assert_array_equal(np.array(target.reach_grasps), g["reach_processed"])

@@ -8,9 +8,10 @@ through the Planner mirror, against
 Tolerances.  KDL's Newton iteration stops as soon as every twist component is below 1e-6, so a returned solution is
 defined only up to that tolerance divided by the arm's conditioning: the reference itself moves by up to ~2e-4 rad
 when its input changes by one ulp (tests/test_cpu_goal_set_host.py).  The device code runs the same operations but
-CUDA's sin/cos/acos differ from glibc's in the last bit, so joint solutions are compared at 1e-3 rad with the median
-required below 1e-8, while the contract that does not depend on the path -- FK(solution) reaches the target within
-KDL's tolerance, inside the joint limits -- is asserted for every solution."""
+CUDA's sin/cos/acos differ from glibc's in the last bit.  The bars asserted are the measured ones: solved / unsolved
+status agreement >= 99.5 %, joint solutions median < 1e-8 rad and 99th percentile <= 1e-5 rad, finished goal sets
+within 1e-4 rad (the north-star bar); the contract that does not depend on the path -- FK(solution) reaches the target
+within KDL's tolerance, inside the joint limits -- is asserted for every solution."""
 import glob
 import os
 import types
@@ -56,8 +57,8 @@ def test_ik_matches_reference_kdl_fixture():
     d = np.abs(sols[:, :, 0] - g["sols"]).max(-1)[both]
     print("status agreement %.4f; both solved %d; |dq| median %.2e p99 %.2e max %.2e" % (
         agree, both.sum(), np.median(d), np.percentile(d, 99), d.max()))
-    assert agree >= 0.98
-    assert np.median(d) < 1e-8 and (d < 1e-3).mean() >= 0.97
+    assert agree >= 0.995
+    assert np.median(d) < 1e-8 and np.percentile(d, 99) <= 1e-5 and (d < 1e-4).mean() >= 0.995
     for p, s in np.argwhere(ok_gpu):
         q = sols[p, s, 0]
         perr, aerr = _twist_error(chain, q, g["targets"][p])
@@ -102,8 +103,8 @@ def test_ik_chains_large_batch_vs_oracle():
     d = np.abs(sols - s_ref).max(axis=(-2, -1))[full]
     print("chains %d; solved-count agreement %.4f; fully solved by both %d; |dq| median %.2e p99 %.2e" % (
         P * Sd, agree, full.sum(), np.median(d), np.percentile(d, 99)))
-    assert agree >= 0.97 and full.sum() > 100
-    assert np.median(d) < 1e-8 and (d < 1e-3).mean() >= 0.95
+    assert agree >= 0.995 and full.sum() > 100
+    assert np.median(d) < 1e-8 and np.percentile(d, 99) <= 1e-5 and (d < 1e-4).mean() >= 0.995
     for p, s in np.argwhere(solved == T)[::7]:
         for t in range(T):
             perr, aerr = _twist_error(chain, sols[p, s, t], targets[p, t])
@@ -114,7 +115,8 @@ def test_ik_chains_large_batch_vs_oracle():
 def _env_for(g):
     sc = S.make_scene(**eval(str(g["scene_args"])))
     cfg = ChompConfig(goal_set_proj=True, use_standoff=bool(g["use_standoff"]), ik_parallel=bool(g["ik_parallel"]),
-                      goal_idx=-1, ol_alg="Baseline")
+                      goal_idx=-1, ol_alg="Baseline",
+                      increment_iks=bool(int(g["increment_iks"])) if "increment_iks" in g.files else False)
     robot = PandaConstants(body_points=g["body_points"])
     env = H.make_env(sc, cfg, robot)
     for i, o in enumerate(env.objects):
@@ -139,9 +141,10 @@ def test_goal_set_construction_matches_reference(path):
         cfg.z_upsample = bool(int(g["z_upsample"]))
     else:
         target.grasps_poses = g["pose_grasp"].copy()
+    np.random.seed(int(g["np_random_seed_ik"]) if "np_random_seed_ik" in g.files else 0)
     planner.load_grasp_set(env)      # batched IK -> flip augmentation -> hand-rotation filter
     assert np.array(target.grasps).shape == g["grasps_processed"].shape
-    assert np.abs(np.array(target.grasps) - g["grasps_processed"]).max() < 1e-3
+    assert np.abs(np.array(target.grasps) - g["grasps_processed"]).max() <= 1e-4
     np.random.seed(int(g["np_random_seed"]))
     planner.setup_goal_set(env)      # collision filter (fused batch_obstacle_cost), diversity filter, sampling
     planner.grasp_init(env)
@@ -149,12 +152,12 @@ def test_goal_set_construction_matches_reference(path):
     assert grasps.shape == g["grasps_final"].shape and reach.shape == g["reach_final"].shape
     d = np.abs(grasps - g["grasps_final"]).max(-1)
     print("final goals %d; |dq| median %.2e max %.2e" % (len(d), np.median(d), d.max()))
-    assert np.median(d) < 1e-8 and d.max() < 1e-3
-    assert np.abs(reach - g["reach_final"]).max() < 1e-3
+    assert np.median(d) < 1e-8 and d.max() <= 1e-4
+    assert np.abs(reach - g["reach_final"]).max() <= 1e-4
     np.testing.assert_allclose(np.array(target.grasp_potentials), g["potentials_final"], rtol=2e-3, atol=1e-5)
     assert traj.goal_idx == int(g["goal_idx"])
-    assert np.abs(traj.end - g["end"]).max() < 1e-3
-    assert np.abs(traj.data - g["xi0"]).max() < 1e-3
+    assert np.abs(traj.end - g["end"]).max() <= 1e-4
+    assert np.abs(traj.data - g["xi0"]).max() <= 1e-4
     # and the plan runs from there
     from omg_planner_b200.online_learner import Learner
     planner.learner = Learner(env, traj, planner.cost)
@@ -172,8 +175,8 @@ def test_raw_ik_goal_lists_and_pool_quirk():
     planner = Planner(env, traj)
     reach, grasps = planner.solve_goal_set_ik(target, env, g["pose_grasp"].copy())
     assert np.array(grasps).shape == g["grasps_raw"].shape
-    assert np.abs(np.array(grasps) - g["grasps_raw"]).max() < 1e-3
-    assert np.abs(np.array(reach) - g["reach_raw"]).max() < 1e-3
+    assert np.abs(np.array(grasps) - g["grasps_raw"]).max() <= 1e-4
+    assert np.abs(np.array(reach) - g["reach_raw"]).max() <= 1e-4
     cfg.ik_parallel = False
     reach_all, grasps_all = planner.solve_goal_set_ik(target, env, g["pose_grasp"].copy())
     assert len(grasps_all) >= len(grasps)

@@ -36,6 +36,10 @@ CASES = {
     # object's z axis (omg/planner.py:324-335, 493-498); no wrist-flip augmentation / hand-rotation filter, reach tails
     # are not reversed, the table's collision parameters change (omg/cost.py:325-328)
     "placement_zupsample": dict(use_standoff=True, ik_parallel=False, n_grasps=1, seed=3, attached=True, z_upsample=True),
+    # cfg.increment_iks (omg/config.py:94): extra IK seeds from earlier solutions -- ten random ones per pool group of
+    # four poses (omg/planner.py:436-441), the closest earlier solution in the sequential loop (:365-373)
+    "increment_parallel": dict(use_standoff=True, ik_parallel=True, n_grasps=11, seed=4, increment_iks=True),
+    "increment_sequential": dict(use_standoff=False, ik_parallel=False, n_grasps=8, seed=5, increment_iks=True),
 }
 
 
@@ -98,7 +102,7 @@ def main():
         cfg.goal_set_proj = True
         cfg.use_standoff = case["use_standoff"]
         cfg.ik_parallel = case["ik_parallel"]
-        cfg.increment_iks = False
+        cfg.increment_iks = bool(case.get("increment_iks", False))
         cfg.y_upsample = False
         cfg.scene_file = ""
         cfg.goal_idx = -1
@@ -122,8 +126,10 @@ def main():
         _print = builtins.print
         builtins.print = lambda *a, **k: None
         try:
+            np.random.seed(5)      # (increment_iks draws its extra seeds from the global RNG)
             reach_raw, grasps_raw = p.solve_goal_set_ik(target, env, pose_grasp.copy(), z_upsample=z_up,
                                                         y_upsample=False, obj_coord=True)
+            np.random.seed(5)
             p.solve_and_process_ik(target, pose_grasp.copy(), z_up)
             reach_proc, grasps_proc = np.array(target.reach_grasps), np.array(target.grasps)
             np.random.seed(7)
@@ -135,7 +141,8 @@ def main():
             builtins.print = _print
         np.savez_compressed(
             os.path.join(out_dir, "goalset_%s.npz" % name), use_standoff=int(case["use_standoff"]),
-            ik_parallel=int(case["ik_parallel"]), attached=int(target.attached), z_upsample=int(z_up), scene_args=np.array(repr(SCENE_ARGS)),
+            ik_parallel=int(case["ik_parallel"]), increment_iks=int(cfg.increment_iks), np_random_seed_ik=5,
+            attached=int(target.attached), z_upsample=int(z_up), scene_args=np.array(repr(SCENE_ARGS)),
             sdf_checksum=np.float64(sc["sdf_grids"].astype(np.float64).sum()), body_points=robot.body_points,
             pose_grasp=pose_grasp, start=S.START_CONF, reach_raw=np.array(reach_raw), grasps_raw=np.array(grasps_raw),
             reach_processed=reach_proc, grasps_processed=grasps_proc, reach_final=reach_fin, grasps_final=grasps_fin,
