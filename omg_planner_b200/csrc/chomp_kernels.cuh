@@ -733,6 +733,7 @@ __device__ __forceinline__ void chomp_iteration(const StepArgs &a, unsigned char
     const int sub = lane / LPI, pl = lane % LPI;  // which instance of the warp, which body point
     const unsigned gmask = (LPI == 32) ? 0xffffffffu : (0xffffu << (sub * 16));
     const bool finger_soft = (prm.uncheck_finger_collision == -1);
+    const int jmax = (topk_mode && !prm.consider_finger) ? NL - 2 : NL;   // links that count towards cost / gradient
     int t_nnz = 0, t_col = 0, t_exact = 0;
     double t_cost = 0.0;
     for (int base = warp * GPW; base < n_act; base += nwarps * GPW) {
@@ -798,6 +799,15 @@ __device__ __forceinline__ void chomp_iteration(const StepArgs &a, unsigned char
             if (have && pl == 0 && mx != 0u) {
                 s_best[li] = __uint_as_float(mx);
                 s_bestp[li] = (unsigned char)((31 - __clz(bal)) - sub * LPI);
+            }
+            // c * |v| of every non-zero point: it IS the obstacle cost when at most k points are non-zero (the usual
+            // case: every non-zero point is a member, cost.py:390-397); otherwise phase 4a sums the members
+            if (live && pot > 0.0f && j < jmax) {
+                const double *Fp = (i > 0) ? (F - NL * 12) : (s_frames + ((size_t)n * NL + j) * 12);
+                double xp, yp, zp;
+                xform(Fp, bp[0], bp[1], bp[2], xp, yp, zp);
+                const double vx = (X - xp) * inv_dt, vy = (Y - yp) * inv_dt, vz = (Z - zp) * inv_dt;
+                t_cost += (double)pot * sqrt(vx * vx + vy * vy + vz * vz);
             }
         } else {
             // full-sum mode: functional gradient of every point with non-zero potential, reduced over
@@ -906,10 +916,10 @@ __device__ __forceinline__ void chomp_iteration(const StepArgs &a, unsigned char
             tau = prefix;   // ties at tau are all kept (reference: unstable argsort, order undefined)
         }
         OMGB_PROF(6);
-        // ---- phase 4a: obstacle cost = sum over members of c*|v| (cost.py:30,416), links 0..7 ---------
-        const int jmax = prm.consider_finger ? NL : NL - 2;
+        // ---- phase 4a: obstacle cost = sum over members of c*|v| (cost.py:30,416), links 0..7; only when more than
+        // k points are non-zero (else the points phase has summed it already) ---------
         double acc = 0.0;
-        if (nnz > 0) {
+        if (nnz > K) {
             for (int k = tid; k < n_act * LPI; k += nthr) {
                 const int li = s_act[k / LPI], p = k % LPI;
                 const int i = li / NL, j = li - i * NL;
@@ -948,7 +958,7 @@ __device__ __forceinline__ void chomp_iteration(const StepArgs &a, unsigned char
         }
         double red1[1] = {acc};
         block_sum_n<1>(red1, s_red);
-        obs_sum = red1[0] * (double)n;   // added to every waypoint row (SURVEY A-3)
+        obs_sum = ((nnz > K) ? red1[0] : red4[3]) * (double)n;   // added to every waypoint row (SURVEY A-3)
         for (int k = tid; k < n * NLU * NS; k += nthr) s_lg[k] = 0.0;
         __syncthreads();
         OMGB_PROF(7);

@@ -891,7 +891,7 @@ static int launch_step(omgb_scene *s, const StepArgs &a_in, cudaStream_t st, con
     // CTA shape by how many CTAs of this footprint fit in an SM's 228 KB (+1 KB reserved each): three 320-thread CTAs
     // for the usual 30-waypoint trajectory, two of 512 threads for 50-60 waypoints, one of 1024 beyond, so that ~30
     // warps stay resident per SM either way.  OMGB_STEP_CONFIG = 0 / 1 / 2 / 3 forces 320x3 / 512x2 / 1024x1 / 256x4.
-    static const int shape_threads[4] = {320, 512, 1024, 256}, shape_ctas[4] = {3, 2, 1, 4};
+    static const int shape_threads[6] = {320, 512, 1024, 256, 192, 256}, shape_ctas[6] = {3, 2, 1, 4, 4, 3};
     auto layout_for = [&](int cfg) {
         return make_layout(n, c, lpi, s->num_objects, s->p, shape_threads[cfg] / 32, topk, fing);
     };
@@ -900,7 +900,7 @@ static int launch_step(omgb_scene *s, const StepArgs &a_in, cudaStream_t st, con
         return L.total <= (size_t)s->smem_optin && (size_t)shape_ctas[cfg] * (L.total + 1024u) <= 228u * 1024u;
     };
     int cfg = step_config();
-    if (cfg < 0 || cfg > 3 || !fits(cfg)) {
+    if (cfg < 0 || cfg > 5 || !fits(cfg)) {
         // (256x4 fits a 30-waypoint trajectory too; measured with a cold L2 it is slower than 320x3 -- 0.121 vs 0.117 ms
         // per step of 1024 trajectories: the per-trajectory critical path grows -- and faster with a warm one)
         cfg = (lpi == 16 && fits(0)) ? 0 : fits(1) ? 1 : 2;
@@ -908,7 +908,7 @@ static int launch_step(omgb_scene *s, const StepArgs &a_in, cudaStream_t st, con
         if (a0.batch <= s->num_sms) cfg = 2;
         else if (a0.batch <= 2 * s->num_sms && (cfg == 0 || cfg == 3)) cfg = 1;
     }
-    if (lpi == 32 && (cfg == 0 || cfg == 3)) cfg = 1;
+    if (lpi == 32 && (cfg == 0 || cfg >= 3)) cfg = 1;
     const SmemLayout L = layout_for(cfg);
     if (L.total > (size_t)s->smem_optin)
         return fail(OMGB_ERR_UNSUPPORTED, "trajectory too long for one CTA's shared memory");
@@ -958,6 +958,8 @@ static int launch_step(omgb_scene *s, const StepArgs &a_in, cudaStream_t st, con
     int rc_ = OMGB_OK;
     if (lpi == 16) {
         if (cfg == 3) rc_ = launch_cfg<16, 256, 4>(a, L.total, st, plan, s->num_sms);
+        else if (cfg == 4) rc_ = launch_cfg<16, 192, 4>(a, L.total, st, plan, s->num_sms);
+        else if (cfg == 5) rc_ = launch_cfg<16, 256, 3>(a, L.total, st, plan, s->num_sms);
         else if (cfg == 0) rc_ = launch_cfg<16, 320, 3>(a, L.total, st, plan, s->num_sms);
         else if (cfg == 1) rc_ = launch_cfg<16, 512, 2>(a, L.total, st, plan, s->num_sms);
         else rc_ = launch_cfg<16, 1024, 1>(a, L.total, st, plan, s->num_sms);
