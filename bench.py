@@ -172,15 +172,24 @@ def run_b200(a):
 
     torch.cuda.set_device(local)
     nccl_log = None
+    json_fd = None
     if world > 1:
-        # NCCL's INFO log goes to a per-rank file (stdout carries the one JSON line); rank 0 copies its init lines to
-        # stderr and into the JSON line ("nccl") so that the communicator size is checkable.
-        os.environ.setdefault("NCCL_DEBUG", "INFO")
-        os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT,ENV")
-        if "NCCL_DEBUG_FILE" not in os.environ:
-            os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-            os.environ["NCCL_DEBUG_FILE"] = os.path.join(ROOT, "gpurun_out", "nccl_n%d_rank%%h_%%p.log" % world)
-        nccl_log = os.environ["NCCL_DEBUG_FILE"]
+        # NCCL logs to stdout, which must carry only the one JSON line: from here on fd 1 is stderr (NCCL's INFO lines
+        # stay visible to whoever captures the run) and the JSON line is written to the saved stdout at the end.
+        # Unless the caller configured NCCL's logging, INFO/INIT is switched on and also written to a per-rank file that
+        # rank 0 summarises into the JSON line ("nccl": communicator size, transport lines).
+        sys.stdout.flush()
+        json_fd = os.dup(1)
+        os.dup2(2, 1)
+        if "NCCL_DEBUG" not in os.environ:
+            os.environ["NCCL_DEBUG"] = "INFO"
+            os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
+            if "NCCL_DEBUG_FILE" not in os.environ:
+                import tempfile
+                os.environ["NCCL_DEBUG_FILE"] = os.path.join(tempfile.gettempdir(), "omgb_nccl_n%d_%%h_%%p.log" % world)
+        nccl_log = os.environ.get("NCCL_DEBUG_FILE")
+        print("rank %d: NCCL_DEBUG=%s NCCL_DEBUG_SUBSYS=%s NCCL_DEBUG_FILE=%s" % (
+            rank, os.environ.get("NCCL_DEBUG"), os.environ.get("NCCL_DEBUG_SUBSYS"), nccl_log), file=sys.stderr)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     cfg = ChompConfig(timesteps=a.waypoints, **mode)
     robot = PandaConstants()
@@ -211,8 +220,14 @@ def run_b200(a):
             timed_events[1].record()
         return out
 
-    for _ in range(max(a.warmup, 3)):
-        one_step()
+    # warm-up = the timed loop's exact allocation pattern (the previous step's outputs still alive, the P_in sums):
+    # a cudaMalloc by torch's caching allocator inside a timed step would stall the device for milliseconds
+    wev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(max(a.warmup, 3))]
+    wpins = []
+    for k in range(len(wev)):
+        out = one_step(wev[k])
+        wpins.append(out["info"][:, 12].sum())
+    del wev, wpins
     barrier()
     from omg_planner_b200 import _lib
     launches0 = int(_lib.lib().omgb_launch_count())
@@ -339,7 +354,6 @@ def run_b200(a):
     configs = None
     if a.configs:
         del flush
-        torch.cuda.empty_cache()
         sys.path.insert(0, os.path.join(ROOT, "tools"))
         import bench_configs
         which = tuple("config" + c.strip() for c in a.configs.split(",") if c.strip())
@@ -394,7 +408,7 @@ def run_b200(a):
         line["cpu_baseline"] = cpu
     if configs is not None:
         line["configs"] = configs
-    if nccl_log is not None:
+    if world > 1:
         line["nccl"] = nccl_summary(nccl_log, world)
     if world == 1 and not a.no_aux:
         # the kernels either side of the CHOMP loop (goal-set IK, SDF packing, point-cloud field, trajectory
@@ -405,7 +419,10 @@ def run_b200(a):
             line["aux_kernels"] = bench_aux.run_aux(peak)
         except Exception as e:   # noqa: BLE001
             line["aux_kernels"] = {"error": repr(e)}
-    print(json.dumps(line))
+    if json_fd is not None:
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
+    else:
+        print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 
@@ -416,7 +433,14 @@ def nccl_summary(pattern, world):
     import re
     import socket
 
-    out = {"debug_file": pattern, "nranks": None, "lines": []}
+    out = {"debug_file": pattern, "nranks": None, "lines": [], "torch_world_size": world}
+    try:
+        import torch
+        out["nccl_version"] = ".".join(str(v) for v in torch.cuda.nccl.version())
+    except Exception:   # noqa: BLE001
+        pass
+    if not pattern:
+        return out
     path = pattern.replace("%h", socket.gethostname()).replace("%p", "*")
     for f in sorted(glob.glob(path)):
         try:

@@ -27,7 +27,7 @@ struct GoalArgs {
     RobotParams rp;
     int num_objects, num_goals, arc, finger_soft;
     float inv_dt;
-    unsigned off_q, off_sc, off_frames, off_mask, off_part, off_objs, smem_total;
+    unsigned off_q, off_sc, off_frames, off_mask, off_part, off_act, off_objs, smem_total;
 };
 
 __host__ inline void goal_layout(GoalArgs &a) {
@@ -39,6 +39,7 @@ __host__ inline void goal_layout(GoalArgs &a) {
     a.off_frames = o; o += sizeof(double) * cfgs * NL * 12;
     a.off_mask = o; o += sizeof(unsigned long long) * a.arc * NL;
     a.off_part = o; o += sizeof(double) * (a.arc * NL + 32);
+    a.off_act = o; o += align_up(sizeof(unsigned short) * (a.arc * NL + 2) + 8, 8);
     o = align_up(o, 16);
     a.off_objs = o; o += sizeof(ObjRec) * a.num_objects;
     a.smem_total = align_up(o, 16);
@@ -52,6 +53,8 @@ __global__ void __launch_bounds__(THREADS) goal_cost_kernel(const GoalArgs a) {
     double *s_frames = reinterpret_cast<double *>(smem + a.off_frames);
     unsigned long long *s_mask = reinterpret_cast<unsigned long long *>(smem + a.off_mask);
     double *s_part = reinterpret_cast<double *>(smem + a.off_part);
+    int *s_count = reinterpret_cast<int *>(smem + a.off_act);                       // active link instances
+    unsigned short *s_act = reinterpret_cast<unsigned short *>(smem + a.off_act + 8);
     ObjRec *s_objs = reinterpret_cast<ObjRec *>(smem + a.off_objs);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -67,6 +70,7 @@ __global__ void __launch_bounds__(THREADS) goal_cost_kernel(const GoalArgs a) {
         const uint32_t *src = reinterpret_cast<const uint32_t *>(a.objs);
         uint32_t *dst = reinterpret_cast<uint32_t *>(s_objs);
         for (int k = tid; k < words; k += THREADS) dst[k] = src[k];
+        if (tid == 0) *s_count = 0;
     }
     {
         const double *qf = a.from + (size_t)b * a.from_stride;
@@ -100,13 +104,15 @@ __global__ void __launch_bounds__(THREADS) goal_cost_kernel(const GoalArgs a) {
     // ---- cull every (waypoint, link) bounding sphere against every object (same tests as the fused step) ----
     const int n_li = arc * NL;
     const bool use_dil = a.dil.enabled != 0;
-    for (int li = tid; li < n_li; li += THREADS) {
+    for (int base_li = 0; base_li < n_li; base_li += THREADS) {   // (uniform trip count: the ballot below needs whole warps)
+        const int li = base_li + tid;
+        unsigned long long m = 0ull;
+        if (li < n_li) {
         const int j = li % NL;
         double cx, cy, cz;
         xform(s_frames + (size_t)(li + NL) * 12, (double)a.rp.sph[j][0], (double)a.rp.sph[j][1], (double)a.rp.sph[j][2],
               cx, cy, cz);
         const float fx = (float)cx, fy = (float)cy, fz = (float)cz, rad = a.rp.sph[j][3];
-        unsigned long long m = 0ull;
         for (int o = 0; o < O; ++o) {
             const ObjRec &ob = s_objs[o];
             if (ob.dis > 0.0f) continue;
@@ -136,22 +142,30 @@ __global__ void __launch_bounds__(THREADS) goal_cost_kernel(const GoalArgs a) {
         }
         s_mask[li] = m;
         s_part[li] = 0.0;
+        }
+        // compaction of the instances that still have work (order is irrelevant: every instance owns its s_part slot)
+        const unsigned bal = __ballot_sync(0xffffffffu, m != 0ull);
+        int wbase = 0;
+        if (lane == 0 && bal) wbase = atomicAdd(s_count, __popc(bal));
+        wbase = __shfl_sync(0xffffffffu, wbase, 0);
+        if (m != 0ull) s_act[wbase + __popc(bal & ((1u << lane) - 1u))] = (unsigned short)li;
     }
     __syncthreads();
+    const int n_act = *s_count;
     // ---- body points: half-warp per (waypoint, link), lane per body point (p <= 16) or warp per instance ----
     const int LPI = P <= 16 ? 16 : 32;
     const int gpw = 32 / LPI;
     const int sub = lane / LPI, pl = lane % LPI;
     const unsigned gmask = (LPI == 32) ? 0xffffffffu : (0xffffu << (sub * 16));
-    for (int base = warp * gpw; base < n_li; base += NWARPS * gpw) {
-        const int li = base + sub;
-        const bool have = li < n_li;
+    for (int base = warp * gpw; base < n_act; base += NWARPS * gpw) {
+        const int idx = base + sub;
+        const bool have = idx < n_act;
+        const int li = have ? (int)s_act[idx] : 0;
         unsigned long long m = have ? s_mask[li] : 0ull;
-        if (!__any_sync(gmask, m != 0ull)) continue;   // uniform per half-warp
         const bool live = have && pl < P;
         if (!live) m = 0ull;
         const int i = have ? li / NL : 0, j = have ? li - i * NL : 0;
-        const double *F = s_frames + (size_t)(li < n_li ? li + NL : NL) * 12;
+        const double *F = s_frames + (size_t)(li + NL) * 12;
         const double *bp = rc->pts[j][pl < P ? pl : 0];
         double X, Y, Z;
         xform(F, bp[0], bp[1], bp[2], X, Y, Z);

@@ -1250,14 +1250,27 @@ extern "C" int omgb_goal_costs(omgb_scene_t *s, int batch, const double *from, l
     goal_layout(a);
     if (a.smem_total > (unsigned)s->smem_optin)
         return fail(OMGB_ERR_UNSUPPORTED, "omgb_goal_costs: arc_length too long for one CTA's shared memory");
-    constexpr int THREADS = 256;
-    static unsigned cached[64] = {0};
-    if (s->device >= 64 || cached[s->device] < a.smem_total) {
-        OMGB_CUDA(cudaFuncSetAttribute(goal_cost_kernel<THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)a.smem_total));
-        if (s->device < 64) cached[s->device] = a.smem_total;
+    // block size by the number of link instances of a line (arc * 10): the cull is one instance per thread
+    const int n_li = arc_length * NL;
+    const int shape = n_li <= 128 ? 0 : n_li <= 192 ? 1 : n_li <= 256 ? 2 : 3;
+    static unsigned cached[4][64] = {{0}};
+    {
+        std::lock_guard<std::mutex> lock(g_attr_mutex);
+        if (s->device >= 64 || cached[shape][s->device] < a.smem_total) {
+            cudaError_t e_ = shape == 0 ? cudaFuncSetAttribute(goal_cost_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)a.smem_total)
+                           : shape == 1 ? cudaFuncSetAttribute(goal_cost_kernel<192>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)a.smem_total)
+                           : shape == 2 ? cudaFuncSetAttribute(goal_cost_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)a.smem_total)
+                                        : cudaFuncSetAttribute(goal_cost_kernel<320>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)a.smem_total);
+            if (e_ != cudaSuccess) return fail(OMGB_ERR_CUDA, std::string("goal_cost_kernel attributes: ") + cudaGetErrorString(e_));
+            if (s->device < 64) cached[shape][s->device] = a.smem_total;
+        }
     }
-    goal_cost_kernel<THREADS><<<batch * num_goals, THREADS, a.smem_total, (cudaStream_t)stream>>>(a);
+    const int grid = batch * num_goals;
+    cudaStream_t gst = (cudaStream_t)stream;
+    if (shape == 0) goal_cost_kernel<128><<<grid, 128, a.smem_total, gst>>>(a);
+    else if (shape == 1) goal_cost_kernel<192><<<grid, 192, a.smem_total, gst>>>(a);
+    else if (shape == 2) goal_cost_kernel<256><<<grid, 256, a.smem_total, gst>>>(a);
+    else goal_cost_kernel<320><<<grid, 320, a.smem_total, gst>>>(a);
     ++g_launches;
     OMGB_CUDA(cudaGetLastError());
     return OMGB_OK;
