@@ -181,7 +181,7 @@ def run_b200(a):
         sys.stdout.flush()
         json_fd = os.dup(1)
         os.dup2(2, 1)
-        if "NCCL_DEBUG" not in os.environ:
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION", "WARN"):   # (this image presets VERSION)
             os.environ["NCCL_DEBUG"] = "INFO"
             os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
             if "NCCL_DEBUG_FILE" not in os.environ:
