@@ -128,7 +128,7 @@ class ClockSampler(object):
                         self.reasons.add(k)
             except Exception:  # noqa: BLE001
                 pass
-            time.sleep(0.01)   # (NVML takes a driver-wide lock: keep the polling of N ranks light)
+            time.sleep(0.002)
 
     def start(self):
         if self.nv:

@@ -164,7 +164,7 @@ def _roofline(p_in_per_launch, B, n, c, kern_ms, peak, peak_src, kernel, traffic
 # ----------------------------------------------------------------------------------------------------------------
 # config 4
 # ----------------------------------------------------------------------------------------------------------------
-def run_config4(rank, world, peak, peak_src, steps=5, warmup=3, total=8192, n=60, objects=20, grid=256, parity=True,
+def run_config4(rank, world, peak, peak_src, steps=10, warmup=6, total=8192, n=60, objects=20, grid=256, parity=True,
                 plan_iters=70):
     import torch
 
@@ -217,7 +217,8 @@ def run_config4(rank, world, peak, peak_src, steps=5, warmup=3, total=8192, n=60
         pins.append(out["info"][:, 12].sum())
     _barrier()
     dev_ms = sum(s.elapsed_time(e) for s, e in evs)
-    print("c4dbg rank %d: per-step device ms %s" % (rank, ["%.3f" % s.elapsed_time(e) for s, e in evs]), file=sys.stderr)
+    print("config4 rank %d: per-step device ms %s" % (rank, " ".join("%.3f" % s.elapsed_time(e) for s, e in evs)),
+          file=sys.stderr)
     dev_ms_max = _max_over_ranks(dev_ms)
     p_in = float(torch.stack(pins).mean().item())
 
