@@ -171,6 +171,12 @@ def run_b200(a):
     from omg_planner_b200.engine import ChompEngine
 
     torch.cuda.set_device(local)
+    numa = None
+    if world > 1 and not os.environ.get("OMGB_NO_NUMA_BIND"):
+        # one process per GPU: keep this rank's pinned host buffers and staging copies on the GPU's own NUMA node
+        from omg_planner_b200 import dist as D0
+        numa = D0.bind_host_to_device_numa(local)
+        print("rank %d: numa binding %s" % (rank, numa), file=sys.stderr)
     nccl_log = None
     json_fd = None
     if world > 1:
@@ -410,6 +416,7 @@ def run_b200(a):
         line["configs"] = configs
     if world > 1:
         line["nccl"] = nccl_summary(nccl_log, world)
+        line["numa_binding_rank0"] = numa
     if world == 1 and not a.no_aux:
         # the kernels either side of the CHOMP loop (goal-set IK, SDF packing, point-cloud field, trajectory
         # initialisation): reported beside the headline, never part of it

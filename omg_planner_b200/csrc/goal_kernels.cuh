@@ -8,10 +8,23 @@
 //   4. reduces over waypoints, links and body points to ONE number (online_learner.py:147-150).
 // The reference materialises [G*n', 10, p] potentials AND gradients AND collision flags through three torch tensors
 // and 4 kernel launches, then sums on the host side; here nothing but the [B, G] cost matrix leaves the SM.
+//
+// Step 3 runs in two stages per warp.  Stage A classifies every surviving (body point, object) pair against the
+// lower-bound grid (one load proves "farther than eps"); the few pairs that need the operator -- ~7 % of the in-bounds
+// pairs, scattered over the lanes -- are pushed into a warp-private queue in shared memory (point, speed, object).
+// Stage B evaluates queued pairs 32 at a time, every lane busy: run in place, the operator's ~120 instructions were
+// issued for warps with one or two live lanes and made up 28 % of the kernel's instructions
+// (profiles/r02p_ncu_goal_cost_lines.txt).  The sum is order-free: every pair's potential x speed is an exact fp64
+// product of two floats, accumulated in 2^-40 fixed point (int64), so the result does not depend on queue order,
+// block shape or SDF layout.  (The reference's own sum over objects is an atomicAdd in arbitrary order followed by a
+// torch fp32 tree reduction: its value is defined to ~1e-6 relative; tests/test_gpu_goal_scoring.py holds 2e-5.)
 #pragma once
 #include "chomp_kernels.cuh"
 
 namespace omgb {
+
+constexpr int GOAL_QCAP = 64;                       // queue entries per warp (a push adds <= 32 to <= 31 pending)
+constexpr double GOAL_FIX = 1099511627776.0;        // 2^40
 
 struct GoalArgs {
     const ObjRec *objs;
@@ -27,34 +40,44 @@ struct GoalArgs {
     RobotParams rp;
     int num_objects, num_goals, arc, finger_soft;
     float inv_dt;
-    unsigned off_q, off_sc, off_frames, off_mask, off_part, off_act, off_objs, smem_total;
+    unsigned off_q, off_sc, off_queue, off_qobj, off_frames, off_mask, off_mask_hi, off_act, off_red, off_objs,
+        smem_total;
 };
 
-__host__ inline void goal_layout(GoalArgs &a) {
+__host__ inline void goal_layout(GoalArgs &a, int warps) {
     const int cfgs = a.arc + 1;
     unsigned o = 0;
-    a.off_q = o; o += sizeof(double) * cfgs * ND;
-    o = align_up(o, 16);
-    a.off_sc = o; o += sizeof(double2) * cfgs * 7;
+    // region A: joint values + sin/cos table (dead once the frames exist), reused by the per-warp queues
+    a.off_q = 0;
+    a.off_sc = align_up((unsigned)(sizeof(double) * cfgs * ND), 16);
+    const unsigned fk_bytes = a.off_sc + (unsigned)(sizeof(double2) * cfgs * 7);
+    a.off_queue = 0;
+    a.off_qobj = (unsigned)(sizeof(float4) * GOAL_QCAP * warps);
+    const unsigned q_bytes = a.off_qobj + (unsigned)(GOAL_QCAP * warps);
+    o = align_up(fk_bytes > q_bytes ? fk_bytes : q_bytes, 16);
     a.off_frames = o; o += sizeof(double) * cfgs * NL * 12;
-    a.off_mask = o; o += sizeof(unsigned long long) * a.arc * NL;
-    a.off_part = o; o += sizeof(double) * (a.arc * NL + 32);
-    a.off_act = o; o += align_up(sizeof(unsigned short) * (a.arc * NL + 2) + 8, 8);
+    a.off_mask = o; o += sizeof(unsigned) * a.arc * NL;
+    a.off_mask_hi = o; if (a.num_objects > 32) o += sizeof(unsigned) * a.arc * NL;
+    a.off_act = o; o += align_up((unsigned)(sizeof(unsigned short) * (a.arc * NL + 2)) + 8, 8);
+    a.off_red = o; o += sizeof(long long) * 32;
     o = align_up(o, 16);
     a.off_objs = o; o += sizeof(ObjRec) * a.num_objects;
     a.smem_total = align_up(o, 16);
 }
 
-template <int THREADS>
-__global__ void __launch_bounds__(THREADS) goal_cost_kernel(const GoalArgs a) {
+// LPI: lanes per link instance (16 when the robot has <= 16 body points per link, else 32); HI: more than 32 objects.
+template <int THREADS, int LPI, bool HI>
+__global__ void __launch_bounds__(THREADS, (THREADS <= 128 ? 8 : THREADS <= 192 ? 6 : THREADS <= 256 ? 5 : 4))
+goal_cost_kernel(const GoalArgs a) {
     extern __shared__ __align__(16) unsigned char smem[];
     double *s_q = reinterpret_cast<double *>(smem + a.off_q);
     double2 *s_sc = reinterpret_cast<double2 *>(smem + a.off_sc);
     double *s_frames = reinterpret_cast<double *>(smem + a.off_frames);
-    unsigned long long *s_mask = reinterpret_cast<unsigned long long *>(smem + a.off_mask);
-    double *s_part = reinterpret_cast<double *>(smem + a.off_part);
+    unsigned *s_mask = reinterpret_cast<unsigned *>(smem + a.off_mask);
+    unsigned *s_mask_hi = reinterpret_cast<unsigned *>(smem + a.off_mask_hi);
     int *s_count = reinterpret_cast<int *>(smem + a.off_act);                       // active link instances
-    unsigned short *s_act = reinterpret_cast<unsigned short *>(smem + a.off_act + 8);
+    unsigned short *s_act = reinterpret_cast<unsigned short *>(smem + a.off_act + 8);   // (config << 4) | link
+    long long *s_red = reinterpret_cast<long long *>(smem + a.off_red);
     ObjRec *s_objs = reinterpret_cast<ObjRec *>(smem + a.off_objs);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -66,10 +89,10 @@ __global__ void __launch_bounds__(THREADS) goal_cost_kernel(const GoalArgs a) {
 
     // ---- stage the object records; interpolate (slot 0 = the trajectory's waypoint, slots 1..arc = the line) ----
     {
-        const int words = (int)(sizeof(ObjRec) / 4) * O;
-        const uint32_t *src = reinterpret_cast<const uint32_t *>(a.objs);
-        uint32_t *dst = reinterpret_cast<uint32_t *>(s_objs);
-        for (int k = tid; k < words; k += THREADS) dst[k] = src[k];
+        const int quads = (int)(sizeof(ObjRec) / 16) * O;
+        const uint4 *src = reinterpret_cast<const uint4 *>(a.objs);
+        uint4 *dst = reinterpret_cast<uint4 *>(s_objs);
+        for (int k = tid; k < quads; k += THREADS) dst[k] = __ldg(src + k);
         if (tid == 0) *s_count = 0;
     }
     {
@@ -106,106 +129,144 @@ __global__ void __launch_bounds__(THREADS) goal_cost_kernel(const GoalArgs a) {
     const bool use_dil = a.dil.enabled != 0;
     for (int base_li = 0; base_li < n_li; base_li += THREADS) {   // (uniform trip count: the ballot below needs whole warps)
         const int li = base_li + tid;
-        unsigned long long m = 0ull;
+        unsigned mlo = 0u, mhi = 0u;
+        int ci = 0, cj = 0;
         if (li < n_li) {
-        const int j = li % NL;
-        double cx, cy, cz;
-        xform(s_frames + (size_t)(li + NL) * 12, (double)a.rp.sph[j][0], (double)a.rp.sph[j][1], (double)a.rp.sph[j][2],
-              cx, cy, cz);
-        const float fx = (float)cx, fy = (float)cy, fz = (float)cz, rad = a.rp.sph[j][3];
-        for (int o = 0; o < O; ++o) {
-            const ObjRec &ob = s_objs[o];
-            if (ob.dis > 0.0f) continue;
-            {   // first level: link sphere vs the object's world-frame bounding sphere (most pairs end here)
-                const float dx = fx - ob.wsx, dy = fy - ob.wsy, dz = fz - ob.wsz, rr = rad + ob.wsr;
-                if (ob.wsr >= 0.0f && dx * dx + dy * dy + dz * dz > rr * rr) continue;
-            }
-            const float qx = ob.r[0] * fx + ob.r[1] * fy + ob.r[2] * fz + ob.tx;
-            const float qy = ob.r[3] * fx + ob.r[4] * fy + ob.r[5] * fz + ob.ty;
-            const float qz = ob.r[6] * fx + ob.r[7] * fy + ob.r[8] * fz + ob.tz;
-            const float s = rad + ob.cull_pad;
-            const bool box = (qx > ob.lox - s) & (qx < ob.hix + s) & (qy > ob.loy - s) & (qy < ob.hiy + s) &
-                             (qz > ob.loz - s) & (qz < ob.hiz + s);
-            if (!box) continue;
-            if (use_dil && ob.cull_pad < 1e29f) {
-                const bool miss = (qx + s < ob.alox) | (qx - s > ob.ahix) | (qy + s < ob.aloy) | (qy - s > ob.ahiy) |
-                                  (qz + s < ob.aloz) | (qz - s > ob.ahiz);
-                if (miss) {
-                    const bool interior =
-                        ((qx - s - ob.minx) * ob.isx >= 1.5f) & ((qx + s - ob.minx) * ob.isx <= ob.fd0 - 1.5f) &
-                        ((qy - s - ob.miny) * ob.isy >= 1.5f) & ((qy + s - ob.miny) * ob.isy <= ob.fd1 - 1.5f) &
-                        ((qz - s - ob.minz) * ob.isz >= 1.5f) & ((qz + s - ob.minz) * ob.isz <= ob.fd2 - 1.5f);
-                    if (interior) continue;
+            ci = li / NL; cj = li - ci * NL;
+            double cx, cy, cz;
+            xform(s_frames + (size_t)(li + NL) * 12, (double)a.rp.sph[cj][0], (double)a.rp.sph[cj][1],
+                  (double)a.rp.sph[cj][2], cx, cy, cz);
+            const float fx = (float)cx, fy = (float)cy, fz = (float)cz, rad = a.rp.sph[cj][3];
+            for (int o = 0; o < O; ++o) {
+                const ObjRec &ob = s_objs[o];
+                if (ob.dis > 0.0f) continue;
+                {   // first level: link sphere vs the object's world-frame bounding sphere (most pairs end here)
+                    const float dx = fx - ob.wsx, dy = fy - ob.wsy, dz = fz - ob.wsz, rr = rad + ob.wsr;
+                    if (ob.wsr >= 0.0f && dx * dx + dy * dy + dz * dz > rr * rr) continue;
                 }
+                const float qx = ob.r[0] * fx + ob.r[1] * fy + ob.r[2] * fz + ob.tx;
+                const float qy = ob.r[3] * fx + ob.r[4] * fy + ob.r[5] * fz + ob.ty;
+                const float qz = ob.r[6] * fx + ob.r[7] * fy + ob.r[8] * fz + ob.tz;
+                const float s = rad + ob.cull_pad;
+                const bool box = (qx > ob.lox - s) & (qx < ob.hix + s) & (qy > ob.loy - s) & (qy < ob.hiy + s) &
+                                 (qz > ob.loz - s) & (qz < ob.hiz + s);
+                if (!box) continue;
+                if (use_dil && ob.cull_pad < 1e29f) {
+                    const bool miss = (qx + s < ob.alox) | (qx - s > ob.ahix) | (qy + s < ob.aloy) | (qy - s > ob.ahiy) |
+                                      (qz + s < ob.aloz) | (qz - s > ob.ahiz);
+                    if (miss) {
+                        const bool interior =
+                            ((qx - s - ob.minx) * ob.isx >= 1.5f) & ((qx + s - ob.minx) * ob.isx <= ob.fd0 - 1.5f) &
+                            ((qy - s - ob.miny) * ob.isy >= 1.5f) & ((qy + s - ob.miny) * ob.isy <= ob.fd1 - 1.5f) &
+                            ((qz - s - ob.minz) * ob.isz >= 1.5f) & ((qz + s - ob.minz) * ob.isz <= ob.fd2 - 1.5f);
+                        if (interior) continue;
+                    }
+                }
+                if (!HI || o < 32) mlo |= 1u << o;
+                else mhi |= 1u << (o - 32);
             }
-            m |= 1ull << o;
+            s_mask[li] = mlo;
+            if (HI) s_mask_hi[li] = mhi;
         }
-        s_mask[li] = m;
-        s_part[li] = 0.0;
-        }
-        // compaction of the instances that still have work (order is irrelevant: every instance owns its s_part slot)
-        const unsigned bal = __ballot_sync(0xffffffffu, m != 0ull);
+        // compaction of the instances that still have work (order is irrelevant: the sum is order-free)
+        const bool any = (mlo | mhi) != 0u;
+        const unsigned bal = __ballot_sync(0xffffffffu, any);
         int wbase = 0;
         if (lane == 0 && bal) wbase = atomicAdd(s_count, __popc(bal));
         wbase = __shfl_sync(0xffffffffu, wbase, 0);
-        if (m != 0ull) s_act[wbase + __popc(bal & ((1u << lane) - 1u))] = (unsigned short)li;
+        if (any) s_act[wbase + __popc(bal & ((1u << lane) - 1u))] = (unsigned short)((ci << 4) | cj);
     }
-    __syncthreads();
+    __syncthreads();   // (the sin/cos table and the joint values are dead: region A now holds the queues)
     const int n_act = *s_count;
-    // ---- body points: half-warp per (waypoint, link), lane per body point (p <= 16) or warp per instance ----
-    const int LPI = P <= 16 ? 16 : 32;
-    const int gpw = 32 / LPI;
+    float4 *q_pt = reinterpret_cast<float4 *>(smem + a.off_queue) + warp * GOAL_QCAP;   // x, y, z, speed
+    unsigned char *q_ob = smem + a.off_qobj + warp * GOAL_QCAP;                           // object | finger flag
+    int q_cnt = 0;
+    long long acc = 0;
+    // stage B for queue slot k: the operator's value-only evaluation, potential x speed in exact fp64, fixed point
+    auto evaluate = [&](int k) {
+        const float4 it = q_pt[k];
+        const unsigned oo = q_ob[k];
+        float po, co;
+        pair_potential(s_objs[oo & 63u], a.grids, a.quad, it.x, it.y, it.z, po, co);
+        double v = (double)po * (double)it.w;
+        if (oo & 0x80u) v *= (double)0.1f;   // omg/cost.py:350-353 (soft finger links)
+        acc += __double2ll_rn(v * GOAL_FIX);
+    };
+    // ---- body points: LPI lanes per (waypoint, link), lane per body point ----
+    constexpr int GPW = 32 / LPI;
     const int sub = lane / LPI, pl = lane % LPI;
-    const unsigned gmask = (LPI == 32) ? 0xffffffffu : (0xffffu << (sub * 16));
-    for (int base = warp * gpw; base < n_act; base += NWARPS * gpw) {
+    const unsigned lt_mask = (1u << lane) - 1u;
+    for (int base = warp * GPW; base < n_act; base += NWARPS * GPW) {
         const int idx = base + sub;
-        const bool have = idx < n_act;
-        const int li = have ? (int)s_act[idx] : 0;
-        unsigned long long m = have ? s_mask[li] : 0ull;
-        const bool live = have && pl < P;
-        if (!live) m = 0ull;
-        const int i = have ? li / NL : 0, j = have ? li - i * NL : 0;
-        const double *F = s_frames + (size_t)(li + NL) * 12;
-        const double *bp = rc->pts[j][pl < P ? pl : 0];
-        double X, Y, Z;
-        xform(F, bp[0], bp[1], bp[2], X, Y, Z);
-        const float x = (float)X, y = (float)Y, z = (float)Z;   // omg/cost.py:218 .float()
-        float pot = 0.0f;
-#pragma unroll 1
-        for (int half = 0; half < 2; ++half) {
-            unsigned mm = half ? (unsigned)(m >> 32) : (unsigned)m;
+        unsigned nlo = 0u, nhi = 0u;   // objects whose operator value this point needs
+        float x = 0.0f, y = 0.0f, z = 0.0f, sp = 0.0f;
+        unsigned fing = 0u;
+        if (idx < n_act && pl < P) {
+            const unsigned v = s_act[idx];
+            const int i = (int)(v >> 4), j = (int)(v & 15u), li = i * NL + j;
+            const double *F = s_frames + (size_t)(li + NL) * 12;
+            const double *bp = rc->pts[j][pl];
+            const double b0 = bp[0], b1 = bp[1], b2 = bp[2];
+            double X, Y, Z;
+            xform(F, b0, b1, b2, X, Y, Z);
+            x = (float)X; y = (float)Y; z = (float)Z;   // omg/cost.py:218 .float()
+            unsigned mm = s_mask[li];
             while (mm) {
-                const int o = __ffs(mm) - 1 + 32 * half;
+                const int o = __ffs(mm) - 1;
                 mm &= mm - 1;
-                if (use_dil && classify_pair(s_objs[o], a.dil, o, x, y, z) != PAIR_EXACT) continue;
-                float po, co;
-                pair_potential(s_objs[o], a.grids, a.quad, x, y, z, po, co);
-                pot = __fadd_rn(pot, po);
+                if (!use_dil || classify_pair(s_objs[o], a.dil, o, x, y, z) == PAIR_EXACT) nlo |= 1u << o;
+            }
+            if (HI) {
+                mm = s_mask_hi[li];
+                while (mm) {
+                    const int o = __ffs(mm) - 1;
+                    mm &= mm - 1;
+                    if (!use_dil || classify_pair(s_objs[o + 32], a.dil, o + 32, x, y, z) == PAIR_EXACT) nhi |= 1u << o;
+                }
+            }
+            if (nlo | nhi) {
+                // workspace speed against the previous configuration of the line (slot i; slot 0 = traj.data[start])
+                double Xp, Yp, Zp;
+                xform(F - NL * 12, b0, b1, b2, Xp, Yp, Zp);
+                const float vx = (x - (float)Xp) * a.inv_dt, vy = (y - (float)Yp) * a.inv_dt,
+                            vz = (z - (float)Zp) * a.inv_dt;
+                sp = sqrtf(vx * vx + vy * vy + vz * vz);
+                fing = (a.finger_soft && j >= 8) ? 0x80u : 0u;
             }
         }
-        if (a.finger_soft && j >= 8) pot = __fmul_rn(pot, 0.1f);   // omg/cost.py:350-353
-        float val = 0.0f;
-        if (pot != 0.0f) {
-            // workspace speed against the previous configuration of the line (slot i; slot 0 = traj.data[start])
-            const double *Fp = F - NL * 12;
-            double Xp, Yp, Zp;
-            xform(Fp, bp[0], bp[1], bp[2], Xp, Yp, Zp);
-            const float vx = (x - (float)Xp) * a.inv_dt, vy = (y - (float)Yp) * a.inv_dt, vz = (z - (float)Zp) * a.inv_dt;
-            val = pot * sqrtf(vx * vx + vy * vy + vz * vz);
+        // push this round's pairs, one object per lane and pass; evaluate whenever 32 are pending
+        for (;;) {
+            const bool has = (nlo | nhi) != 0u;
+            const unsigned bal = __ballot_sync(0xffffffffu, has);
+            if (!bal) break;
+            if (has) {
+                unsigned o;
+                if (nlo) { o = (unsigned)(__ffs(nlo) - 1); nlo &= nlo - 1; }
+                else { o = 32u + (unsigned)(__ffs(nhi) - 1); nhi &= nhi - 1; }
+                const int pos = q_cnt + __popc(bal & lt_mask);
+                q_pt[pos] = make_float4(x, y, z, sp);
+                q_ob[pos] = (unsigned char)(o | fing);
+            }
+            q_cnt += __popc(bal);
+            __syncwarp();
+            if (q_cnt >= 32) {
+                q_cnt -= 32;
+                evaluate(q_cnt + lane);
+                __syncwarp();
+            }
         }
-        double acc = (double)val;
-#pragma unroll
-        for (int off = 8; off > 0; off >>= 1) acc += __shfl_xor_sync(gmask, acc, off, 16);
-        if (LPI == 32) acc += __shfl_xor_sync(gmask, acc, 16, 32);
-        if (have && pl == 0) s_part[li] = acc;
     }
+    if (lane < q_cnt) evaluate(lane);
+    // ---- order-free reduction ----
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+    if (lane == 0) s_red[warp] = acc;
     __syncthreads();
-    // ---- deterministic reduction over the link instances ----
-    if (warp == 0) {
-        double t = 0.0;
-        for (int k = lane; k < n_li; k += 32) t += s_part[k];
-        t = warp_sum(t);
-        if (lane == 0) a.costs[(size_t)b * a.num_goals + g] = (float)t;
+    if (tid == 0) {
+        long long t = 0;
+#pragma unroll
+        for (int w = 0; w < NWARPS; ++w) t += s_red[w];
+        a.costs[(size_t)b * a.num_goals + g] = (float)((double)t * (1.0 / GOAL_FIX));
     }
 }
 

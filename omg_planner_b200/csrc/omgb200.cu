@@ -1247,30 +1247,37 @@ extern "C" int omgb_goal_costs(omgb_scene_t *s, int batch, const double *from, l
     a.num_objects = s->num_objects; a.num_goals = num_goals; a.arc = arc_length;
     a.finger_soft = uncheck_finger_collision == -1 ? 1 : 0;
     a.inv_dt = (float)(1.0 / time_interval);
-    goal_layout(a);
-    if (a.smem_total > (unsigned)s->smem_optin)
-        return fail(OMGB_ERR_UNSUPPORTED, "omgb_goal_costs: arc_length too long for one CTA's shared memory");
     // block size by the number of link instances of a line (arc * 10): the cull is one instance per thread
     const int n_li = arc_length * NL;
-    const int shape = n_li <= 128 ? 0 : n_li <= 192 ? 1 : n_li <= 256 ? 2 : 3;
-    static unsigned cached[4][64] = {{0}};
-    {
-        std::lock_guard<std::mutex> lock(g_attr_mutex);
-        if (s->device >= 64 || cached[shape][s->device] < a.smem_total) {
-            cudaError_t e_ = shape == 0 ? cudaFuncSetAttribute(goal_cost_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)a.smem_total)
-                           : shape == 1 ? cudaFuncSetAttribute(goal_cost_kernel<192>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)a.smem_total)
-                           : shape == 2 ? cudaFuncSetAttribute(goal_cost_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)a.smem_total)
-                                        : cudaFuncSetAttribute(goal_cost_kernel<320>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)a.smem_total);
-            if (e_ != cudaSuccess) return fail(OMGB_ERR_CUDA, std::string("goal_cost_kernel attributes: ") + cudaGetErrorString(e_));
-            if (s->device < 64) cached[shape][s->device] = a.smem_total;
-        }
-    }
+    const int lpi = s->p <= 16 ? 16 : 32;
+    const int shape = lpi == 32 ? 2 : (n_li <= 128 ? 0 : n_li <= 192 ? 1 : n_li <= 256 ? 2 : 3);
+    static const int shape_threads[4] = {128, 192, 256, 320};
+    const int hi = s->num_objects > 32 ? 1 : 0;
+    goal_layout(a, shape_threads[shape] / 32);
+    if (a.smem_total > (unsigned)s->smem_optin)
+        return fail(OMGB_ERR_UNSUPPORTED, "omgb_goal_costs: arc_length too long for one CTA's shared memory");
     const int grid = batch * num_goals;
     cudaStream_t gst = (cudaStream_t)stream;
-    if (shape == 0) goal_cost_kernel<128><<<grid, 128, a.smem_total, gst>>>(a);
-    else if (shape == 1) goal_cost_kernel<192><<<grid, 192, a.smem_total, gst>>>(a);
-    else if (shape == 2) goal_cost_kernel<256><<<grid, 256, a.smem_total, gst>>>(a);
-    else goal_cost_kernel<320><<<grid, 320, a.smem_total, gst>>>(a);
+    static unsigned cached[2][4][2][64] = {{{{0}}}};
+    cudaError_t e_ = cudaSuccess;
+    {
+        std::lock_guard<std::mutex> lock(g_attr_mutex);
+        const bool set_attr = s->device >= 64 || cached[lpi == 32][shape][hi][s->device] < a.smem_total;
+#define OMGB_GOAL_CASE(T, L, H)                                                                                        \
+    do {                                                                                                               \
+        if (set_attr) e_ = cudaFuncSetAttribute(goal_cost_kernel<T, L, H>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                                (int)a.smem_total);                                                    \
+        if (e_ == cudaSuccess) goal_cost_kernel<T, L, H><<<grid, T, a.smem_total, gst>>>(a);                           \
+    } while (0)
+        if (lpi == 32) { if (hi) OMGB_GOAL_CASE(256, 32, true); else OMGB_GOAL_CASE(256, 32, false); }
+        else if (shape == 0) { if (hi) OMGB_GOAL_CASE(128, 16, true); else OMGB_GOAL_CASE(128, 16, false); }
+        else if (shape == 1) { if (hi) OMGB_GOAL_CASE(192, 16, true); else OMGB_GOAL_CASE(192, 16, false); }
+        else if (shape == 2) { if (hi) OMGB_GOAL_CASE(256, 16, true); else OMGB_GOAL_CASE(256, 16, false); }
+        else { if (hi) OMGB_GOAL_CASE(320, 16, true); else OMGB_GOAL_CASE(320, 16, false); }
+#undef OMGB_GOAL_CASE
+        if (e_ != cudaSuccess) return fail(OMGB_ERR_CUDA, std::string("goal_cost_kernel attributes: ") + cudaGetErrorString(e_));
+        if (set_attr && s->device < 64) cached[lpi == 32][shape][hi][s->device] = a.smem_total;
+    }
     ++g_launches;
     OMGB_CUDA(cudaGetLastError());
     return OMGB_OK;

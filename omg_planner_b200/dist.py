@@ -34,3 +34,38 @@ def all_gather_ragged(local, batch, group=None):
     pad[: sizes[rank]] = local
     out = all_gather_costs(pad, group).reshape((world, mx) + tuple(local.shape[1:]))
     return torch.cat([out[r, : sizes[r]] for r in range(world)], 0)
+
+
+def _parse_cpulist(text):
+    cpus = set()
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        lo, _, hi = part.partition("-")
+        cpus.update(range(int(lo), int(hi or lo) + 1))
+    return cpus
+
+
+def bind_host_to_device_numa(device_index):
+    """Pin the calling process to the CPUs of the NUMA node its GPU hangs off, so that the pinned host buffers of the
+    host-buffer entry points (first touch) and the staging memcpys are node-local.  One process per GPU drives
+    ~5 MB per step over PCIe in each direction of the link; with 8 processes on a two-socket box, buffers that land
+    on the far socket cross the inter-socket link as well.  A no-op (returns None) when the topology cannot be read,
+    the node has no CPUs of the current affinity mask, or there is a single node.  Returns a small dict otherwise."""
+    import os
+
+    try:
+        props = torch.cuda.get_device_properties(device_index)
+        bdf = "%04x:%02x:%02x.0" % (props.pci_domain_id, props.pci_bus_id, props.pci_device_id)
+        with open("/sys/bus/pci/devices/%s/numa_node" % bdf) as f:
+            node = int(f.read().strip())
+        if node < 0 or not os.path.isdir("/sys/devices/system/node/node1"):
+            return None
+        with open("/sys/devices/system/node/node%d/cpulist" % node) as f:
+            cpus = _parse_cpulist(f.read()) & set(os.sched_getaffinity(0))
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return {"pci": bdf, "numa_node": node, "cpus": len(cpus)}
+    except Exception:   # noqa: BLE001 -- best effort: any failure leaves the affinity as it was
+        return None

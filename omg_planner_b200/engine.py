@@ -201,7 +201,9 @@ class ChompEngine(object):
              history=False):
         """iters fused iterations with the reference's schedules (optimizer.py:63-80) in ONE persistent launch.
         history=True also records xi and the info row after every iteration (Planner.history_trajectories[1:] and
-        Planner.info, omg/planner.py:621-622): out["hist_xi"] [iters,B,n,9], out["hist_info"] [iters,B,16]."""
+        Planner.info, omg/planner.py:621-622): out["hist_xi"] [iters,B,n,9], out["hist_info"] [iters,B,16];
+        out["hist_all"] [iters+1,B,n,9] is the same storage with the initial trajectory in slot 0 (what
+        Planner.history_trajectories holds), so the host side needs one copy and no concatenation."""
         self.set_metric(cfg)
         iters = cfg.optim_steps + cfg.extra_smooth_steps if iters is None else iters
         B, n, c = xi.shape[0], cfg.timesteps, cfg.constraint_rows
@@ -210,7 +212,11 @@ class ChompEngine(object):
         ow, sw, ss = (np.ascontiguousarray(sched[:, k]) for k in range(3))
         info = torch.empty((B, _lib.INFO_STRIDE), dtype=torch.float64, device=xi.device)
         done = torch.zeros((B,), dtype=torch.uint8, device=xi.device)
-        hx = torch.empty((iters, B, n, 9), dtype=torch.float64, device=xi.device) if history else None
+        hall = torch.empty((iters + 1, B, n, 9), dtype=torch.float64, device=xi.device) if history else None
+        hx = None
+        if history:
+            hall[0].copy_(xi)
+            hx = hall[1:]
         hi = torch.empty((iters, B, _lib.INFO_STRIDE), dtype=torch.float64, device=xi.device) if history else None
         prm = self.params_from(cfg, True)
         _lib.check(self.L.omgb_chomp_plan_history(self._h, ctypes.byref(prm), iters, _hp(ow), _hp(sw), _hp(ss),
@@ -219,7 +225,7 @@ class ChompEngine(object):
                                                   _dp(hi), _stream()), "omgb_chomp_plan_history")
         out = {"info": info, "done": done}
         if history:
-            out["hist_xi"], out["hist_info"] = hx, hi
+            out["hist_xi"], out["hist_info"], out["hist_all"] = hx, hi, hall
         return out
 
     def set_host_mode(self, mode):

@@ -71,6 +71,16 @@ class InfoList(object):
         return (self[i] for i in range(len(self)))
 
 
+def _to_host_fresh(t):
+    """Device tensor -> numpy view of a FRESH pinned tensor (torch's caching host allocator recycles the block once
+    the caller drops the arrays): histories handed to the user must not alias a buffer the next plan overwrites, and
+    a pageable copy of a 150 MB history plus its concatenation cost more than the plan itself."""
+    buf = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+    buf.copy_(t, non_blocking=True)
+    torch.cuda.current_stream().synchronize()
+    return buf.numpy()
+
+
 def _to_host(t, cache, key):
     """Device tensor -> numpy through a cached pinned staging buffer (large histories: pageable copies are slow)."""
     buf = cache.get(key)
@@ -231,11 +241,12 @@ class Planner(GoalSetMixin):
         eng = cost.engine
         xi, start, end, rows, batched = cost._traj_tensors(traj)
         B, n, c = xi.shape[0], xi.shape[1], ecfg.constraint_rows
-        xi0 = xi.clone()
         st = DeviceLearnerState(lrn, xi.device)
         done = torch.zeros((B,), dtype=torch.uint8, device=xi.device)
         info = torch.empty((B, _lib.INFO_STRIDE), dtype=torch.float64, device=xi.device)
-        hist_xi = torch.empty((iters, B, n, 9), dtype=torch.float64, device=xi.device)
+        hist_all = torch.empty((iters + 1, B, n, 9), dtype=torch.float64, device=xi.device)
+        hist_all[0].copy_(xi)                          # history_trajectories[0] (planner.py:606)
+        hist_xi = hist_all[1:]
         hist_info = torch.zeros((iters, B, _lib.INFO_STRIDE), dtype=torch.float64, device=xi.device)
         n_sel = min(iters, cfg.optim_steps)
         selected = torch.zeros((max(n_sel, 1), B), dtype=torch.int32, device=xi.device)
@@ -266,10 +277,10 @@ class Planner(GoalSetMixin):
                                                   vp(hist_info.data_ptr()), stream), "omgb_chomp_plan_step")
             ran = t + 1
         if ran < iters:                                                  # stopped by cfg.timeout
-            iters, hist_xi, hist_info = ran, hist_xi[:ran], hist_info[:ran]
+            iters, hist_all, hist_info = ran, hist_all[:ran + 1], hist_info[:ran]
             n_sel = min(n_sel, ran)
         stage = self.__dict__.setdefault("_stage", {})
-        h_info, h_xi, sel = (_to_host(hist_info, stage, "info").copy(), _to_host(hist_xi, stage, "xi"),
+        h_info, hist, sel = (_to_host(hist_info, stage, "info").copy(), _to_host_fresh(hist_all),
                              selected.cpu().numpy())
         term = h_info[:, :, 8] > 0
         term[0] = False
@@ -283,18 +294,19 @@ class Planner(GoalSetMixin):
             ecfg = cost.engine_cfg()
             final = eng.step(ecfg, xi, start, end, rows, active=active, update=0)["info"].cpu().numpy()
         st.store()
-        sel_lists = self._assemble(traj, batched, xi0.cpu().numpy(), h_xi, h_info, stop, stopped, final,
-                                   xi.cpu().numpy(), sel=sel, n_sel=n_sel)
-        lrn.Ti = np.zeros((B, lrn.N))
-        for b in range(B):
-            np.add.at(lrn.Ti[b], sel_lists[b], 1)
+        self._assemble(traj, batched, hist, h_info, stop, stopped, final, xi.cpu().numpy(), sel=sel, n_sel=n_sel)
+        # Learner.Ti: how often every goal was selected over the iterations the trajectory's own loop ran
+        cut = np.minimum(stop + 1, n_sel)
+        live = np.arange(sel.shape[0])[:, None] < cut[None, :]
+        flat = (np.arange(B)[None, :] * lrn.N + sel)[live]
+        lrn.Ti = np.bincount(flat, minlength=B * lrn.N).reshape(B, lrn.N).astype(np.float64)
 
-    def _assemble(self, traj, batched, xi0, h_xi, h_info, stop, stopped, final, new_xi, sel=None, n_sel=0):
+    def _assemble(self, traj, batched, hist, h_info, stop, stopped, final, new_xi, sel=None, n_sel=0):
         """history_trajectories / info (/ selected_goals) per trajectory, each cut where the reference's loop would
-        have stopped for it (omg/planner.py:627-635).  Batched plans get views and lazily built dicts."""
+        have stopped for it (omg/planner.py:627-635).  hist: [iters + 1, B, n, 9], the initial trajectory in slot 0.
+        Batched plans get views and lazily built dicts."""
         cfg = self.cfg
-        B, n = xi0.shape[0], xi0.shape[1]
-        hist = np.concatenate([xi0[None], h_xi], axis=0)                # [iters + 1, B, n, 9]
+        B, n = hist.shape[1], hist.shape[2]
         infos, hists, sels = [], [], []
         for b in range(B):
             k = int(stop[b])
@@ -376,13 +388,12 @@ class Planner(GoalSetMixin):
         ecfg = cost.engine_cfg()
         xi, start, end, rows, batched = cost._traj_tensors(traj)
         B, n = xi.shape[0], xi.shape[1]
-        xi0 = xi.clone()
         first = self.optim.step + 1
         out = cost.engine.plan(ecfg, xi, start, end, rows, iters=iters, stop_on_terminate=True, first_step=first,
                                history=True)
         stage = self.__dict__.setdefault("_stage", {})
         hist_info = _to_host(out["hist_info"], stage, "info").copy()    # [iters,B,16]
-        hist_xi = _to_host(out["hist_xi"], stage, "xi")
+        hist = _to_host_fresh(out["hist_all"])                          # [iters + 1,B,n,9]
         term = hist_info[:, :, 8] > 0
         term[0] = False                                                 # the t > 0 rule (planner.py:627)
         stopped = term.any(0)
@@ -395,4 +406,4 @@ class Planner(GoalSetMixin):
             self.optim.update()                                         # schedule of the info-only call
             ecfg = cost.engine_cfg()
             final = cost.engine.step(ecfg, xi, start, end, rows, active=active, update=0)["info"].cpu().numpy()
-        self._assemble(traj, batched, xi0.cpu().numpy(), hist_xi, hist_info, stop, stopped, final, xi.cpu().numpy())
+        self._assemble(traj, batched, hist, hist_info, stop, stopped, final, xi.cpu().numpy())

@@ -34,3 +34,12 @@ def _worker(rank, world, port, batch):
 def test_all_gather_world_size_2_gloo():
     s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
     mp.spawn(_worker, args=(2, port, 9), nprocs=2, join=True)
+
+
+def test_numa_binding_helpers():
+    assert D._parse_cpulist("0-3,8,10-11\n") == {0, 1, 2, 3, 8, 10, 11}
+    assert D._parse_cpulist("") == set()
+    before = os.sched_getaffinity(0)
+    assert D.bind_host_to_device_numa(0) is None or isinstance(D.bind_host_to_device_numa(0), dict)   # no GPU here: no-op
+    if not torch.cuda.is_available():
+        assert os.sched_getaffinity(0) == before

@@ -34,7 +34,8 @@ def test_assemble_cuts_histories_like_the_reference_loop():
     traj = types.SimpleNamespace(set=lambda x: setattr(traj, "data", x), data=None)
     p = _planner(cfg)
     sel = np.arange(iters * B).reshape(iters, B)
-    sels = p._assemble(traj, True, xi0, h_xi, h_info, stop, stopped, final, h_xi[-1], sel=sel, n_sel=4)
+    hist = np.concatenate([xi0[None], h_xi], axis=0)         # slot 0 = the initial trajectory (one device buffer)
+    sels = p._assemble(traj, True, hist, h_info, stop, stopped, final, h_xi[-1], sel=sel, n_sel=4)
     # not terminated: initial state + every iteration; info list = every iteration + the info-only pass
     assert p.history_trajectories[0].shape[0] == iters + 1 and len(p.info[0]) == iters + 1
     np.testing.assert_array_equal(p.history_trajectories[0][0], xi0[0])
@@ -48,7 +49,7 @@ def test_assemble_cuts_histories_like_the_reference_loop():
     assert sels[0] == [0, 3, 6, 9] and sels[1] == [1, 4, 7]  # selections stop with the plan (and at optim_steps)
     # reference shape for one trajectory: plain lists
     p2 = _planner(cfg)
-    p2._assemble(traj, False, xi0[:1], h_xi[:, :1], h_info[:, :1], stop[:1], stopped[:1], final[:1], h_xi[-1, :1])
+    p2._assemble(traj, False, hist[:, :1], h_info[:, :1], stop[:1], stopped[:1], final[:1], h_xi[-1, :1])
     assert isinstance(p2.info, list) and isinstance(p2.history_trajectories, list) and traj.data.shape == (n, 9)
 
 

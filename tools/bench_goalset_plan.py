@@ -30,27 +30,45 @@ def main():
     goals, reach = S.make_goal_sets(B, G, robot.joint_lower_limit, robot.joint_upper_limit, seed=4, spread=0.3)
     res = {"workload": "%d trajectories x %d goals x 30 waypoints, 10 SDFs @128^3, ol_alg MD, standoff, 50 + 20 iterations, "
                        "pre_terminate off (every iteration runs)" % (B, G)}
-    for host in (True, False):
+    reps = int(os.environ.get("REPS", 2))
+    prof = os.environ.get("PLAN_PROFILE")          # cProfile of the last device-learner plan -> this file
+    for host in ((False,) if os.environ.get("SKIP_HOST") else (True, False)):
         cfg = ChompConfig(goal_set_proj=True, use_standoff=True, ol_alg="MD", pre_terminate=False, host_learner=host)
         env = H.make_env(sc, cfg, robot)
         target = env.objects[env.target_idx]
         target.grasps, target.reach_grasps = goals, reach
         traj = C.Trajectory(30, cfg=cfg, start=np.tile(S.START_CONF, (B, 1)), end=goals[:, 0])
         planner = Planner(env, traj)
-        for rep in range(2):   # second pass = warm
+        for rep in range(reps):   # later passes = warm
             traj = C.Trajectory(30, cfg=cfg, start=np.tile(S.START_CONF, (B, 1)), end=goals[:, 0])
             traj.goal_set = goals
             planner.update(env, traj)
             torch.cuda.synchronize()
+            pr = None
+            if prof and not host and rep == reps - 1:
+                import cProfile
+                pr = cProfile.Profile()
+                pr.enable()
             t0 = time.perf_counter()
             planner.plan(traj)
             torch.cuda.synchronize()
             dt = time.perf_counter() - t0
+            if pr is not None:
+                import io
+                import pstats
+                pr.disable()
+                buf = io.StringIO()
+                pstats.Stats(pr, stream=buf).sort_stats("cumulative").print_stats(35)
+                open(prof, "w").write("plan wall %.4f s\n" % dt + buf.getvalue())
         iters = cfg.optim_steps + cfg.extra_smooth_steps
         res["host_learner" if host else "device_learner"] = {
             "plan_wall_s": dt, "ms_per_iteration": dt / iters * 1e3, "trajectory_iterations_per_s": B * iters / dt,
             "goals_selected": int(len(set(np.array(planner.selected_goals).reshape(-1).tolist())))}
-    res["speedup"] = res["host_learner"]["plan_wall_s"] / res["device_learner"]["plan_wall_s"]
+    if "host_learner" in res:
+        res["speedup"] = res["host_learner"]["plan_wall_s"] / res["device_learner"]["plan_wall_s"]
+    if os.environ.get("SKIP_SINGLE"):
+        print(json.dumps(res))
+        return
     # one trajectory (the reference's own shape): whole Planner.plan latency, fixed goal (one persistent launch) and
     # goal set with the MD learner (device pipeline)
     one = {}

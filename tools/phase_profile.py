@@ -20,12 +20,13 @@ NAMES = ["stage", "fk", "cull", "compact", "points", "reduce+select", "cost", "w
 
 def main():
     mode = dict(goal_set_proj=True, use_standoff=True, top_k_collision=0 if "fullsum" in sys.argv else 1000)
-    B = 1024
-    sc = S.make_scene(num_objects=10, grid=128, seed=0)
-    cfg = ChompConfig(**mode)
+    B = int(os.environ.get("B", 1024))
+    W, O, GRID = int(os.environ.get("W", 30)), int(os.environ.get("O", 10)), int(os.environ.get("GRID", 128))
+    sc = S.make_scene(num_objects=O, grid=GRID, seed=0, device="cuda" if GRID > 128 else None)
+    cfg = ChompConfig(timesteps=W, **mode)
     robot = PandaConstants()
     eng = ChompEngine(robot=robot).load_scene(sc, cfg)
-    xi, st, en, tails = S.make_trajectories(B, 30, robot.joint_lower_limit, robot.joint_upper_limit, seed=0)
+    xi, st, en, tails = S.make_trajectories(B, W, robot.joint_lower_limit, robot.joint_upper_limit, seed=0)
     dev = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
     x, s, e, t = dev(xi), dev(st), dev(en), dev(tails)
     prof = torch.zeros((B, 16), dtype=torch.int64, device="cuda")
@@ -41,14 +42,14 @@ def main():
     p = p[:, :12]
     d = np.diff(p, axis=1)
     info = out["info"].cpu().numpy()
-    lines = ["mode %s; per-CTA cycles (mean / median / max over %d CTAs)" % (mode, B)]
+    lines = ["mode %s, %d waypoints, %d objects @%d^3; per-CTA cycles (mean / median / max over %d CTAs)" % (mode, W, O, GRID, B)]
     tot = (p[:, 11] - p[:, 0])
     for k, name in enumerate(NAMES):
         lines.append("%-14s mean %9.0f  median %9.0f  max %9.0f  share %.3f" % (
             name, d[:, k].mean(), np.median(d[:, k]), d[:, k].max(), d[:, k].sum() / tot.sum()))
     lines.append("total          mean %9.0f  median %9.0f  max %9.0f" % (tot.mean(), np.median(tot), tot.max()))
     lines.append("exact operator evaluations in the points phase: mean %.1f max %.0f per trajectory" % (exact.mean(), exact.max()))
-    lines.append("P_in mean %.1f  nnz mean %.1f  active link instances mean %.1f / 300  limit rounds mean %.2f" % (
+    lines.append("P_in mean %.1f  nnz mean %.1f  active link instances mean %.1f / (10 x waypoints)  limit rounds mean %.2f" % (
         info[:, 12].mean(), info[:, 13].mean(), info[:, 15].mean(), info[:, 14].mean()))
     order = np.argsort(-tot)[:6]
     lines.append("heaviest CTAs (cycles per phase):")
