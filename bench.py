@@ -298,6 +298,9 @@ def run_b200(a):
         it_h += 1
         flush.zero_()
         if events is not None:
+            # the flush must be over before the timed region starts: otherwise the host side of the call (argument
+            # marshalling, launch) would run hidden under it and the events would only see the kernel + sync
+            torch.cuda.synchronize()
             events[0].record()
         eng.step_host(cfg, hx, hs, he, ht)
         if events is not None:
@@ -395,7 +398,8 @@ def run_b200(a):
                 "ms_per_step": e2e_ms_max / a.steps,
                 "api": "omgb_chomp_step_host (pinned host buffers, mode 0: the fused kernel reads xi/start/end/goal "
                        "rows from and writes xi/info to mapped pinned host memory over PCIe -- the H2D/D2H bytes move "
-                       "inside the kernel; stream synchronised before return)",
+                       "inside the kernel; stream synchronised before return); timed per step by CUDA events recorded "
+                       "on an idle device (synchronised after the L2 flush), so the host side of the call is inside",
                 "ms_per_step_by_transfer_mode": {k: v / a.steps for k, v in e2e_modes.items()}},
         "e2e_plugin": e2e_plugin,
         "allgather_ms": allgather_ms,

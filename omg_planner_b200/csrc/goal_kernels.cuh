@@ -18,6 +18,11 @@
 // product of two floats, accumulated in 2^-40 fixed point (int64), so the result does not depend on queue order,
 // block shape or SDF layout.  (The reference's own sum over objects is an atomicAdd in arbitrary order followed by a
 // torch fp32 tree reduction: its value is defined to ~1e-6 relative; tests/test_gpu_goal_scoring.py holds 2e-5.)
+//
+// The lines get shorter as the plan proceeds (n' = timesteps - start, online_learner.py:109-114): a CTA takes as many
+// goals of its trajectory as fit ~30 configurations (1 goal at n' = 30, 6 at n' = 5), sharing the trajectory's
+// waypoint (slot 0) and its forward kinematics, so that late iterations do not pay a CTA's fixed cost per 5-waypoint
+// line.
 #pragma once
 #include "chomp_kernels.cuh"
 
@@ -25,6 +30,7 @@ namespace omgb {
 
 constexpr int GOAL_QCAP = 64;                       // queue entries per warp (a push adds <= 32 to <= 31 pending)
 constexpr double GOAL_FIX = 1099511627776.0;        // 2^40
+constexpr int GOAL_MAX_GPC = 32;                    // goals per CTA
 
 struct GoalArgs {
     const ObjRec *objs;
@@ -39,13 +45,14 @@ struct GoalArgs {
     DilDesc dil;
     RobotParams rp;
     int num_objects, num_goals, arc, finger_soft;
+    int gpc, ctas_per_traj;    // goals per CTA; CTAs per trajectory = ceil(num_goals / gpc)
     float inv_dt;
     unsigned off_q, off_sc, off_queue, off_qobj, off_frames, off_mask, off_mask_hi, off_act, off_red, off_objs,
         smem_total;
 };
 
 __host__ inline void goal_layout(GoalArgs &a, int warps) {
-    const int cfgs = a.arc + 1;
+    const int cfgs = a.gpc * a.arc + 1, n_li = a.gpc * a.arc * NL;
     unsigned o = 0;
     // region A: joint values + sin/cos table (dead once the frames exist), reused by the per-warp queues
     a.off_q = 0;
@@ -53,13 +60,13 @@ __host__ inline void goal_layout(GoalArgs &a, int warps) {
     const unsigned fk_bytes = a.off_sc + (unsigned)(sizeof(double2) * cfgs * 7);
     a.off_queue = 0;
     a.off_qobj = (unsigned)(sizeof(float4) * GOAL_QCAP * warps);
-    const unsigned q_bytes = a.off_qobj + (unsigned)(GOAL_QCAP * warps);
+    const unsigned q_bytes = a.off_qobj + (unsigned)(sizeof(unsigned short) * GOAL_QCAP * warps);
     o = align_up(fk_bytes > q_bytes ? fk_bytes : q_bytes, 16);
     a.off_frames = o; o += sizeof(double) * cfgs * NL * 12;
-    a.off_mask = o; o += sizeof(unsigned) * a.arc * NL;
-    a.off_mask_hi = o; if (a.num_objects > 32) o += sizeof(unsigned) * a.arc * NL;
-    a.off_act = o; o += align_up((unsigned)(sizeof(unsigned short) * (a.arc * NL + 2)) + 8, 8);
-    a.off_red = o; o += sizeof(long long) * 32;
+    a.off_mask = o; o += sizeof(unsigned) * n_li;
+    a.off_mask_hi = o; if (a.num_objects > 32) o += sizeof(unsigned) * n_li;
+    a.off_act = o; o += align_up((unsigned)(sizeof(unsigned short) * (n_li + 2)) + 8, 8);
+    a.off_red = o; o += sizeof(unsigned long long) * GOAL_MAX_GPC;
     o = align_up(o, 16);
     a.off_objs = o; o += sizeof(ObjRec) * a.num_objects;
     a.smem_total = align_up(o, 16);
@@ -77,13 +84,15 @@ goal_cost_kernel(const GoalArgs a) {
     unsigned *s_mask_hi = reinterpret_cast<unsigned *>(smem + a.off_mask_hi);
     int *s_count = reinterpret_cast<int *>(smem + a.off_act);                       // active link instances
     unsigned short *s_act = reinterpret_cast<unsigned short *>(smem + a.off_act + 8);   // (config << 4) | link
-    long long *s_red = reinterpret_cast<long long *>(smem + a.off_red);
+    unsigned long long *s_cost = reinterpret_cast<unsigned long long *>(smem + a.off_red);   // per goal of this CTA
     ObjRec *s_objs = reinterpret_cast<ObjRec *>(smem + a.off_objs);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr int NWARPS = THREADS / 32;
-    const int g = blockIdx.x % a.num_goals, b = blockIdx.x / a.num_goals;
-    const int arc = a.arc, cfgs = arc + 1, O = a.num_objects;
+    const int b = blockIdx.x / a.ctas_per_traj, g0 = (blockIdx.x % a.ctas_per_traj) * a.gpc;
+    const int ng = min(a.gpc, a.num_goals - g0);          // goals of this CTA: g0 .. g0 + ng - 1
+    // configuration slots: 0 = the trajectory's waypoint, then `arc` per goal line
+    const int arc = a.arc, cfgs = ng * arc + 1, O = a.num_objects;
     const RobotConst *__restrict__ rc = a.robot;
     const int P = rc->p;
 
@@ -94,18 +103,20 @@ goal_cost_kernel(const GoalArgs a) {
         uint4 *dst = reinterpret_cast<uint4 *>(s_objs);
         for (int k = tid; k < quads; k += THREADS) dst[k] = __ldg(src + k);
         if (tid == 0) *s_count = 0;
+        if (tid < GOAL_MAX_GPC) s_cost[tid] = 0ull;
     }
     {
         const double *qf = a.from + (size_t)b * a.from_stride;
-        const double *qg = a.goals + (size_t)b * a.goal_stride_b + (size_t)g * ND;
+        const double *qg0 = a.goals + (size_t)b * a.goal_stride_b + (size_t)g0 * ND;
         const double step = 1.0 / (double)(arc + 1);   // np.linspace(0, 1, arc + 2): i * step
         for (int k = tid; k < cfgs * ND; k += THREADS) {
-            const int i = k / ND, d = k - i * ND;
+            const int sl = k / ND, d = k - sl * ND;
             double v = qf[d];
-            if (i > 0) {
+            if (sl > 0) {
                 // scipy interp1d(kind="linear") on the two knots (0, from), (1, goal): w_hi * y_hi + w_lo * y_lo
+                const int l = (sl - 1) / arc, i = sl - l * arc;
                 const double t = (double)i * step;
-                v = __dadd_rn(__dmul_rn(t, qg[d]), __dmul_rn(__dsub_rn(1.0, t), v));
+                v = __dadd_rn(__dmul_rn(t, qg0[(size_t)l * ND + d]), __dmul_rn(__dsub_rn(1.0, t), v));
             }
             s_q[k] = v;
         }
@@ -125,7 +136,7 @@ goal_cost_kernel(const GoalArgs a) {
     }
     __syncthreads();
     // ---- cull every (waypoint, link) bounding sphere against every object (same tests as the fused step) ----
-    const int n_li = arc * NL;
+    const int n_li = ng * arc * NL;
     const bool use_dil = a.dil.enabled != 0;
     for (int base_li = 0; base_li < n_li; base_li += THREADS) {   // (uniform trip count: the ballot below needs whole warps)
         const int li = base_li + tid;
@@ -179,18 +190,35 @@ goal_cost_kernel(const GoalArgs a) {
     __syncthreads();   // (the sin/cos table and the joint values are dead: region A now holds the queues)
     const int n_act = *s_count;
     float4 *q_pt = reinterpret_cast<float4 *>(smem + a.off_queue) + warp * GOAL_QCAP;   // x, y, z, speed
-    unsigned char *q_ob = smem + a.off_qobj + warp * GOAL_QCAP;                           // object | finger flag
+    unsigned short *q_ob = reinterpret_cast<unsigned short *>(smem + a.off_qobj) + warp * GOAL_QCAP;   // object | finger flag | goal << 8
     int q_cnt = 0;
-    long long acc = 0;
-    // stage B for queue slot k: the operator's value-only evaluation, potential x speed in exact fp64, fixed point
+    // stage B for queue slot k (k < 0: this lane has none): the operator's value-only evaluation, potential x speed in
+    // exact fp64, fixed point; then one integer add per goal present in the batch (redux over 21-bit limbs)
     auto evaluate = [&](int k) {
-        const float4 it = q_pt[k];
-        const unsigned oo = q_ob[k];
-        float po, co;
-        pair_potential(s_objs[oo & 63u], a.grids, a.quad, it.x, it.y, it.z, po, co);
-        double v = (double)po * (double)it.w;
-        if (oo & 0x80u) v *= (double)0.1f;   // omg/cost.py:350-353 (soft finger links)
-        acc += __double2ll_rn(v * GOAL_FIX);
+        unsigned long long f = 0ull;
+        unsigned l = 0xffffffffu;
+        if (k >= 0) {
+            const float4 it = q_pt[k];
+            const unsigned oo = q_ob[k];
+            float po, co;
+            pair_potential(s_objs[oo & 63u], a.grids, a.quad, it.x, it.y, it.z, po, co);
+            double v = (double)po * (double)it.w;
+            if (oo & 0x80u) v *= (double)0.1f;   // omg/cost.py:350-353 (soft finger links)
+            f = (unsigned long long)__double2ll_rn(v * GOAL_FIX);   // (v >= 0)
+            if (f != 0ull) l = oo >> 8;
+        }
+        unsigned pending = __ballot_sync(0xffffffffu, l != 0xffffffffu);
+        while (pending) {
+            const unsigned l0 = __shfl_sync(0xffffffffu, l, __ffs(pending) - 1);
+            const bool mine = l == l0;
+            const unsigned long long w = mine ? f : 0ull;
+            const unsigned s0 = __reduce_add_sync(0xffffffffu, (unsigned)(w & 0x1fffffull));
+            const unsigned s1 = __reduce_add_sync(0xffffffffu, (unsigned)((w >> 21) & 0x1fffffull));
+            const unsigned s2 = __reduce_add_sync(0xffffffffu, (unsigned)(w >> 42));
+            if (lane == 0)
+                atomicAdd(s_cost + l0, (unsigned long long)s0 + ((unsigned long long)s1 << 21) + ((unsigned long long)s2 << 42));
+            pending &= ~__ballot_sync(0xffffffffu, mine);
+        }
     };
     // ---- body points: LPI lanes per (waypoint, link), lane per body point ----
     constexpr int GPW = 32 / LPI;
@@ -200,10 +228,10 @@ goal_cost_kernel(const GoalArgs a) {
         const int idx = base + sub;
         unsigned nlo = 0u, nhi = 0u;   // objects whose operator value this point needs
         float x = 0.0f, y = 0.0f, z = 0.0f, sp = 0.0f;
-        unsigned fing = 0u;
+        unsigned tag = 0u;
         if (idx < n_act && pl < P) {
             const unsigned v = s_act[idx];
-            const int i = (int)(v >> 4), j = (int)(v & 15u), li = i * NL + j;
+            const int i = (int)(v >> 4), j = (int)(v & 15u), li = i * NL + j;   // i: configuration index over the CTA's lines
             const double *F = s_frames + (size_t)(li + NL) * 12;
             const double *bp = rc->pts[j][pl];
             const double b0 = bp[0], b1 = bp[1], b2 = bp[2];
@@ -225,13 +253,16 @@ goal_cost_kernel(const GoalArgs a) {
                 }
             }
             if (nlo | nhi) {
-                // workspace speed against the previous configuration of the line (slot i; slot 0 = traj.data[start])
+                // workspace speed against the previous configuration of the line (a line's first one: slot 0 =
+                // traj.data[start])
+                const int l = i / arc;
+                const double *Fp = (i - l * arc == 0) ? (s_frames + (size_t)j * 12) : (F - NL * 12);
                 double Xp, Yp, Zp;
-                xform(F - NL * 12, b0, b1, b2, Xp, Yp, Zp);
+                xform(Fp, b0, b1, b2, Xp, Yp, Zp);
                 const float vx = (x - (float)Xp) * a.inv_dt, vy = (y - (float)Yp) * a.inv_dt,
                             vz = (z - (float)Zp) * a.inv_dt;
                 sp = sqrtf(vx * vx + vy * vy + vz * vz);
-                fing = (a.finger_soft && j >= 8) ? 0x80u : 0u;
+                tag = ((a.finger_soft && j >= 8) ? 0x80u : 0u) | ((unsigned)l << 8);
             }
         }
         // push this round's pairs, one object per lane and pass; evaluate whenever 32 are pending
@@ -245,7 +276,7 @@ goal_cost_kernel(const GoalArgs a) {
                 else { o = 32u + (unsigned)(__ffs(nhi) - 1); nhi &= nhi - 1; }
                 const int pos = q_cnt + __popc(bal & lt_mask);
                 q_pt[pos] = make_float4(x, y, z, sp);
-                q_ob[pos] = (unsigned char)(o | fing);
+                q_ob[pos] = (unsigned short)(o | tag);
             }
             q_cnt += __popc(bal);
             __syncwarp();
@@ -256,18 +287,9 @@ goal_cost_kernel(const GoalArgs a) {
             }
         }
     }
-    if (lane < q_cnt) evaluate(lane);
-    // ---- order-free reduction ----
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
-    if (lane == 0) s_red[warp] = acc;
+    if (q_cnt > 0) evaluate(lane < q_cnt ? lane : -1);   // (warp-uniform)
     __syncthreads();
-    if (tid == 0) {
-        long long t = 0;
-#pragma unroll
-        for (int w = 0; w < NWARPS; ++w) t += s_red[w];
-        a.costs[(size_t)b * a.num_goals + g] = (float)((double)t * (1.0 / GOAL_FIX));
-    }
+    if (tid < ng) a.costs[(size_t)b * a.num_goals + g0 + tid] = (float)((double)s_cost[tid] * (1.0 / GOAL_FIX));
 }
 
 }  // namespace omgb

@@ -1247,8 +1247,18 @@ extern "C" int omgb_goal_costs(omgb_scene_t *s, int batch, const double *from, l
     a.num_objects = s->num_objects; a.num_goals = num_goals; a.arc = arc_length;
     a.finger_soft = uncheck_finger_collision == -1 ? 1 : 0;
     a.inv_dt = (float)(1.0 / time_interval);
-    // block size by the number of link instances of a line (arc * 10): the cull is one instance per thread
-    const int n_li = arc_length * NL;
+    // goals per CTA: as many lines as fit ~30 configurations; block size by the number of link instances of a CTA
+    // (goals x arc x 10): the cull is one instance per thread
+    int gpc = arc_length >= 16 ? 1 : 30 / arc_length;
+    gpc = gpc > num_goals ? num_goals : (gpc > GOAL_MAX_GPC ? GOAL_MAX_GPC : gpc);
+    {
+        static int env_gpc = -1;
+        if (env_gpc < 0) { const char *e = getenv("OMGB_GOAL_GPC"); env_gpc = e ? atoi(e) : 0; }
+        if (env_gpc > 0) gpc = env_gpc > num_goals ? num_goals : (env_gpc > GOAL_MAX_GPC ? GOAL_MAX_GPC : env_gpc);
+    }
+    a.gpc = gpc;
+    a.ctas_per_traj = (num_goals + gpc - 1) / gpc;
+    const int n_li = gpc * arc_length * NL;
     const int lpi = s->p <= 16 ? 16 : 32;
     const int shape = lpi == 32 ? 2 : (n_li <= 128 ? 0 : n_li <= 192 ? 1 : n_li <= 256 ? 2 : 3);
     static const int shape_threads[4] = {128, 192, 256, 320};
@@ -1256,7 +1266,8 @@ extern "C" int omgb_goal_costs(omgb_scene_t *s, int batch, const double *from, l
     goal_layout(a, shape_threads[shape] / 32);
     if (a.smem_total > (unsigned)s->smem_optin)
         return fail(OMGB_ERR_UNSUPPORTED, "omgb_goal_costs: arc_length too long for one CTA's shared memory");
-    const int grid = batch * num_goals;
+    if ((long long)batch * a.ctas_per_traj > 0x7fffffffLL) return fail(OMGB_ERR_INVALID, "omgb_goal_costs: batch x goals too large");
+    const int grid = batch * a.ctas_per_traj;
     cudaStream_t gst = (cudaStream_t)stream;
     static unsigned cached[2][4][2][64] = {{{{0}}}};
     cudaError_t e_ = cudaSuccess;

@@ -308,14 +308,16 @@ class Planner(GoalSetMixin):
         cfg = self.cfg
         B, n = hist.shape[1], hist.shape[2]
         infos, hists, sels = [], [], []
+        stop_l, stopped_l = np.asarray(stop).tolist(), np.asarray(stopped).tolist()
+        sel_t = None if sel is None else np.ascontiguousarray(np.asarray(sel).T)    # [B, n_sel]: rows .tolist() in C
         for b in range(B):
-            k = int(stop[b])
+            k = stop_l[b]
             # terminated: the state after the terminating iteration is dropped from the history (:634-635)
-            hists.append(hist[:k + 1, b] if stopped[b] else hist[:k + 2, b])
-            extra = None if stopped[b] else final[b]
+            hists.append(hist[:k + 1, b] if stopped_l[b] else hist[:k + 2, b])
+            extra = None if stopped_l[b] else final[b]
             infos.append(InfoList(cfg, h_info[:k + 1, b], n, extra))
-            if sel is not None:
-                sels.append([int(v) for v in sel[:min(k + 1, n_sel), b]])
+            if sel_t is not None:
+                sels.append(sel_t[b, :min(k + 1, n_sel)].tolist())
         traj.set(new_xi if batched else new_xi[0])
         if batched:
             self.info, self.history_trajectories = infos, hists

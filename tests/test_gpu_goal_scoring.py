@@ -30,7 +30,8 @@ def _dev(a):
     return torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64)).cuda()
 
 
-@pytest.mark.parametrize("first,shared", [(0, False), (11, False), (29, True), (20, True)])
+# line lengths 30 / 19 (one goal per CTA), 12 / 7 (2 / 4 goals per CTA, the last CTA ragged), 10 (3 per CTA), 1 (all 9)
+@pytest.mark.parametrize("first,shared", [(0, False), (11, False), (29, True), (20, True), (18, False), (23, True)])
 def test_goal_costs_vs_oracle(first, shared):
     sc = S.make_scene(num_objects=6, grid=48, seed=11, grid_choices=[32, 40, 48])
     cfg = ChompConfig(goal_set_proj=True, use_standoff=True)

@@ -426,7 +426,7 @@ def run_config5(rank, world, total=512, n=50, objects=30, goals_per_traj=20, par
     return block
 
 
-def run_config3(rank, world, scenes=100, B=256, n=30, goals_per_traj=20, streams=4, parity=True):
+def run_config3(rank, world, scenes=100, B=256, n=30, goals_per_traj=20, streams=3, parity=True):
     import torch
 
     from omg_planner_b200 import _lib
@@ -451,22 +451,58 @@ def run_config3(rank, world, scenes=100, B=256, n=30, goals_per_traj=20, streams
     t_build = time.perf_counter() - t0
     iters = plans[0][2].optim_steps + plans[0][2].extra_smooth_steps
 
-    def sweep(num_streams):
-        st = [torch.cuda.Stream() for _ in range(num_streams)]
+    def sweep(num_threads):
+        """One pass over this rank's scenes.  num_threads > 1: that many host threads, each with its own CUDA stream,
+        take scenes from a shared queue (scenes are independent; every Planner owns its scene handle) -- one scene's
+        host tail (history D2H, info lists) overlaps the next scenes' kernels."""
         trajs = [_fresh_traj(p, env, cfg, goals, n) for p, env, cfg, goals, _, _ in plans]
         _barrier()
         t0 = time.perf_counter()
-        for k, (p, env, cfg, goals, _, _) in enumerate(plans):
-            with torch.cuda.stream(st[k % num_streams]):
+        if num_threads <= 1:
+            for k, (p, env, cfg, goals, _, _) in enumerate(plans):
                 p.plan(trajs[k])
+        else:
+            import queue
+            import threading
+
+            todo, errs = queue.SimpleQueue(), []
+            for k in range(len(plans)):
+                todo.put(k)
+
+            def worker():
+                torch.cuda.set_device(dev)
+                with torch.cuda.stream(torch.cuda.Stream()):
+                    try:
+                        while True:
+                            try:
+                                k = todo.get_nowait()
+                            except queue.Empty:
+                                return
+                            plans[k][0].plan(trajs[k])
+                    except Exception as e:   # noqa: BLE001
+                        errs.append(e)
+
+            ths = [threading.Thread(target=worker) for _ in range(num_threads)]
+            for t in ths:
+                t.start()
+            for t in ths:
+                t.join()
+            if errs:
+                raise errs[0]
         torch.cuda.synchronize()
-        return time.perf_counter() - t0
+        return time.perf_counter() - t0, trajs
 
     sweep(1)   # warm-up
     l0 = int(_lib.lib().omgb_launch_count())
-    t_seq = sweep(1)
+    t_seq, trajs_seq = sweep(1)
     launches = int(_lib.lib().omgb_launch_count()) - l0
-    wall_ms = _max_over_ranks(t_seq * 1e3)
+    seq_final = [np.array(t.data) for t in trajs_seq]
+    sweep(streams)   # warm-up of the threads' streams
+    t_par, trajs_par = sweep(streams)
+    same = all(np.array_equal(a, np.array(t.data)) for a, t in zip(seq_final, trajs_par))
+    del seq_final, trajs_seq, trajs_par
+    seq_ms = _max_over_ranks(t_seq * 1e3)
+    wall_ms = _max_over_ranks(t_par * 1e3)
     total = scenes * B
     block = {
         "workload": "config3: -exp sweep, %d scenes x %d traj x %d wpt, 5-10 SDFs per scene (64^3..128^3), goal sets of %d "
@@ -474,8 +510,14 @@ def run_config3(rank, world, scenes=100, B=256, n=30, goals_per_traj=20, streams
                     "split over %d GPU(s) (%d per GPU)" % (scenes, B, n, goals_per_traj, world, len(mine)),
         "value": total * iters / (wall_ms * 1e-3), "unit": METRIC_UNIT, "scaling": "strong",
         "ms_per_step": wall_ms / (len(mine) * iters), "steps": len(mine) * iters, "scenes_per_gpu": len(mine),
-        "timing": "host wall clock around the loop of Planner.plan calls over this rank's scenes (one scene after the "
-                  "other; numpy in / out, H2D and D2H inside), after a warm-up sweep, max over ranks",
+        "host_threads": streams,
+        "value_one_scene_at_a_time": total * iters / (seq_ms * 1e-3),
+        "ms_per_step_one_scene_at_a_time": seq_ms / (len(mine) * iters),
+        "concurrent_equals_sequential": bool(same),
+        "timing": "host wall clock around the sweep of Planner.plan calls over this rank's scenes (numpy in / out, H2D and "
+                  "D2H inside), after a warm-up sweep, max over ranks; value: %d host threads with one CUDA stream each "
+                  "pull scenes from a queue (independent scenes; identical results); value_one_scene_at_a_time: a plain "
+                  "loop" % streams,
         "gpu_launches_per_sweep": launches, "scene_and_planner_build_s": t_build,
     }
     if parity and rank == 0:

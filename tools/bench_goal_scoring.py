@@ -30,7 +30,7 @@ def main():
     x, g = dev(xi), dev(goals)
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
     res = {}
-    for first in (0, 15):
+    for first in (0, 15, 24):
         for _ in range(3):
             out = eng.goal_costs(x, first, g, cfg.time_interval, 0)
         torch.cuda.synchronize()
