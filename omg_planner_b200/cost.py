@@ -45,7 +45,7 @@ class BatchInfos(object):
     def __init__(self, cost, cfg, rows, n, grad_dev, rowobs_dev, xi_before, start, end):
         self._cost, self._cfg, self.rows, self._n = cost, cfg, rows, n
         self._grad_dev, self._rowobs_dev, self._host = grad_dev, rowobs_dev, None
-        self._before, self._start, self._end = xi_before, start, end
+        self._before, self._start, self._end = xi_before, start, end   # (xi_before: numpy, or a device tensor fetched on demand)
         self._cache = {}
 
     def __len__(self):
@@ -74,6 +74,8 @@ class BatchInfos(object):
             raise IndexError(b)
         if b not in self._cache:
             grad = self.gradient()
+            if torch.is_tensor(self._before):
+                self._before = self._before.cpu().numpy()
             self._cache[b] = self._cost._info_dict(self._cfg, self.rows[b], self._n, grad[b], self._host[1][b],
                                                    self._before[b], self._start[b], self._end[b])
         return self._cache[b]
@@ -91,6 +93,7 @@ class Cost(object):
             self.target_obj = self.env.objects[self.env.target_idx]
         self.engine = ChompEngine()
         self._stage = {}
+        self._pinned = {}      # id(ndarray) -> (weakref to it, the pinned tensor it views): results handed out by evaluate()
         self._robot_sig = None
         self._sdf_sig = None
         self._obj_sig = None
@@ -174,9 +177,31 @@ class Cost(object):
             slot = (torch.empty(arr.shape, dtype=torch.float64).pin_memory(),
                     torch.empty(arr.shape, dtype=torch.float64, device=dev))
             self._stage[key] = slot
+        ent = self._pinned.get(id(arr))
+        if ent is not None and ent[0]() is arr and ent[1].shape == slot[1].shape:
+            # the array is the pinned result of the previous evaluate() (Optimizer.optimize put it back into
+            # traj.data): copy straight from it, no staging memcpy
+            slot[1].copy_(ent[1], non_blocking=True)
+            return slot[1]
         np.copyto(slot[0].numpy(), arr)
         slot[1].copy_(slot[0], non_blocking=True)
         return slot[1]
+
+    def _fresh_pinned_result(self, dev_tensor):
+        """Device tensor -> a FRESH pinned host tensor (async copy on the current stream; torch's caching host allocator
+        recycles the block once the caller drops the array).  Returned as (tensor, register) where register(ndarray)
+        remembers the numpy view so that the next evaluate() can copy from it directly."""
+        import weakref
+
+        host = torch.empty(dev_tensor.shape, dtype=dev_tensor.dtype, pin_memory=True)
+        host.copy_(dev_tensor, non_blocking=True)
+
+        def register(arr):
+            if len(self._pinned) > 8:
+                self._pinned = {k: v for k, v in self._pinned.items() if v[0]() is not None}
+            self._pinned[id(arr)] = (weakref.ref(arr), host)
+            return arr
+        return host, register
 
     def _traj_tensors(self, traj):
         data = np.asarray(traj.data, dtype=np.float64)
@@ -253,23 +278,23 @@ class Cost(object):
         cfg = self.engine_cfg()
         xi, start, end, rows, batched = self._traj_tensors(traj)
         want_dbg = bool(getattr(self.cfg, "vis", False))
-        before = np.array(traj.data, dtype=np.float64, copy=True)
-        before = before if batched else before[None]
+        before = xi.clone()     # (device copy; fetched only if somebody looks at cost_traj)
         out = self.engine.step(cfg, xi, start, end, rows, update=update_mode, want_grad=True, debug=want_dbg,
                                want_row_obs=True)
         B, n = xi.shape[0], xi.shape[1]
-        host = self._stage.get(("host", B, n))
-        if host is None:
-            host = (torch.empty((B, n, 9), dtype=torch.float64).pin_memory(),
-                    torch.empty((B, out["info"].shape[1]), dtype=torch.float64).pin_memory())
-            self._stage[("host", B, n)] = host
-        host[0].copy_(xi, non_blocking=True)
-        host[1].copy_(out["info"], non_blocking=True)
+        host_xi, register = self._fresh_pinned_result(xi)
+        host_info = self._stage.get(("host_info", B))
+        if host_info is None:
+            host_info = torch.empty((B, out["info"].shape[1]), dtype=torch.float64).pin_memory()
+            self._stage[("host_info", B)] = host_info
+        host_info.copy_(out["info"], non_blocking=True)
         torch.cuda.current_stream().synchronize()
-        new_xi, info_rows = host[0].numpy().copy(), host[1].numpy().copy()
+        new_xi, info_rows = host_xi.numpy(), host_info.numpy().copy()
+        if batched:
+            register(new_xi)    # Optimizer.optimize hands this very array back as traj.data
         st_h, en_h = self._stage["start"][0].numpy().copy(), self._stage["end"][0].numpy().copy()
         self._last_start, self._last_end = st_h, en_h
-        infos = BatchInfos(self, cfg, info_rows, n, out["grad"].clone(), out["row_obs"].clone(), before, st_h, en_h)
+        infos = BatchInfos(self, cfg, info_rows, n, out["grad"], out["row_obs"], before, st_h, en_h)
         if want_dbg:
             self._fill_collision_pts(infos, out)
         return (infos if batched else [infos[0]]), new_xi, batched
