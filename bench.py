@@ -511,7 +511,7 @@ def run_plugin_e2e(a, scene, mode, xi0, st, en, tails, robot, steps):
             target.reach_grasps = [tails[0]] if name == "single" else tails[:, None]
         opt = Optimizer(env, cost)
         calls = max(steps, 20) if name == "single" else steps
-        for _ in range(3):
+        for _ in range(6):   # (past the transient: the result arrays cycle through three pinned blocks)
             opt.optimize(traj, force_update=True)
         torch.cuda.synchronize()
         t0 = time.perf_counter()
@@ -523,8 +523,10 @@ def run_plugin_e2e(a, scene, mode, xi0, st, en, tails, robot, steps):
         res[name] = {"trajectories": nb, "ms_per_call": ms, "value": nb / (ms * 1e-3), "unit": "trajectory-iterations/s",
                      "calls": calls}
     res["api"] = ("omg_planner_b200.optimizer.Optimizer.optimize(traj, force_update=True) over Cost.evaluate: numpy "
-                  "trajectory -> pinned staging -> H2D -> ONE fused launch -> D2H of xi + the [B,16] info array; "
-                  "gradient / cost_traj / per-trajectory dicts fetched lazily for a batch; host wall clock per call")
+                  "trajectory -> H2D (straight from the array when it is the pinned result of the previous call, else "
+                  "through pinned staging) -> ONE fused launch -> D2H of xi into a fresh pinned array (the new "
+                  "traj.data) + the [B,16] info array; gradient / cost_traj / per-trajectory dicts fetched lazily for "
+                  "a batch; host wall clock per call")
     res["reference_call"] = "omg/planner.py:621 self.optim.optimize(traj, force_update=True) (omg/optimizer.py:115-135)"
     return res
 

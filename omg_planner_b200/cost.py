@@ -62,7 +62,8 @@ class BatchInfos(object):
     def gradient(self):
         """[B,n,9] numpy (one D2H copy, cached)."""
         if self._host is None:
-            self._host = (self._grad_dev.cpu().numpy(), self._rowobs_dev.cpu().numpy())
+            to_np = lambda t: t.cpu().numpy() if torch.is_tensor(t) else t
+            self._host = (to_np(self._grad_dev), to_np(self._rowobs_dev))
         return self._host[0]
 
     def __getitem__(self, b):
@@ -197,8 +198,9 @@ class Cost(object):
         host.copy_(dev_tensor, non_blocking=True)
 
         def register(arr):
-            if len(self._pinned) > 8:
-                self._pinned = {k: v for k, v in self._pinned.items() if v[0]() is not None}
+            # entries of arrays the caller has dropped go first: their pinned blocks return to torch's host cache, so
+            # a loop of optimize() calls cycles through two or three blocks instead of pinning new memory every call
+            self._pinned = {k: v for k, v in self._pinned.items() if v[0]() is not None}
             self._pinned[id(arr)] = (weakref.ref(arr), host)
             return arr
         return host, register
@@ -288,13 +290,25 @@ class Cost(object):
             host_info = torch.empty((B, out["info"].shape[1]), dtype=torch.float64).pin_memory()
             self._stage[("host_info", B)] = host_info
         host_info.copy_(out["info"], non_blocking=True)
+        grad, row_obs = out["grad"], out["row_obs"]
+        if not batched:
+            # one trajectory: its info dict is built right away (the reference's shape), so the gradient, the per-row
+            # obstacle costs and the previous state ride back behind the same synchronisation
+            small = self._stage.get(("host_small", n))
+            if small is None:
+                small = tuple(torch.empty(shp, dtype=torch.float64).pin_memory() for shp in ((1, n, 9), (1, n), (1, n, 9)))
+                self._stage[("host_small", n)] = small
+            for dst, src in zip(small, (grad, row_obs, before)):
+                dst.copy_(src, non_blocking=True)
         torch.cuda.current_stream().synchronize()
         new_xi, info_rows = host_xi.numpy(), host_info.numpy().copy()
         if batched:
             register(new_xi)    # Optimizer.optimize hands this very array back as traj.data
+        else:
+            grad, row_obs, before = (t.numpy().copy() for t in small)
         st_h, en_h = self._stage["start"][0].numpy().copy(), self._stage["end"][0].numpy().copy()
         self._last_start, self._last_end = st_h, en_h
-        infos = BatchInfos(self, cfg, info_rows, n, out["grad"], out["row_obs"], before, st_h, en_h)
+        infos = BatchInfos(self, cfg, info_rows, n, grad, row_obs, before, st_h, en_h)
         if want_dbg:
             self._fill_collision_pts(infos, out)
         return (infos if batched else [infos[0]]), new_xi, batched

@@ -427,6 +427,7 @@ def run_config5(rank, world, total=512, n=50, objects=30, goals_per_traj=20, par
 
 
 def run_config3(rank, world, scenes=100, B=256, n=30, goals_per_traj=20, streams=3, parity=True):
+    streams = int(os.environ.get("OMGB_SWEEP_THREADS", streams))
     import torch
 
     from omg_planner_b200 import _lib
