@@ -20,6 +20,13 @@
 #include "../../include/omgb200.h"
 #include "sdf_device.cuh"
 
+#ifdef OMGB_NO_FP64_FMA
+// Experiment only (tools/gpu_r02y.sh): every explicit fp64 multiply-add of the fused step rounded
+// twice -- with -fmad=false for the implicit ones -- to see whether the 70-iteration outliers against the numpy oracle
+// are an artefact of fused rounding.  The shipped library is built without this.
+#define fma(a, b, c) __dadd_rn(__dmul_rn((a), (b)), (c))
+#endif
+
 namespace omgb {
 
 constexpr int NL = OMGB_NUM_LINKS;

@@ -89,3 +89,43 @@ def test_batch_obstacle_cost_with_and_without_arc_length():
                                             start=start, end=goals)
     rp, _, _ = R.batch_obstacle_cost(R.PandaRef(), sc, R.RefConfig(), traj, n, 0, start)
     np.testing.assert_allclose(pot.cpu().numpy(), rp, rtol=2e-5, atol=1e-6)
+
+
+def test_batched_optimize_hands_out_arrays_that_stay_put():
+    """Optimizer.optimize replaces traj.data by a new array every call (omg/core.py:43-57) and the caller may keep the
+    old ones (Planner.history_trajectories).  Here the new array is a view of a pinned block that the next call copies
+    from directly and that is recycled once dropped: arrays still held must never change, the batched path must
+    equal per-trajectory calls, and a caller that edits traj.data in place (or swaps in its own array) must be seen."""
+    mode = H.MODES["goalset_standoff_topk"]
+    sc = S.make_scene(num_objects=6, grid=48, seed=11, grid_choices=[32, 40, 48])
+    robot = PandaConstants()
+    xi, st, en, tails = S.make_trajectories(5, 30, robot.joint_lower_limit, robot.joint_upper_limit, seed=4)
+
+    def run(batched_ix, edit):
+        cfg = ChompConfig(**mode)
+        env = H.make_env(sc, cfg, robot)
+        cost = Cost(env)
+        optim = Optimizer(env, cost)
+        ix = batched_ix
+        env.objects[env.target_idx].reach_grasps = tails[ix][:, None]
+        cost.target_obj = env.objects[env.target_idx]
+        traj = H.FakeTrajectory(xi[ix].copy(), st[ix], en[ix], goal_set=en[ix][:, None], goal_idx=np.zeros(len(ix), dtype=int))
+        held, snaps = [], []
+        for t in range(8):
+            optim.optimize(traj, force_update=True)
+            held.append(traj.data)
+            snaps.append(traj.data.copy())
+            if edit and t == 3:
+                traj.data[:, 5, 2] += 0.01            # in place, in the pinned block
+            if edit and t == 5:
+                traj.data = traj.data * 1.0           # the caller's own (pageable) array
+        for a, b in zip(held, snaps):
+            if not (edit and a is held[3]):
+                np.testing.assert_array_equal(a, b)
+        return traj.data.copy()
+
+    all5 = run(np.arange(5), edit=False)
+    for b in range(5):
+        np.testing.assert_array_equal(run(np.array([b]), edit=False)[0], all5[b])
+    edited = run(np.arange(5), edit=True)
+    assert np.abs(edited - all5).max() > 1e-6          # the in-place edit went through the next iterations
