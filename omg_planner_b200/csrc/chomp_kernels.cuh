@@ -68,6 +68,12 @@ struct SmemLayout {
 
 __host__ __device__ inline unsigned align_up(unsigned v, unsigned a) { return (v + a - 1) / a * a; }
 
+// Points phase of the top-k path: every warp owns a ring of pending exact (body point, object) pairs and the potential
+// accumulators of the PQ_WIN rounds (32 body-point lanes each) whose pairs may be in flight.
+constexpr int PQ_CAP = 64;    // ring entries per warp (at most 31 pending + 32 pushed)
+constexpr int PQ_WIN = 4;     // rounds per window
+constexpr unsigned PQ_WARP_BYTES = PQ_CAP * 16u + PQ_WIN * 32u * 4u;
+
 // Shared memory of one CTA (one trajectory).  Sized so that a 30-waypoint trajectory fits four times and a
 // 60-waypoint one twice into an SM's 228 KB: the per-point potentials of the top-k path live in a global scratch
 // (written and read once by the same CTA, L2-resident), link gradients only for the links that can own a winner,
@@ -86,6 +92,8 @@ __host__ __device__ inline SmemLayout make_layout(int n, int c, int lpi, int nob
     // link gradients [n*nlu][8] fp64; aliased with the sin/cos table of the FK phase
     unsigned lg = sizeof(double) * n * L.nlu * NS, sc = sizeof(double2) * (n + 2) * 7;
     unsigned u = lg > sc ? lg : sc;
+    // top-k mode: the region is dead between the FK phase and phase 4b and holds the points phase's per-warp queues
+    if (topk && (unsigned)nwarps * PQ_WARP_BYTES > u) u = (unsigned)nwarps * PQ_WARP_BYTES;
     o = align_up(o, 16);   // double2 sin/cos table
     L.off_lg = o; o += align_up(u, 16);
     // grad / u / viol (+ the scan scratch of metric_apply) live in the frames region: the link frames are dead once
@@ -153,6 +161,7 @@ struct StepArgs {
     int metric_kind;         // 0: dense Ainv; 1: Ainv = s*min(i,j) (goal-set, free end); 2: s*min(i,j)(n+1-max(i,j))/(n+1)
     double metric_scale;     // s (= dt^2)
     int bulk_stage;          // 1: xi and the object records are device memory -> staged by cp.async.bulk (TMA)
+    int win_seg_min;         // phase 4b: from this many winners on (and more than blockDim / 4) pairs are evaluated one per lane
     int iteration;           // index inside a plan (for the t > 0 rule of planner.py:627)
     int stop_on_terminate;
     omgb_step_params_t prm;
@@ -492,6 +501,105 @@ __device__ __forceinline__ void winners_pass(const WinCtx &c) {
     }
 }
 
+// Phase 4b for MANY winners: one lane per winner would walk its object mask serially and divergently (the heaviest
+// trajectories: ~200 winners x up to 10 objects, the longest phase of the launch's critical path).  Here a warp takes a
+// chunk of winners (lane = winner), classifies every (winner, object) pair with one lower-bound load, and then evaluates
+// the surviving pairs ONE PER LANE, 32 at a time: pair t of the chunk belongs to the winner w with
+// excl[w] <= t < incl[w] (prefix sums of the per-winner pair counts, found by a shuffle binary search) and is that
+// winner's (t - excl[w])-th surviving object.  Results return to the owner by shuffles in pair order, so a winner's
+// fp32 sums run over its objects in ascending order exactly as in the one-lane form.  No shared memory.
+__device__ __forceinline__ void winners_pass_seg(const WinCtx &c) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    int per = (c.n_win + nwarps - 1) / nwarps;   // winners per warp and chunk: all warps busy, at most one per lane
+    per = per > 32 ? 32 : per;
+    for (int cbase = warp * per; cbase < c.n_win; cbase += nwarps * per) {   // (warp-uniform)
+        const int idx = cbase + lane;
+        const bool have = lane < per && idx < c.n_win;
+        const int li = have ? c.win[idx] : 0;
+        const int i = li / NL, j = li - i * NL;
+        const double *F = c.frames + (size_t)li * 12;
+        const double *bp = c.rc->pts[j][have ? c.bestp[li] : 0];
+        const double b0 = bp[0], b1 = bp[1], b2 = bp[2];
+        double X, Y, Z;
+        xform(F, b0, b1, b2, X, Y, Z);
+        const float x = (float)X, y = (float)Y, z = (float)Z;
+        unsigned nlo = 0u, nhi = 0u;
+        if (have) {
+            unsigned m = c.mask_lo[li];
+            while (m) {
+                const int o = __ffs(m) - 1;
+                m &= m - 1;
+                if (!c.use_dil || classify_pair(c.objs[o], *c.dil, o, x, y, z) == PAIR_EXACT) nlo |= 1u << o;
+            }
+            if (c.mask_hi) {
+                m = c.mask_hi[li];
+                while (m) {
+                    const int o = __ffs(m) - 1;
+                    m &= m - 1;
+                    if (!c.use_dil || classify_pair(c.objs[o + 32], *c.dil, o + 32, x, y, z) == PAIR_EXACT) nhi |= 1u << o;
+                }
+            }
+        }
+        const int cnt = __popc(nlo) + __popc(nhi);
+        int incl = cnt;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, off);
+            if (lane >= off) incl += t;
+        }
+        const int excl = incl - cnt, total = __shfl_sync(0xffffffffu, incl, 31);
+        float pot = 0.0f, gx = 0.0f, gy = 0.0f, gz = 0.0f;
+        for (int t0 = 0; t0 < total; t0 += 32) {
+            const bool on = t0 + lane < total;
+            const int t = on ? t0 + lane : total - 1;
+            int lo = 0, hi = 31;   // owner: the first lane whose inclusive count exceeds t
+#pragma unroll
+            for (int q = 0; q < 5; ++q) {
+                const int mid = (lo + hi) >> 1;
+                if (__shfl_sync(0xffffffffu, incl, mid) > t) hi = mid;
+                else lo = mid + 1;
+            }
+            const int w = lo;
+            const int k = t - __shfl_sync(0xffffffffu, excl, w);
+            const unsigned wl = __shfl_sync(0xffffffffu, nlo, w), wh = __shfl_sync(0xffffffffu, nhi, w);
+            const float wx = __shfl_sync(0xffffffffu, x, w), wy = __shfl_sync(0xffffffffu, y, w),
+                        wz = __shfl_sync(0xffffffffu, z, w);
+            float po = 0.0f, ax = 0.0f, ay = 0.0f, az = 0.0f, co;
+            if (on) {
+                const int nl = __popc(wl);
+                const int o = (k < nl) ? (int)__fns(wl, 0, k + 1) : 32 + (int)__fns(wh, 0, k - nl + 1);
+                pair_full(c.objs[o], c.grids, *c.quad, wx, wy, wz, po, ax, ay, az, co);
+            }
+            // back to the owners, in pair order
+            const int s0 = max(excl, t0) - t0, m = min(incl, t0 + 32) - t0 - s0;   // this batch holds m of my pairs from lane s0
+            const int mmax = __reduce_max_sync(0xffffffffu, m);
+            for (int r = 0; r < mmax; ++r) {
+                const int src = (s0 + r) & 31;
+                const float vp = __shfl_sync(0xffffffffu, po, src), vx = __shfl_sync(0xffffffffu, ax, src),
+                            vy = __shfl_sync(0xffffffffu, ay, src), vz = __shfl_sync(0xffffffffu, az, src);
+                if (r < m) {
+                    pot = __fadd_rn(pot, vp);
+                    gx = __fadd_rn(gx, vx); gy = __fadd_rn(gy, vy); gz = __fadd_rn(gz, vz);
+                }
+            }
+        }
+        if (c.finger_soft && j >= 8) {
+            pot = __fmul_rn(pot, 0.1f); gx = __fmul_rn(gx, 0.1f); gy = __fmul_rn(gy, 0.1f); gz = __fmul_rn(gz, 0.1f);
+        }
+        if (have) {
+            const double *Fp = (i > 0) ? (F - NL * 12) : (c.frames + ((size_t)c.n * NL + j) * 12);
+            const double *Fn = (i < c.n - 1) ? (F + NL * 12) : (c.frames + ((size_t)(c.n + 1) * NL + j) * 12);
+            double xp, yp, zp, xn, yn, zn, wx, wy, wz;
+            xform(Fp, b0, b1, b2, xp, yp, zp);
+            xform(Fn, b0, b1, b2, xn, yn, zn);
+            fg_weight(X, Y, Z, xp, yp, zp, xn, yn, zn, (double)pot, (double)gx, (double)gy, (double)gz, c.inv_dt, wx, wy, wz);
+#pragma unroll 1
+            for (int s = 0; s < NS; ++s)
+                c.lg[((size_t)i * c.nlu + j) * NS + s] = fg_slot(c.rc, c.frames + (size_t)i * NL * 12, j, s, X, Y, Z, wx, wy, wz);
+        }
+    }
+}
+
 // dst = Ainv * src for [n][9] arrays in shared memory (all threads call; ends with a barrier).  The smoothness metric
 // A = K^T K is tridiagonal, so its inverse has the closed forms above and Ainv * g is two running
 // sums per DOF column instead of a dense n x n product: 9 threads scan, everyone combines.  tmp: [2][n][9] scratch.
@@ -743,82 +851,201 @@ __device__ __forceinline__ void chomp_iteration(const StepArgs &a, unsigned char
     const int jmax = (topk_mode && !prm.consider_finger) ? NL - 2 : NL;   // links that count towards cost / gradient
     int t_nnz = 0, t_col = 0, t_exact = 0;
     double t_cost = 0.0;
-    for (int base = warp * GPW; base < n_act; base += nwarps * GPW) {
-        const int idx = base + sub;
-        const bool have = idx < n_act;
-        const int li = s_act[have ? idx : n_act - 1];
-        const bool live = have && (pl < P);
-        const int i = li / NL, j = li - i * NL;
-        const double *F = s_frames + (size_t)li * 12;
-        const double *bp = rc->pts[j][pl < P ? pl : 0];
-        double X, Y, Z;
-        xform(F, bp[0], bp[1], bp[2], X, Y, Z);
-        const float x = (float)X, y = (float)Y, z = (float)Z;   // omg/cost.py:136 .float()
-        float pot = 0.0f, col = 0.0f, gx = 0.0f, gy = 0.0f, gz = 0.0f;
-#pragma unroll 1
-        for (int half = 0; half < (s_mhi ? 2 : 1); ++half) {   // object mask: one or two 32-bit words
-            unsigned m = live ? (half ? s_mhi[li] : s_mlo[li]) : 0u;
-            while (m) {
-                const int o = __ffs(m) - 1 + 32 * half;
-                m &= m - 1;
-                float po, co;
-                bool inb;
-                if (use_dil) {
-                    const int cls = classify_pair(s_objs[o], a.dil, o, x, y, z);
-                    if (cls != PAIR_EXACT) {   // provably contributes nothing
-                        t_pin += (cls == PAIR_FAR) ? 1 : 0;
-                        continue;
-                    }
-                }
+    if (topk_mode) {
+        // Classification and operator evaluation are split: a lane classifies its body point against the objects of
+        // its link instance's mask (one lower-bound load each) and queues the pairs that need the operator in the
+        // warp's ring; whenever 32 are pending the warp evaluates them one pair per lane, fully converged, instead of
+        // one divergent pass per object.  A point's potential is the fp32 sum over objects in ascending order
+        // (cost.py:336-349 over kernel.cu:229-246), so non-zero results are added to the owner's accumulator in queue
+        // order: a lane pushes its pairs in ascending object order, batches leave the ring first-in first-out, and
+        // within a batch results for the same owner are applied by rank.  Zero results leave the sum unchanged.
+        float4 *q_ent = reinterpret_cast<float4 *>(smem + L.off_lg + (size_t)warp * PQ_WARP_BYTES);
+        float *q_acc = reinterpret_cast<float *>(q_ent + PQ_CAP);
+        const unsigned lt_mask = (1u << lane) - 1u;
+        int q_cnt = 0, q_head = 0;
+        auto evaluate = [&](const int cnt) {   // the first cnt (<= 32) entries of the ring
+            float po = 0.0f;
+            unsigned slot = 0x1000u + (unsigned)lane;   // no accumulator: matches nobody
+            if (lane < cnt) {
+                const float4 it = q_ent[(q_head + lane) & (PQ_CAP - 1)];
+                const unsigned tg = __float_as_uint(it.w);   // object | soft-finger flag << 7 | accumulator << 8
+                float co;
+                const bool inb = pair_potential(s_objs[tg & 63u], a.grids, a.quad, it.x, it.y, it.z, po, co);
                 t_exact += 1;
-                if (topk_mode) {
-                    inb = pair_potential(s_objs[o], a.grids, a.quad, x, y, z, po, co);
-                } else {
-                    float ax, ay, az;
-                    inb = pair_full(s_objs[o], a.grids, a.quad, x, y, z, po, ax, ay, az, co);
-                    gx = __fadd_rn(gx, ax); gy = __fadd_rn(gy, ay); gz = __fadd_rn(gz, az);
-                }
-                pot = __fadd_rn(pot, po);
-                col = __fadd_rn(col, co);
                 t_pin += inb ? 1 : 0;
+                if (!(tg & 0x80u)) t_col += (int)co;   // (soft fingers never collide, omg/cost.py:350-353)
+                if (po != 0.0f) slot = tg >> 8;
+            }
+            q_head = (q_head + cnt) & (PQ_CAP - 1);
+            q_cnt -= cnt;
+            const bool nz = slot < 0x1000u;
+            if (__ballot_sync(0xffffffffu, nz)) {
+                const unsigned same = __match_any_sync(0xffffffffu, slot);
+                const unsigned rank = (unsigned)__popc(same & lt_mask);
+                const unsigned last = __reduce_max_sync(0xffffffffu, nz ? rank : 0u);
+                for (unsigned r = 0; r <= last; ++r) {
+                    if (nz && rank == r) q_acc[slot] = __fadd_rn(q_acc[slot], po);
+                    __syncwarp();
+                }
+            }
+        };
+        const int stride = nwarps * GPW;
+        for (int wbase = warp * GPW; wbase < n_act; wbase += stride * PQ_WIN) {
+#pragma unroll
+            for (int r = 0; r < PQ_WIN; ++r) q_acc[r * 32 + lane] = 0.0f;
+            __syncwarp();
+            // classify and queue the window's rounds; the last pass (flush) drains the ring
+#pragma unroll 1
+            for (int r = 0; r <= PQ_WIN; ++r) {
+                const int base = wbase + r * stride;
+                const bool flush = (r == PQ_WIN) || (base >= n_act);
+                unsigned nlo = 0u, nhi = 0u, tag = 0u;
+                float x = 0.0f, y = 0.0f, z = 0.0f;
+                const int idx = base + sub;
+                if (!flush && idx < n_act && pl < P) {
+                    const int li = s_act[idx];
+                    const int j = li % NL;
+                    const double *bp = rc->pts[j][pl];
+                    double X, Y, Z;
+                    xform(s_frames + (size_t)li * 12, bp[0], bp[1], bp[2], X, Y, Z);
+                    x = (float)X; y = (float)Y; z = (float)Z;   // omg/cost.py:136 .float()
+                    unsigned m = s_mlo[li];
+                    while (m) {
+                        const int o = __ffs(m) - 1;
+                        m &= m - 1;
+                        const int cls = use_dil ? classify_pair(s_objs[o], a.dil, o, x, y, z) : PAIR_EXACT;
+                        if (cls == PAIR_EXACT) nlo |= 1u << o;
+                        else t_pin += (cls == PAIR_FAR) ? 1 : 0;   // provably contributes nothing
+                    }
+                    if (s_mhi) {
+                        m = s_mhi[li];
+                        while (m) {
+                            const int o = __ffs(m) - 1;
+                            m &= m - 1;
+                            const int cls = use_dil ? classify_pair(s_objs[o + 32], a.dil, o + 32, x, y, z) : PAIR_EXACT;
+                            if (cls == PAIR_EXACT) nhi |= 1u << o;
+                            else t_pin += (cls == PAIR_FAR) ? 1 : 0;
+                        }
+                    }
+                    tag = ((unsigned)(r * 32 + lane) << 8) | ((finger_soft && j >= 8) ? 0x80u : 0u);
+                }
+                for (;;) {   // (every condition below is warp-uniform)
+                    const bool has = (nlo | nhi) != 0u;
+                    const unsigned bal = __ballot_sync(0xffffffffu, has);
+                    if (bal) {   // one object per lane and pass
+                        if (has) {
+                            unsigned o;
+                            if (nlo) { o = (unsigned)(__ffs(nlo) - 1); nlo &= nlo - 1; }
+                            else { o = 32u + (unsigned)(__ffs(nhi) - 1); nhi &= nhi - 1; }
+                            q_ent[(q_head + q_cnt + __popc(bal & lt_mask)) & (PQ_CAP - 1)] =
+                                make_float4(x, y, z, __uint_as_float(tag | o));
+                        }
+                        q_cnt += __popc(bal);
+                        __syncwarp();
+                    }
+                    if (q_cnt >= 32 || (flush && q_cnt > 0)) evaluate(q_cnt < 32 ? q_cnt : 32);
+                    else if (!bal) break;
+                }
+                if (flush) break;
+            }
+            __syncwarp();
+            // the window's potentials are final: per-point outputs, argmax per link instance, obstacle cost
+#pragma unroll 1
+            for (int r = 0; r < PQ_WIN; ++r) {
+                const int base = wbase + r * stride;
+                if (base >= n_act) break;
+                const int idx = base + sub;
+                const bool have = idx < n_act;
+                const int li = s_act[have ? idx : n_act - 1];
+                const bool live = have && (pl < P);
+                const int i = li / NL, j = li - i * NL;
+                float pot = q_acc[r * 32 + lane];
+                if (finger_soft && j >= 8) pot = __fmul_rn(pot, 0.1f);   // omg/cost.py:350-353
+                const double *F = s_frames + (size_t)li * 12;
+                const double *bp = rc->pts[j][pl < P ? pl : 0];
+                if (live) {
+                    t_nnz += (pot > 0.0f) ? 1 : 0;
+                    if (a.dbg_pot) a.dbg_pot[((size_t)b * n_li + li) * P + pl] = pot;
+                    if (a.dbg_pts) {
+                        double X, Y, Z;
+                        xform(F, bp[0], bp[1], bp[2], X, Y, Z);
+                        float *d = a.dbg_pts + (((size_t)b * n_li + li) * P + pl) * 3;
+                        d[0] = (float)X; d[1] = (float)Y; d[2] = (float)Z;
+                    }
+                    __stcg(g_pot + (size_t)li * LPI + pl, pot);
+                }
+                // argmax over the body points of this link instance (potentials are >= 0, so their bit patterns
+                // order like the values); ties -> highest point index
+                const unsigned bits = live ? __float_as_uint(pot) : 0u;
+                const unsigned mx = __reduce_max_sync(gmask, bits);
+                const unsigned bal = __ballot_sync(gmask, live && bits == mx) & gmask;
+                if (have && pl == 0 && mx != 0u) {
+                    s_best[li] = __uint_as_float(mx);
+                    s_bestp[li] = (unsigned char)((31 - __clz(bal)) - sub * LPI);
+                }
+                // c * |v| of every non-zero point: it IS the obstacle cost when at most k points are non-zero (the usual
+                // case: every non-zero point is a member, cost.py:390-397); otherwise phase 4a sums the members
+                if (live && pot > 0.0f && j < jmax) {
+                    const double *Fp = (i > 0) ? (F - NL * 12) : (s_frames + ((size_t)n * NL + j) * 12);
+                    double X, Y, Z, xp, yp, zp;
+                    xform(F, bp[0], bp[1], bp[2], X, Y, Z);
+                    xform(Fp, bp[0], bp[1], bp[2], xp, yp, zp);
+                    const double vx = (X - xp) * inv_dt, vy = (Y - yp) * inv_dt, vz = (Z - zp) * inv_dt;
+                    t_cost += (double)pot * sqrt(vx * vx + vy * vy + vz * vz);
+                }
             }
         }
-        if (finger_soft && j >= 8) {   // omg/cost.py:350-353
-            pot = __fmul_rn(pot, 0.1f); gx = __fmul_rn(gx, 0.1f); gy = __fmul_rn(gy, 0.1f);
-            gz = __fmul_rn(gz, 0.1f); col = 0.0f;
-        }
-        if (live) {
-            t_nnz += (pot > 0.0f) ? 1 : 0;
-            t_col += (int)col;
-            if (a.dbg_pot) a.dbg_pot[((size_t)b * n_li + li) * P + pl] = pot;
-            if (a.dbg_pts) {
-                float *d = a.dbg_pts + (((size_t)b * n_li + li) * P + pl) * 3;
-                d[0] = x; d[1] = y; d[2] = z;
+    } else {
+        // full-sum mode: every pair needs the operator's gradient too; lanes evaluate their own pairs in object order
+        for (int base = warp * GPW; base < n_act; base += nwarps * GPW) {
+            const int idx = base + sub;
+            const bool have = idx < n_act;
+            const int li = s_act[have ? idx : n_act - 1];
+            const bool live = have && (pl < P);
+            const int i = li / NL, j = li - i * NL;
+            const double *F = s_frames + (size_t)li * 12;
+            const double *bp = rc->pts[j][pl < P ? pl : 0];
+            double X, Y, Z;
+            xform(F, bp[0], bp[1], bp[2], X, Y, Z);
+            const float x = (float)X, y = (float)Y, z = (float)Z;   // omg/cost.py:136 .float()
+            float pot = 0.0f, col = 0.0f, gx = 0.0f, gy = 0.0f, gz = 0.0f;
+#pragma unroll 1
+            for (int half = 0; half < (s_mhi ? 2 : 1); ++half) {   // object mask: one or two 32-bit words
+                unsigned m = live ? (half ? s_mhi[li] : s_mlo[li]) : 0u;
+                while (m) {
+                    const int o = __ffs(m) - 1 + 32 * half;
+                    m &= m - 1;
+                    if (use_dil) {
+                        const int cls = classify_pair(s_objs[o], a.dil, o, x, y, z);
+                        if (cls != PAIR_EXACT) {   // provably contributes nothing
+                            t_pin += (cls == PAIR_FAR) ? 1 : 0;
+                            continue;
+                        }
+                    }
+                    t_exact += 1;
+                    float po, co, ax, ay, az;
+                    const bool inb = pair_full(s_objs[o], a.grids, a.quad, x, y, z, po, ax, ay, az, co);
+                    gx = __fadd_rn(gx, ax); gy = __fadd_rn(gy, ay); gz = __fadd_rn(gz, az);
+                    pot = __fadd_rn(pot, po);
+                    col = __fadd_rn(col, co);
+                    t_pin += inb ? 1 : 0;
+                }
             }
-        }
-        if (topk_mode) {
-            if (live) __stcg(g_pot + (size_t)li * LPI + pl, pot);
-            // argmax over the body points of this link instance (potentials are >= 0, so their bit patterns
-            // order like the values); ties -> highest point index
-            const unsigned bits = live ? __float_as_uint(pot) : 0u;
-            const unsigned mx = __reduce_max_sync(gmask, bits);
-            const unsigned bal = __ballot_sync(gmask, live && bits == mx) & gmask;
-            if (have && pl == 0 && mx != 0u) {
-                s_best[li] = __uint_as_float(mx);
-                s_bestp[li] = (unsigned char)((31 - __clz(bal)) - sub * LPI);
+            if (finger_soft && j >= 8) {   // omg/cost.py:350-353
+                pot = __fmul_rn(pot, 0.1f); gx = __fmul_rn(gx, 0.1f); gy = __fmul_rn(gy, 0.1f);
+                gz = __fmul_rn(gz, 0.1f); col = 0.0f;
             }
-            // c * |v| of every non-zero point: it IS the obstacle cost when at most k points are non-zero (the usual
-            // case: every non-zero point is a member, cost.py:390-397); otherwise phase 4a sums the members
-            if (live && pot > 0.0f && j < jmax) {
-                const double *Fp = (i > 0) ? (F - NL * 12) : (s_frames + ((size_t)n * NL + j) * 12);
-                double xp, yp, zp;
-                xform(Fp, bp[0], bp[1], bp[2], xp, yp, zp);
-                const double vx = (X - xp) * inv_dt, vy = (Y - yp) * inv_dt, vz = (Z - zp) * inv_dt;
-                t_cost += (double)pot * sqrt(vx * vx + vy * vy + vz * vz);
+            if (live) {
+                t_nnz += (pot > 0.0f) ? 1 : 0;
+                t_col += (int)col;
+                if (a.dbg_pot) a.dbg_pot[((size_t)b * n_li + li) * P + pl] = pot;
+                if (a.dbg_pts) {
+                    float *d = a.dbg_pts + (((size_t)b * n_li + li) * P + pl) * 3;
+                    d[0] = x; d[1] = y; d[2] = z;
+                }
             }
-        } else {
-            // full-sum mode: functional gradient of every point with non-zero potential, reduced over
-            // the link instance's body points with warp shuffles
+            // functional gradient of every point with non-zero potential, reduced over the link instance's body
+            // points with warp shuffles
             double g[NS];
             double cst = 0.0;
 #pragma unroll
@@ -979,8 +1206,10 @@ __device__ __forceinline__ void chomp_iteration(const StepArgs &a, unsigned char
             wc.finger_soft = finger_soft; wc.use_dil = use_dil;
             if (wc.n_win * 8 <= nthr) winners_pass<8>(wc);
             else if (wc.n_win * 4 <= nthr) winners_pass<4>(wc);
-            else if (wc.n_win * 2 <= nthr) winners_pass<2>(wc);
-            else winners_pass<1>(wc);
+            else if (wc.n_win < a.win_seg_min) {
+                if (wc.n_win * 2 <= nthr) winners_pass<2>(wc);
+                else winners_pass<1>(wc);
+            } else winners_pass_seg(wc);
         }
     } else {
         obs_sum = red4[3];

@@ -997,6 +997,11 @@ static StepArgs make_args(const omgb_scene *s, const omgb_step_params_t *prm, in
         if (env_bulk < 0) { const char *e = getenv("OMGB_NO_BULK"); env_bulk = (e && atoi(e)) ? 0 : 1; }
         a.bulk_stage = env_bulk;
     }
+    {   // phase 4b: pairs one per lane from this many winners on (diagnostic override; results do not depend on it)
+        static int env_seg = -1;
+        if (env_seg < 0) { const char *e = getenv("OMGB_WIN_SEG_MIN"); env_seg = e ? atoi(e) : 0; }
+        a.win_seg_min = env_seg;
+    }
     a.prm = *prm;
     if (!a.prm.goal_set_proj) a.prm.constraint_rows = 0;
     return a;
