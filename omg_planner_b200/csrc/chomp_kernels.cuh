@@ -60,19 +60,14 @@ struct DilDesc {
 
 struct SmemLayout {
     unsigned off_xi, off_start, off_end, off_goal, off_frames, off_lg, off_grad, off_u, off_viol, off_red,
-        off_mask, off_mask_hi, off_best, off_bestp, off_act, off_win, off_objs, off_hist, off_mbar, total;
+        off_mask, off_mask_hi, off_best, off_bestp, off_act, off_win, off_objs, off_sph, off_hist, off_mbar, total;
     int nlu;        // links that own gradient rows: 8 in top-k mode without consider_finger (cost.py:401-402), else 10
-    int red_max;    // index of the block-argmax slot inside the reduction scratch
+    int red_max;    // first slot behind the sum buffers inside the reduction scratch
     int mask_hi;    // 1: more than 32 objects, the object masks are two 32-bit words
 };
 
 __host__ __device__ inline unsigned align_up(unsigned v, unsigned a) { return (v + a - 1) / a * a; }
 
-// Points phase of the top-k path: every warp owns a ring of pending exact (body point, object) pairs and the potential
-// accumulators of the PQ_WIN rounds (32 body-point lanes each) whose pairs may be in flight.
-constexpr int PQ_CAP = 64;    // ring entries per warp (at most 31 pending + 32 pushed)
-constexpr int PQ_WIN = 4;     // rounds per window
-constexpr unsigned PQ_WARP_BYTES = PQ_CAP * 16u + PQ_WIN * 32u * 4u;
 
 // Shared memory of one CTA (one trajectory).  Sized so that a 30-waypoint trajectory fits four times and a
 // 60-waypoint one twice into an SM's 228 KB: the per-point potentials of the top-k path live in a global scratch
@@ -92,8 +87,6 @@ __host__ __device__ inline SmemLayout make_layout(int n, int c, int lpi, int nob
     // link gradients [n*nlu][8] fp64; aliased with the sin/cos table of the FK phase
     unsigned lg = sizeof(double) * n * L.nlu * NS, sc = sizeof(double2) * (n + 2) * 7;
     unsigned u = lg > sc ? lg : sc;
-    // top-k mode: the region is dead between the FK phase and phase 4b and holds the points phase's per-warp queues
-    if (topk && (unsigned)nwarps * PQ_WARP_BYTES > u) u = (unsigned)nwarps * PQ_WARP_BYTES;
     o = align_up(o, 16);   // double2 sin/cos table
     L.off_lg = o; o += align_up(u, 16);
     // grad / u / viol (+ the scan scratch of metric_apply) live in the frames region: the link frames are dead once
@@ -101,9 +94,10 @@ __host__ __device__ inline SmemLayout make_layout(int n, int c, int lpi, int nob
     L.off_grad = L.off_frames;
     L.off_u = L.off_grad + sizeof(double) * n * ND;
     L.off_viol = L.off_u + sizeof(double) * n * ND;
-    // reduction scratch: (nwarps + 1) x 8 partial sums, then the argmax slot; never less than the 16-double info row
-    L.red_max = (nwarps + 1) * 8;
-    L.off_red = o; o += sizeof(double) * (L.red_max + 8 < 24 ? 24 : L.red_max + 8);
+    // reduction scratch: two buffers of nwarps x 8 partial sums (block_sum_n), then from red_max on the per-warp and
+    // final argmax slots of the joint-limit projection, later the 16-double info row
+    L.red_max = 2 * nwarps * 8;
+    L.off_red = o; o += sizeof(double) * (L.red_max + (nwarps + 1 < 16 ? 16 : nwarps + 1));
     L.off_mask = o; o += sizeof(unsigned) * n * NL;
     L.off_mask_hi = o; o += L.mask_hi ? sizeof(unsigned) * n * NL : 0;
     L.off_best = o; o += sizeof(float) * n * NL;
@@ -112,6 +106,7 @@ __host__ __device__ inline SmemLayout make_layout(int n, int c, int lpi, int nob
     L.off_bestp = o; o += align_up(n * NL, 16);
     o = align_up(o, 16);
     L.off_objs = o; o += sizeof(ObjRec) * nobj;
+    L.off_sph = o; o += sizeof(float4) * nobj;
     L.off_hist = o; o += sizeof(int) * 264;
     L.off_mbar = o; o += 8;   // mbarrier of the bulk (TMA) staging copies
     L.total = align_up(o, 16);
@@ -199,26 +194,28 @@ __device__ __forceinline__ double warp_sum(double v) {
     return v;
 }
 
-// Block-wide sum of K values at once; every thread gets the results.  scratch: >= (warps + 1) * K doubles.
+// Block-wide sum of K <= 8 values at once; every thread gets the results.  ONE barrier per call: the warp partials
+// go to one of two scratch buffers of warps * 8 doubles, alternating from call to call (`flip`, kept in step by every
+// thread of the CTA).  A partial written by call t + 2 cannot overtake a read of call t: its writer has passed the
+// barrier of call t + 1, which every reader of call t reaches after its reads.  The partials are combined in warp
+// order by lanes 0..K-1 of EVERY warp and broadcast by shuffles.
 template <int K>
-__device__ __forceinline__ void block_sum_n(double (&v)[K], double *scratch) {
+__device__ __forceinline__ void block_sum_n(double (&v)[K], double *scratch, int &flip) {
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    double *buf = scratch + flip * nw * 8;
+    flip ^= 1;
 #pragma unroll
     for (int k = 0; k < K; ++k) v[k] = warp_sum(v[k]);
-    __syncthreads();
     if (lane == 0) {
 #pragma unroll
-        for (int k = 0; k < K; ++k) scratch[w * K + k] = v[k];
+        for (int k = 0; k < K; ++k) buf[w * 8 + k] = v[k];
     }
     __syncthreads();
-    if (threadIdx.x < K) {
-        double t = 0.0;
-        for (int q = 0; q < nw; ++q) t += scratch[q * K + threadIdx.x];
-        scratch[nw * K + threadIdx.x] = t;
-    }
-    __syncthreads();
+    double t = 0.0;
+    if (lane < K)
+        for (int q = 0; q < nw; ++q) t += buf[q * 8 + lane];
 #pragma unroll
-    for (int k = 0; k < K; ++k) v[k] = scratch[nw * K + k];
+    for (int k = 0; k < K; ++k) v[k] = __shfl_sync(0xffffffffu, t, k);
 }
 
 __device__ __forceinline__ void xform(const double *F, double px, double py, double pz, double &x, double &y,
@@ -434,6 +431,28 @@ __device__ __forceinline__ int classify_pair(const ObjRec &ob, const DilDesc &dd
     const float *addr;
     const int st = classify_prepare(ob, dd, oi, x, y, z, addr);
     return st == PAIR_LOAD ? classify_finish(ob, __ldg(addr)) : st;
+}
+
+// First level of the cull, branch-free: (waypoint, link) sphere against every object's world-frame bounding sphere, one
+// 128-bit shared-memory load per object from a compact copy of the spheres (sph_stage), independent iterations.  Most
+// pairs end here; the survivors' bits go through the box tests.  Disabled objects sit at infinity; radius < 0: never cull.
+__device__ __forceinline__ void sph_stage(const ObjRec *s_objs, float4 *s_sph, int O) {
+    for (int o = threadIdx.x; o < O; o += blockDim.x) {
+        const ObjRec &ob = s_objs[o];
+        const float inf = __int_as_float(0x7f800000);
+        s_sph[o] = (ob.dis > 0.0f) ? make_float4(inf, inf, inf, 0.0f) : make_float4(ob.wsx, ob.wsy, ob.wsz, ob.wsr);
+    }
+}
+__device__ __forceinline__ unsigned sph_near(const float4 *s_sph, int o0, int o1, float fx, float fy, float fz, float rad) {
+    unsigned near = 0u;
+#pragma unroll 4
+    for (int o = o0; o < o1; ++o) {
+        const float4 sp = s_sph[o];
+        const float dx = fx - sp.x, dy = fy - sp.y, dz = fz - sp.z, rr = rad + sp.w;
+        const bool far = (sp.w >= 0.0f) & (dx * dx + dy * dy + dz * dz > rr * rr);
+        near |= (far ? 0u : 1u) << (o - o0);
+    }
+    return near;
 }
 
 // Phase 4b body: the winners of the top-k branch, G lanes per winner (the operator's 7 trilinear samples and the
@@ -685,10 +704,12 @@ __device__ __forceinline__ void chomp_iteration(const StepArgs &a, unsigned char
     unsigned short *s_act = reinterpret_cast<unsigned short *>(smem + L.off_act);
     unsigned short *s_win = reinterpret_cast<unsigned short *>(smem + L.off_win);
     ObjRec *s_objs = reinterpret_cast<ObjRec *>(smem + L.off_objs);
+    float4 *s_sph = reinterpret_cast<float4 *>(smem + L.off_sph);
     int *s_hist = reinterpret_cast<int *>(smem + L.off_hist);
 
     const int tid = threadIdx.x, nthr = blockDim.x;
     const int lane = tid & 31, warp = tid >> 5, nwarps = nthr >> 5;
+    int bs_flip = 0;   // block_sum_n's scratch buffer of the next call
     const double dt = prm.time_interval;
     const double inv_dt = 1.0 / dt, inv_dt2 = inv_dt * inv_dt;   // fp64 divisions are ~50 instructions each
     constexpr bool topk_mode = TOPK;   // prm.top_k_collision > 0
@@ -750,6 +771,7 @@ __device__ __forceinline__ void chomp_iteration(const StepArgs &a, unsigned char
     for (int k = k0 + tid + 2 * nthr; k < n_in; k += nthr) s_xi[k] = __ldcg(stage_src(k));   // (long trajectories)
     __syncthreads();
     if (bulk) mbar_wait(mbar, 0u);
+    sph_stage(s_objs, s_sph, O);   // (read after the barriers of the FK phase)
 
     OMGB_PROF(1);
     // ---- phase 1: forward kinematics (n waypoints, then start, then end) ---------------------------
@@ -784,13 +806,14 @@ __device__ __forceinline__ void chomp_iteration(const StepArgs &a, unsigned char
         xform(s_frames + (size_t)li * 12, (double)a.rp.sph[j][0], (double)a.rp.sph[j][1], (double)a.rp.sph[j][2], cx, cy, cz);
         const float fx = (float)cx, fy = (float)cy, fz = (float)cz, rad = a.rp.sph[j][3];
         unsigned long long m = 0ull;
-        for (int o = 0; o < O; ++o) {
+        // first level: link sphere vs the objects' world-frame bounding spheres
+        unsigned long long near = sph_near(s_sph, 0, O < 32 ? O : 32, fx, fy, fz, rad);
+        if (O > 32) near |= (unsigned long long)sph_near(s_sph, 32, O, fx, fy, fz, rad) << 32;
+        while (near) {
+            const int o = __ffsll((long long)near) - 1;
+            near &= near - 1;
             const ObjRec &ob = s_objs[o];
             if (ob.dis > 0.0f) continue;
-            {   // first level: link sphere vs the object's world-frame bounding sphere (most pairs end here)
-                const float dx = fx - ob.wsx, dy = fy - ob.wsy, dz = fz - ob.wsz, rr = rad + ob.wsr;
-                if (ob.wsr >= 0.0f && dx * dx + dy * dy + dz * dz > rr * rr) continue;
-            }
             const float qx = ob.r[0] * fx + ob.r[1] * fy + ob.r[2] * fz + ob.tx;
             const float qy = ob.r[3] * fx + ob.r[4] * fy + ob.r[5] * fz + ob.ty;
             const float qz = ob.r[6] * fx + ob.r[7] * fy + ob.r[8] * fz + ob.tz;
@@ -851,201 +874,82 @@ __device__ __forceinline__ void chomp_iteration(const StepArgs &a, unsigned char
     const int jmax = (topk_mode && !prm.consider_finger) ? NL - 2 : NL;   // links that count towards cost / gradient
     int t_nnz = 0, t_col = 0, t_exact = 0;
     double t_cost = 0.0;
-    if (topk_mode) {
-        // Classification and operator evaluation are split: a lane classifies its body point against the objects of
-        // its link instance's mask (one lower-bound load each) and queues the pairs that need the operator in the
-        // warp's ring; whenever 32 are pending the warp evaluates them one pair per lane, fully converged, instead of
-        // one divergent pass per object.  A point's potential is the fp32 sum over objects in ascending order
-        // (cost.py:336-349 over kernel.cu:229-246), so non-zero results are added to the owner's accumulator in queue
-        // order: a lane pushes its pairs in ascending object order, batches leave the ring first-in first-out, and
-        // within a batch results for the same owner are applied by rank.  Zero results leave the sum unchanged.
-        float4 *q_ent = reinterpret_cast<float4 *>(smem + L.off_lg + (size_t)warp * PQ_WARP_BYTES);
-        float *q_acc = reinterpret_cast<float *>(q_ent + PQ_CAP);
-        const unsigned lt_mask = (1u << lane) - 1u;
-        int q_cnt = 0, q_head = 0;
-        auto evaluate = [&](const int cnt) {   // the first cnt (<= 32) entries of the ring
-            float po = 0.0f;
-            unsigned slot = 0x1000u + (unsigned)lane;   // no accumulator: matches nobody
-            if (lane < cnt) {
-                const float4 it = q_ent[(q_head + lane) & (PQ_CAP - 1)];
-                const unsigned tg = __float_as_uint(it.w);   // object | soft-finger flag << 7 | accumulator << 8
-                float co;
-                const bool inb = pair_potential(s_objs[tg & 63u], a.grids, a.quad, it.x, it.y, it.z, po, co);
+    for (int base = warp * GPW; base < n_act; base += nwarps * GPW) {
+        const int idx = base + sub;
+        const bool have = idx < n_act;
+        const int li = s_act[have ? idx : n_act - 1];
+        const bool live = have && (pl < P);
+        const int i = li / NL, j = li - i * NL;
+        const double *F = s_frames + (size_t)li * 12;
+        const double *bp = rc->pts[j][pl < P ? pl : 0];
+        double X, Y, Z;
+        xform(F, bp[0], bp[1], bp[2], X, Y, Z);
+        const float x = (float)X, y = (float)Y, z = (float)Z;   // omg/cost.py:136 .float()
+        float pot = 0.0f, col = 0.0f, gx = 0.0f, gy = 0.0f, gz = 0.0f;
+#pragma unroll 1
+        for (int half = 0; half < (s_mhi ? 2 : 1); ++half) {   // object mask: one or two 32-bit words
+            unsigned m = live ? (half ? s_mhi[li] : s_mlo[li]) : 0u;
+            while (m) {
+                const int o = __ffs(m) - 1 + 32 * half;
+                m &= m - 1;
+                float po, co;
+                bool inb;
+                if (use_dil) {
+                    const int cls = classify_pair(s_objs[o], a.dil, o, x, y, z);
+                    if (cls != PAIR_EXACT) {   // provably contributes nothing
+                        t_pin += (cls == PAIR_FAR) ? 1 : 0;
+                        continue;
+                    }
+                }
                 t_exact += 1;
+                if (topk_mode) {
+                    inb = pair_potential(s_objs[o], a.grids, a.quad, x, y, z, po, co);
+                } else {
+                    float ax, ay, az;
+                    inb = pair_full(s_objs[o], a.grids, a.quad, x, y, z, po, ax, ay, az, co);
+                    gx = __fadd_rn(gx, ax); gy = __fadd_rn(gy, ay); gz = __fadd_rn(gz, az);
+                }
+                pot = __fadd_rn(pot, po);
+                col = __fadd_rn(col, co);
                 t_pin += inb ? 1 : 0;
-                if (!(tg & 0x80u)) t_col += (int)co;   // (soft fingers never collide, omg/cost.py:350-353)
-                if (po != 0.0f) slot = tg >> 8;
-            }
-            q_head = (q_head + cnt) & (PQ_CAP - 1);
-            q_cnt -= cnt;
-            const bool nz = slot < 0x1000u;
-            if (__ballot_sync(0xffffffffu, nz)) {
-                const unsigned same = __match_any_sync(0xffffffffu, slot);
-                const unsigned rank = (unsigned)__popc(same & lt_mask);
-                const unsigned last = __reduce_max_sync(0xffffffffu, nz ? rank : 0u);
-                for (unsigned r = 0; r <= last; ++r) {
-                    if (nz && rank == r) q_acc[slot] = __fadd_rn(q_acc[slot], po);
-                    __syncwarp();
-                }
-            }
-        };
-        const int stride = nwarps * GPW;
-        for (int wbase = warp * GPW; wbase < n_act; wbase += stride * PQ_WIN) {
-#pragma unroll
-            for (int r = 0; r < PQ_WIN; ++r) q_acc[r * 32 + lane] = 0.0f;
-            __syncwarp();
-            // classify and queue the window's rounds; the last pass (flush) drains the ring
-#pragma unroll 1
-            for (int r = 0; r <= PQ_WIN; ++r) {
-                const int base = wbase + r * stride;
-                const bool flush = (r == PQ_WIN) || (base >= n_act);
-                unsigned nlo = 0u, nhi = 0u, tag = 0u;
-                float x = 0.0f, y = 0.0f, z = 0.0f;
-                const int idx = base + sub;
-                if (!flush && idx < n_act && pl < P) {
-                    const int li = s_act[idx];
-                    const int j = li % NL;
-                    const double *bp = rc->pts[j][pl];
-                    double X, Y, Z;
-                    xform(s_frames + (size_t)li * 12, bp[0], bp[1], bp[2], X, Y, Z);
-                    x = (float)X; y = (float)Y; z = (float)Z;   // omg/cost.py:136 .float()
-                    unsigned m = s_mlo[li];
-                    while (m) {
-                        const int o = __ffs(m) - 1;
-                        m &= m - 1;
-                        const int cls = use_dil ? classify_pair(s_objs[o], a.dil, o, x, y, z) : PAIR_EXACT;
-                        if (cls == PAIR_EXACT) nlo |= 1u << o;
-                        else t_pin += (cls == PAIR_FAR) ? 1 : 0;   // provably contributes nothing
-                    }
-                    if (s_mhi) {
-                        m = s_mhi[li];
-                        while (m) {
-                            const int o = __ffs(m) - 1;
-                            m &= m - 1;
-                            const int cls = use_dil ? classify_pair(s_objs[o + 32], a.dil, o + 32, x, y, z) : PAIR_EXACT;
-                            if (cls == PAIR_EXACT) nhi |= 1u << o;
-                            else t_pin += (cls == PAIR_FAR) ? 1 : 0;
-                        }
-                    }
-                    tag = ((unsigned)(r * 32 + lane) << 8) | ((finger_soft && j >= 8) ? 0x80u : 0u);
-                }
-                for (;;) {   // (every condition below is warp-uniform)
-                    const bool has = (nlo | nhi) != 0u;
-                    const unsigned bal = __ballot_sync(0xffffffffu, has);
-                    if (bal) {   // one object per lane and pass
-                        if (has) {
-                            unsigned o;
-                            if (nlo) { o = (unsigned)(__ffs(nlo) - 1); nlo &= nlo - 1; }
-                            else { o = 32u + (unsigned)(__ffs(nhi) - 1); nhi &= nhi - 1; }
-                            q_ent[(q_head + q_cnt + __popc(bal & lt_mask)) & (PQ_CAP - 1)] =
-                                make_float4(x, y, z, __uint_as_float(tag | o));
-                        }
-                        q_cnt += __popc(bal);
-                        __syncwarp();
-                    }
-                    if (q_cnt >= 32 || (flush && q_cnt > 0)) evaluate(q_cnt < 32 ? q_cnt : 32);
-                    else if (!bal) break;
-                }
-                if (flush) break;
-            }
-            __syncwarp();
-            // the window's potentials are final: per-point outputs, argmax per link instance, obstacle cost
-#pragma unroll 1
-            for (int r = 0; r < PQ_WIN; ++r) {
-                const int base = wbase + r * stride;
-                if (base >= n_act) break;
-                const int idx = base + sub;
-                const bool have = idx < n_act;
-                const int li = s_act[have ? idx : n_act - 1];
-                const bool live = have && (pl < P);
-                const int i = li / NL, j = li - i * NL;
-                float pot = q_acc[r * 32 + lane];
-                if (finger_soft && j >= 8) pot = __fmul_rn(pot, 0.1f);   // omg/cost.py:350-353
-                const double *F = s_frames + (size_t)li * 12;
-                const double *bp = rc->pts[j][pl < P ? pl : 0];
-                if (live) {
-                    t_nnz += (pot > 0.0f) ? 1 : 0;
-                    if (a.dbg_pot) a.dbg_pot[((size_t)b * n_li + li) * P + pl] = pot;
-                    if (a.dbg_pts) {
-                        double X, Y, Z;
-                        xform(F, bp[0], bp[1], bp[2], X, Y, Z);
-                        float *d = a.dbg_pts + (((size_t)b * n_li + li) * P + pl) * 3;
-                        d[0] = (float)X; d[1] = (float)Y; d[2] = (float)Z;
-                    }
-                    __stcg(g_pot + (size_t)li * LPI + pl, pot);
-                }
-                // argmax over the body points of this link instance (potentials are >= 0, so their bit patterns
-                // order like the values); ties -> highest point index
-                const unsigned bits = live ? __float_as_uint(pot) : 0u;
-                const unsigned mx = __reduce_max_sync(gmask, bits);
-                const unsigned bal = __ballot_sync(gmask, live && bits == mx) & gmask;
-                if (have && pl == 0 && mx != 0u) {
-                    s_best[li] = __uint_as_float(mx);
-                    s_bestp[li] = (unsigned char)((31 - __clz(bal)) - sub * LPI);
-                }
-                // c * |v| of every non-zero point: it IS the obstacle cost when at most k points are non-zero (the usual
-                // case: every non-zero point is a member, cost.py:390-397); otherwise phase 4a sums the members
-                if (live && pot > 0.0f && j < jmax) {
-                    const double *Fp = (i > 0) ? (F - NL * 12) : (s_frames + ((size_t)n * NL + j) * 12);
-                    double X, Y, Z, xp, yp, zp;
-                    xform(F, bp[0], bp[1], bp[2], X, Y, Z);
-                    xform(Fp, bp[0], bp[1], bp[2], xp, yp, zp);
-                    const double vx = (X - xp) * inv_dt, vy = (Y - yp) * inv_dt, vz = (Z - zp) * inv_dt;
-                    t_cost += (double)pot * sqrt(vx * vx + vy * vy + vz * vz);
-                }
             }
         }
-    } else {
-        // full-sum mode: every pair needs the operator's gradient too; lanes evaluate their own pairs in object order
-        for (int base = warp * GPW; base < n_act; base += nwarps * GPW) {
-            const int idx = base + sub;
-            const bool have = idx < n_act;
-            const int li = s_act[have ? idx : n_act - 1];
-            const bool live = have && (pl < P);
-            const int i = li / NL, j = li - i * NL;
-            const double *F = s_frames + (size_t)li * 12;
-            const double *bp = rc->pts[j][pl < P ? pl : 0];
-            double X, Y, Z;
-            xform(F, bp[0], bp[1], bp[2], X, Y, Z);
-            const float x = (float)X, y = (float)Y, z = (float)Z;   // omg/cost.py:136 .float()
-            float pot = 0.0f, col = 0.0f, gx = 0.0f, gy = 0.0f, gz = 0.0f;
-#pragma unroll 1
-            for (int half = 0; half < (s_mhi ? 2 : 1); ++half) {   // object mask: one or two 32-bit words
-                unsigned m = live ? (half ? s_mhi[li] : s_mlo[li]) : 0u;
-                while (m) {
-                    const int o = __ffs(m) - 1 + 32 * half;
-                    m &= m - 1;
-                    if (use_dil) {
-                        const int cls = classify_pair(s_objs[o], a.dil, o, x, y, z);
-                        if (cls != PAIR_EXACT) {   // provably contributes nothing
-                            t_pin += (cls == PAIR_FAR) ? 1 : 0;
-                            continue;
-                        }
-                    }
-                    t_exact += 1;
-                    float po, co, ax, ay, az;
-                    const bool inb = pair_full(s_objs[o], a.grids, a.quad, x, y, z, po, ax, ay, az, co);
-                    gx = __fadd_rn(gx, ax); gy = __fadd_rn(gy, ay); gz = __fadd_rn(gz, az);
-                    pot = __fadd_rn(pot, po);
-                    col = __fadd_rn(col, co);
-                    t_pin += inb ? 1 : 0;
-                }
+        if (finger_soft && j >= 8) {   // omg/cost.py:350-353
+            pot = __fmul_rn(pot, 0.1f); gx = __fmul_rn(gx, 0.1f); gy = __fmul_rn(gy, 0.1f);
+            gz = __fmul_rn(gz, 0.1f); col = 0.0f;
+        }
+        if (live) {
+            t_nnz += (pot > 0.0f) ? 1 : 0;
+            t_col += (int)col;
+            if (a.dbg_pot) a.dbg_pot[((size_t)b * n_li + li) * P + pl] = pot;
+            if (a.dbg_pts) {
+                float *d = a.dbg_pts + (((size_t)b * n_li + li) * P + pl) * 3;
+                d[0] = x; d[1] = y; d[2] = z;
             }
-            if (finger_soft && j >= 8) {   // omg/cost.py:350-353
-                pot = __fmul_rn(pot, 0.1f); gx = __fmul_rn(gx, 0.1f); gy = __fmul_rn(gy, 0.1f);
-                gz = __fmul_rn(gz, 0.1f); col = 0.0f;
+        }
+        if (topk_mode) {
+            if (live) __stcg(g_pot + (size_t)li * LPI + pl, pot);
+            // argmax over the body points of this link instance (potentials are >= 0, so their bit patterns
+            // order like the values); ties -> highest point index
+            const unsigned bits = live ? __float_as_uint(pot) : 0u;
+            const unsigned mx = __reduce_max_sync(gmask, bits);
+            const unsigned bal = __ballot_sync(gmask, live && bits == mx) & gmask;
+            if (have && pl == 0 && mx != 0u) {
+                s_best[li] = __uint_as_float(mx);
+                s_bestp[li] = (unsigned char)((31 - __clz(bal)) - sub * LPI);
             }
-            if (live) {
-                t_nnz += (pot > 0.0f) ? 1 : 0;
-                t_col += (int)col;
-                if (a.dbg_pot) a.dbg_pot[((size_t)b * n_li + li) * P + pl] = pot;
-                if (a.dbg_pts) {
-                    float *d = a.dbg_pts + (((size_t)b * n_li + li) * P + pl) * 3;
-                    d[0] = x; d[1] = y; d[2] = z;
-                }
+            // c * |v| of every non-zero point: it IS the obstacle cost when at most k points are non-zero (the usual
+            // case: every non-zero point is a member, cost.py:390-397); otherwise phase 4a sums the members
+            if (live && pot > 0.0f && j < jmax) {
+                const double *Fp = (i > 0) ? (F - NL * 12) : (s_frames + ((size_t)n * NL + j) * 12);
+                double xp, yp, zp;
+                xform(Fp, bp[0], bp[1], bp[2], xp, yp, zp);
+                const double vx = (X - xp) * inv_dt, vy = (Y - yp) * inv_dt, vz = (Z - zp) * inv_dt;
+                t_cost += (double)pot * sqrt(vx * vx + vy * vy + vz * vz);
             }
-            // functional gradient of every point with non-zero potential, reduced over the link instance's body
-            // points with warp shuffles
+        } else {
+            // full-sum mode: functional gradient of every point with non-zero potential, reduced over
+            // the link instance's body points with warp shuffles
             double g[NS];
             double cst = 0.0;
 #pragma unroll
@@ -1078,10 +982,10 @@ __device__ __forceinline__ void chomp_iteration(const StepArgs &a, unsigned char
     }
     OMGB_PROF(5);
     double red4[4] = {(double)t_nnz, (double)t_pin, (double)t_col, t_cost};
-    block_sum_n<4>(red4, s_red);
+    block_sum_n<4>(red4, s_red, bs_flip);
     if (a.prof) {   // diagnostic: exact operator evaluations in the points phase
         double ex[1] = {(double)t_exact};
-        block_sum_n<1>(ex, s_red);
+        block_sum_n<1>(ex, s_red, bs_flip);
         if (tid == 0) a.prof[(size_t)b * 16 + 12] = (long long)(ex[0] + 0.5);
     }
     const int nnz = (int)(red4[0] + 0.5), p_in = (int)(red4[1] + 0.5), collide = (int)(red4[2] + 0.5);
@@ -1091,6 +995,7 @@ __device__ __forceinline__ void chomp_iteration(const StepArgs &a, unsigned char
         // ---- phase 3: membership threshold = k-th largest potential (bit pattern; potentials >= 0) ----
         const int K = prm.top_k_collision;
         uint32_t tau = 1u;   // "pot >= tau" <=> pot > 0
+        double acc = 0.0;
         if (nnz > K) {
             uint32_t prefix = 0u, pmask = 0u;
             int remaining = K;
@@ -1106,10 +1011,16 @@ __device__ __forceinline__ void chomp_iteration(const StepArgs &a, unsigned char
             for (int shift = 24; shift >= 0; shift -= 8) {
                 for (int k = tid; k < 256; k += nthr) s_hist[k] = 0;
                 __syncthreads();
+                // (potentials of one trajectory share their leading bytes: the candidates of a warp are counted per
+                // distinct bucket -- one shared-memory atomic per bucket and warp instead of up to 32 on one address)
 #pragma unroll
                 for (int q = 0; q < RC; ++q) {
                     const uint32_t u = cache[q];
-                    if (u != 0u && (u & pmask) == prefix) atomicAdd(&s_hist[(u >> shift) & 255u], 1);
+                    const bool cand = u != 0u && (u & pmask) == prefix;
+                    if (__ballot_sync(0xffffffffu, cand) == 0u) continue;   // (warp-uniform)
+                    const unsigned bucket = (u >> shift) & 255u;
+                    const unsigned peers = __match_any_sync(0xffffffffu, cand ? bucket : 0x100u + (unsigned)lane);
+                    if (cand && (__ffs(peers) - 1) == lane) atomicAdd(&s_hist[bucket], __popc(peers));
                 }
                 for (int k = tid + RC * nthr; k < n_as; k += nthr) {   // (only when n_as > 16 * blockDim)
                     if ((k % LPI) >= P) continue;
@@ -1148,29 +1059,31 @@ __device__ __forceinline__ void chomp_iteration(const StepArgs &a, unsigned char
                 __syncthreads();
             }
             tau = prefix;   // ties at tau are all kept (reference: unstable argsort, order undefined)
-        }
-        OMGB_PROF(6);
-        // ---- phase 4a: obstacle cost = sum over members of c*|v| (cost.py:30,416), links 0..7; only when more than
-        // k points are non-zero (else the points phase has summed it already) ---------
-        double acc = 0.0;
-        if (nnz > K) {
-            for (int k = tid; k < n_act * LPI; k += nthr) {
+            // ---- phase 4a: obstacle cost = sum over members of c*|v| (cost.py:30,416), links 0..7; only when more than
+            // k points are non-zero (else the points phase has summed it already).  The potentials are still in the
+            // registers the selection kept them in; same slots per thread, same order as a sweep of the scratch ----
+            auto member_cost = [&](int k, uint32_t u) {
+                if (u == 0u || u < tau) return;
                 const int li = s_act[k / LPI], p = k % LPI;
                 const int i = li / NL, j = li - i * NL;
-                if (p >= P || j >= jmax) continue;
-                const float pv = __ldcg(g_pot + (size_t)li * LPI + p);
-                if (pv > 0.0f && __float_as_uint(pv) >= tau) {
-                    const double *F = s_frames + (size_t)li * 12;
-                    const double *Fp = (i > 0) ? (F - NL * 12) : (s_frames + ((size_t)n * NL + j) * 12);
-                    const double *bp = rc->pts[j][p];
-                    double X, Y, Z, xp, yp, zp;
-                    xform(F, bp[0], bp[1], bp[2], X, Y, Z);
-                    xform(Fp, bp[0], bp[1], bp[2], xp, yp, zp);
-                    const double vx = (X - xp) * inv_dt, vy = (Y - yp) * inv_dt, vz = (Z - zp) * inv_dt;
-                    acc += (double)pv * sqrt(vx * vx + vy * vy + vz * vz);
-                }
+                if (j >= jmax) return;
+                const double *F = s_frames + (size_t)li * 12;
+                const double *Fp = (i > 0) ? (F - NL * 12) : (s_frames + ((size_t)n * NL + j) * 12);
+                const double *bp = rc->pts[j][p];
+                double X, Y, Z, xp, yp, zp;
+                xform(F, bp[0], bp[1], bp[2], X, Y, Z);
+                xform(Fp, bp[0], bp[1], bp[2], xp, yp, zp);
+                const double vx = (X - xp) * inv_dt, vy = (Y - yp) * inv_dt, vz = (Z - zp) * inv_dt;
+                acc += (double)__uint_as_float(u) * sqrt(vx * vx + vy * vy + vz * vz);
+            };
+#pragma unroll
+            for (int q = 0; q < RC; ++q) member_cost(tid + q * nthr, cache[q]);
+            for (int k = tid + RC * nthr; k < n_as; k += nthr) {   // (only when n_as > 16 * blockDim)
+                if ((k % LPI) >= P) continue;
+                member_cost(k, __float_as_uint(__ldcg(g_pot + (size_t)s_act[k / LPI] * LPI + (k % LPI))));
             }
         }
+        OMGB_PROF(6);
         // winner list: active link instances whose best point is a top-k member (unordered; each winner writes
         // only its own gradient rows)
         if (tid == 0) s_hist[261] = 0;
@@ -1190,9 +1103,13 @@ __device__ __forceinline__ void chomp_iteration(const StepArgs &a, unsigned char
             wbase = __shfl_sync(0xffffffffu, wbase, 0);
             if (win) s_win[wbase + __popc(bal & ((1u << lane) - 1u))] = (unsigned short)li;
         }
-        double red1[1] = {acc};
-        block_sum_n<1>(red1, s_red);
-        obs_sum = ((nnz > K) ? red1[0] : red4[3]) * (double)n;   // added to every waypoint row (SURVEY A-3)
+        obs_sum = red4[3];
+        if (nnz > K) {   // (uniform)
+            double red1[1] = {acc};
+            block_sum_n<1>(red1, s_red, bs_flip);
+            obs_sum = red1[0];
+        }
+        obs_sum *= (double)n;   // added to every waypoint row (SURVEY A-3)
         for (int k = tid; k < n * NLU * NS; k += nthr) s_lg[k] = 0.0;
         __syncthreads();
         OMGB_PROF(7);
@@ -1254,7 +1171,7 @@ __device__ __forceinline__ void chomp_iteration(const StepArgs &a, unsigned char
         v *= prm.link_smooth_weight[d];
         red7[3] += v * v;
     }
-    block_sum_n<7>(red7, s_red);
+    block_sum_n<7>(red7, s_red, bs_flip);
     const double norm_wo = sqrt(red7[0]), norm_ws = sqrt(red7[1]), norm_g = sqrt(red7[2]);
     const double smooth_sum = 0.5 * red7[3];
     const double goal_dist = goal_set ? sqrt(red7[4]) : 0.0;
@@ -1312,7 +1229,7 @@ __device__ __forceinline__ void chomp_iteration(const StepArgs &a, unsigned char
                 const double m = fabs(viol);
                 if (m > bm) { bm = m; bk = k; }   // first occurrence of the max in flat order (np.argmax)
             }
-            block_sum_n<1>(t, s_red);
+            block_sum_n<1>(t, s_red, bs_flip);
             const double vn = sqrt(t[0]);
             if (!(vn > 1e-2) || round == prm.joint_limit_max_steps) break;
 #pragma unroll
@@ -1321,18 +1238,19 @@ __device__ __forceinline__ void chomp_iteration(const StepArgs &a, unsigned char
                 const int ok = __shfl_xor_sync(0xffffffffu, bk, off);
                 if (om > bm || (om == bm && ok < bk)) { bm = om; bk = ok; }
             }
-            if (lane == 0) { s_red[warp] = bm; s_hist[warp] = bk; }
+            double *s_am = s_red + L.red_max;   // per-warp maxima, then the block's
+            if (lane == 0) { s_am[warp] = bm; s_hist[warp] = bk; }
             __syncthreads();
             if (tid == 0) {
-                double fm = s_red[0];
+                double fm = s_am[0];
                 int fk = s_hist[0];
                 for (int w = 1; w < nwarps; ++w)
-                    if (s_red[w] > fm || (s_red[w] == fm && s_hist[w] < fk)) { fm = s_red[w]; fk = s_hist[w]; }
-                s_red[L.red_max] = fm;
+                    if (s_am[w] > fm || (s_am[w] == fm && s_hist[w] < fk)) { fm = s_am[w]; fk = s_hist[w]; }
+                s_am[nwarps] = fm;
                 s_hist[260] = fk;
             }
             __syncthreads();
-            const double vmax = s_red[L.red_max];
+            const double vmax = s_am[nwarps];
             const int kmax = s_hist[260];
             metric_apply(a, n, s_viol, s_u, s_viol + n * ND);
             const double scale = vmax / (fabs(s_u[kmax]) + 1e-8);
@@ -1350,7 +1268,7 @@ __device__ __forceinline__ void chomp_iteration(const StepArgs &a, unsigned char
         a.prof[(size_t)b * 16 + 15] = (long long)gt;
     }
     if (tid == 0) {
-        double *inf = s_red;   // staged in shared memory, written as one coalesced 128-byte row below
+        double *inf = s_red + L.red_max;   // staged in shared memory, written as one coalesced 128-byte row below
         inf[OMGB_INFO_OBS] = obs_sum;
         inf[OMGB_INFO_SMOOTH] = smooth_sum;
         inf[OMGB_INFO_COST] = w_obs * obs_sum + w_smooth * smooth_sum;
@@ -1374,8 +1292,9 @@ __device__ __forceinline__ void chomp_iteration(const StepArgs &a, unsigned char
     }
     __syncwarp();
     if (tid < OMGB_INFO_STRIDE) {
-        a.info[(size_t)b * OMGB_INFO_STRIDE + tid] = s_red[tid];
-        if (a.hist_info) a.hist_info[((size_t)iteration * a.batch + b) * OMGB_INFO_STRIDE + tid] = s_red[tid];
+        const double v = s_red[L.red_max + tid];
+        a.info[(size_t)b * OMGB_INFO_STRIDE + tid] = v;
+        if (a.hist_info) a.hist_info[((size_t)iteration * a.batch + b) * OMGB_INFO_STRIDE + tid] = v;
     }
     if (a.hist_xi) {   // planner.py:622: history_trajectories.append(np.copy(traj.data))
         double *h = a.hist_xi + ((size_t)iteration * a.batch + b) * (size_t)(n * ND);

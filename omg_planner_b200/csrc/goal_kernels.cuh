@@ -48,7 +48,7 @@ struct GoalArgs {
     int gpc, ctas_per_traj;    // goals per CTA; CTAs per trajectory = ceil(num_goals / gpc)
     float inv_dt;
     unsigned off_q, off_sc, off_queue, off_qobj, off_frames, off_mask, off_mask_hi, off_act, off_red, off_objs,
-        smem_total;
+        off_sph, smem_total;
 };
 
 __host__ inline void goal_layout(GoalArgs &a, int warps) {
@@ -69,6 +69,7 @@ __host__ inline void goal_layout(GoalArgs &a, int warps) {
     a.off_red = o; o += sizeof(unsigned long long) * GOAL_MAX_GPC;
     o = align_up(o, 16);
     a.off_objs = o; o += sizeof(ObjRec) * a.num_objects;
+    a.off_sph = o; o += sizeof(float4) * a.num_objects;
     a.smem_total = align_up(o, 16);
 }
 
@@ -86,6 +87,7 @@ goal_cost_kernel(const GoalArgs a) {
     unsigned short *s_act = reinterpret_cast<unsigned short *>(smem + a.off_act + 8);   // (config << 4) | link
     unsigned long long *s_cost = reinterpret_cast<unsigned long long *>(smem + a.off_red);   // per goal of this CTA
     ObjRec *s_objs = reinterpret_cast<ObjRec *>(smem + a.off_objs);
+    float4 *s_sph = reinterpret_cast<float4 *>(smem + a.off_sph);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr int NWARPS = THREADS / 32;
@@ -122,6 +124,7 @@ goal_cost_kernel(const GoalArgs a) {
         }
     }
     __syncthreads();
+    sph_stage(s_objs, s_sph, O);   // (read after the barriers of the FK phase)
     // ---- forward kinematics: sin/cos table, then 3 threads (one transform row each) per configuration ----
     for (int k = tid; k < cfgs * 7; k += THREADS) {
         const int cfg = k / 7, i = k - cfg * 7;
@@ -148,13 +151,14 @@ goal_cost_kernel(const GoalArgs a) {
             xform(s_frames + (size_t)(li + NL) * 12, (double)a.rp.sph[cj][0], (double)a.rp.sph[cj][1],
                   (double)a.rp.sph[cj][2], cx, cy, cz);
             const float fx = (float)cx, fy = (float)cy, fz = (float)cz, rad = a.rp.sph[cj][3];
-            for (int o = 0; o < O; ++o) {
+            // first level: link sphere vs the objects' world-frame bounding spheres (most pairs end here)
+            unsigned long long near = sph_near(s_sph, 0, O < 32 ? O : 32, fx, fy, fz, rad);
+            if (HI) near |= (unsigned long long)sph_near(s_sph, 32, O, fx, fy, fz, rad) << 32;
+            while (near) {
+                const int o = __ffsll((long long)near) - 1;
+                near &= near - 1;
                 const ObjRec &ob = s_objs[o];
                 if (ob.dis > 0.0f) continue;
-                {   // first level: link sphere vs the object's world-frame bounding sphere (most pairs end here)
-                    const float dx = fx - ob.wsx, dy = fy - ob.wsy, dz = fz - ob.wsz, rr = rad + ob.wsr;
-                    if (ob.wsr >= 0.0f && dx * dx + dy * dy + dz * dz > rr * rr) continue;
-                }
                 const float qx = ob.r[0] * fx + ob.r[1] * fy + ob.r[2] * fz + ob.tx;
                 const float qy = ob.r[3] * fx + ob.r[4] * fy + ob.r[5] * fz + ob.ty;
                 const float qz = ob.r[6] * fx + ob.r[7] * fy + ob.r[8] * fz + ob.tz;
