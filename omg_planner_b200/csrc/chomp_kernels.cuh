@@ -64,6 +64,7 @@ struct SmemLayout {
     int nlu;        // links that own gradient rows: 8 in top-k mode without consider_finger (cost.py:401-402), else 10
     int red_max;    // first slot behind the sum buffers inside the reduction scratch
     int mask_hi;    // 1: more than 32 objects, the object masks are two 32-bit words
+    int member_list;   // 1: phase 4a lists the cost members per warp in the (then dead) link-gradient region
 };
 
 __host__ __device__ inline unsigned align_up(unsigned v, unsigned a) { return (v + a - 1) / a * a; }
@@ -89,6 +90,8 @@ __host__ __device__ inline SmemLayout make_layout(int n, int c, int lpi, int nob
     unsigned u = lg > sc ? lg : sc;
     o = align_up(o, 16);   // double2 sin/cos table
     L.off_lg = o; o += align_up(u, 16);
+    // top-k mode: room for every warp's list of cost members (16 slot rounds x 32 lanes, 2 bytes each)?
+    L.member_list = (topk && (unsigned)nwarps * 1024u <= u && n * NL * lpi < 65536) ? 1 : 0;
     // grad / u / viol (+ the scan scratch of metric_apply) live in the frames region: the link frames are dead once
     // the obstacle gradient is assembled; 5 * n * 9 doubles <= (n + 2) * 120
     L.off_grad = L.off_frames;
@@ -110,7 +113,7 @@ __host__ __device__ inline SmemLayout make_layout(int n, int c, int lpi, int nob
     L.off_hist = o; o += sizeof(int) * 264;
     L.off_mbar = o; o += 8;   // mbarrier of the bulk (TMA) staging copies
     L.total = align_up(o, 16);
-    (void)p; (void)lpi;
+    (void)p;
     return L;
 }
 
@@ -938,6 +941,15 @@ __device__ __forceinline__ void chomp_iteration(const StepArgs &a, unsigned char
                 s_best[li] = __uint_as_float(mx);
                 s_bestp[li] = (unsigned char)((31 - __clz(bal)) - sub * LPI);
             }
+            // c * |v| of every non-zero point: it IS the obstacle cost when at most k points are non-zero (the usual
+            // case: every non-zero point is a member, cost.py:390-397); otherwise phase 4a sums the members
+            if (live && pot > 0.0f && j < jmax) {
+                const double *Fp = (i > 0) ? (F - NL * 12) : (s_frames + ((size_t)n * NL + j) * 12);
+                double xp, yp, zp;
+                xform(Fp, bp[0], bp[1], bp[2], xp, yp, zp);
+                const double vx = (X - xp) * inv_dt, vy = (Y - yp) * inv_dt, vz = (Z - zp) * inv_dt;
+                t_cost += (double)pot * sqrt(vx * vx + vy * vy + vz * vz);
+            }
         } else {
             // full-sum mode: functional gradient of every point with non-zero potential, reduced over
             // the link instance's body points with warp shuffles
@@ -987,9 +999,10 @@ __device__ __forceinline__ void chomp_iteration(const StepArgs &a, unsigned char
         const int K = prm.top_k_collision;
         uint32_t tau = 1u;   // "pot >= tau" <=> pot > 0
         double acc = 0.0;
-        if (nnz > 0) {   // (uniform)
-            // each thread keeps its share of the active slots' bit patterns in registers: across the four passes of
-            // the selection, and for the obstacle cost of the members
+        if (nnz > K) {
+            uint32_t prefix = 0u, pmask = 0u;
+            int remaining = K;
+            // each thread keeps its share of the active slots' bit patterns in registers across the four passes
             constexpr int RC = 16;
             uint32_t cache[RC];
             const int n_as = n_act * LPI;
@@ -998,68 +1011,54 @@ __device__ __forceinline__ void chomp_iteration(const StepArgs &a, unsigned char
                 const int k = tid + q * nthr;
                 cache[q] = (k < n_as && (k % LPI) < P) ? __float_as_uint(__ldcg(g_pot + (size_t)s_act[k / LPI] * LPI + (k % LPI))) : 0u;
             }
-            if (nnz > K) {
-                uint32_t prefix = 0u, pmask = 0u;
-                int remaining = K;
-                for (int shift = 24; shift >= 0; shift -= 8) {
-                    for (int k = tid; k < 256; k += nthr) s_hist[k] = 0;
-                    __syncthreads();
-                    // (potentials of one trajectory share their leading bytes: the candidates that fall into the
-                    // bucket of the warp's first candidate are counted with one shared-memory atomic, not up to 32
-                    // on one address)
+            for (int shift = 24; shift >= 0; shift -= 8) {
+                for (int k = tid; k < 256; k += nthr) s_hist[k] = 0;
+                __syncthreads();
 #pragma unroll
-                    for (int q = 0; q < RC; ++q) {
-                        const uint32_t u = cache[q];
-                        const bool cand = u != 0u && (u & pmask) == prefix;
-                        const unsigned cb = __ballot_sync(0xffffffffu, cand);
-                        if (cb == 0u) continue;   // (warp-uniform)
-                        const unsigned bucket = (u >> shift) & 255u;
-                        const int lead = __ffs(cb) - 1;
-                        const unsigned b0 = __shfl_sync(0xffffffffu, bucket, lead);
-                        const unsigned same = __ballot_sync(0xffffffffu, cand && bucket == b0);
-                        if (lane == lead) atomicAdd(&s_hist[b0], __popc(same));
-                        else if (cand && bucket != b0) atomicAdd(&s_hist[bucket], 1);
-                    }
-                    for (int k = tid + RC * nthr; k < n_as; k += nthr) {   // (only when n_as > 16 * blockDim)
-                        if ((k % LPI) >= P) continue;
-                        const uint32_t u = __float_as_uint(__ldcg(g_pot + (size_t)s_act[k / LPI] * LPI + (k % LPI)));
-                        if (u != 0u && (u & pmask) == prefix) atomicAdd(&s_hist[(u >> shift) & 255u], 1);
-                    }
-                    __syncthreads();
-                    if (warp == 0) {   // descending scan of the 256 buckets: 8 per lane
-                        int loc[8], sum = 0;
-#pragma unroll
-                        for (int q = 0; q < 8; ++q) { loc[q] = s_hist[255 - (lane * 8 + q)]; sum += loc[q]; }
-                        int incl = sum;
-#pragma unroll
-                        for (int off = 1; off < 32; off <<= 1) {
-                            const int t = __shfl_up_sync(0xffffffffu, incl, off);
-                            if (lane >= off) incl += t;
-                        }
-                        const int excl = incl - sum;
-                        if (excl < remaining && incl >= remaining) {
-                            int cum = excl;
-#pragma unroll
-                            for (int q = 0; q < 8; ++q) {
-                                if (cum + loc[q] >= remaining) {
-                                    s_hist[256] = 255 - (lane * 8 + q);
-                                    s_hist[257] = remaining - cum;
-                                    break;
-                                }
-                                cum += loc[q];
-                            }
-                        }
-                    }
-                    __syncthreads();
-                    prefix |= ((uint32_t)s_hist[256]) << shift;
-                    pmask |= 255u << shift;
-                    remaining = s_hist[257];
-                    __syncthreads();
+                for (int q = 0; q < RC; ++q) {
+                    const uint32_t u = cache[q];
+                    if (u != 0u && (u & pmask) == prefix) atomicAdd(&s_hist[(u >> shift) & 255u], 1);
                 }
-                tau = prefix;   // ties at tau are all kept (reference: unstable argsort, order undefined)
+                for (int k = tid + RC * nthr; k < n_as; k += nthr) {   // (only when n_as > 16 * blockDim)
+                    if ((k % LPI) >= P) continue;
+                    const uint32_t u = __float_as_uint(__ldcg(g_pot + (size_t)s_act[k / LPI] * LPI + (k % LPI)));
+                    if (u != 0u && (u & pmask) == prefix) atomicAdd(&s_hist[(u >> shift) & 255u], 1);
+                }
+                __syncthreads();
+                if (warp == 0) {   // descending scan of the 256 buckets: 8 per lane
+                    int loc[8], sum = 0;
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) { loc[q] = s_hist[255 - (lane * 8 + q)]; sum += loc[q]; }
+                    int incl = sum;
+#pragma unroll
+                    for (int off = 1; off < 32; off <<= 1) {
+                        const int t = __shfl_up_sync(0xffffffffu, incl, off);
+                        if (lane >= off) incl += t;
+                    }
+                    const int excl = incl - sum;
+                    if (excl < remaining && incl >= remaining) {
+                        int acc = excl;
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) {
+                            if (acc + loc[q] >= remaining) {
+                                s_hist[256] = 255 - (lane * 8 + q);
+                                s_hist[257] = remaining - acc;
+                                break;
+                            }
+                            acc += loc[q];
+                        }
+                    }
+                }
+                __syncthreads();
+                prefix |= ((uint32_t)s_hist[256]) << shift;
+                pmask |= 255u << shift;
+                remaining = s_hist[257];
+                __syncthreads();
             }
-            // ---- phase 4a: obstacle cost = sum over members of c*|v| (cost.py:30,416), links 0..7.  At most k non-zero
-            // points: every one of them is a member (cost.py:390-397).  The potentials are in registers already ----
+            tau = prefix;   // ties at tau are all kept (reference: unstable argsort, order undefined)
+            // ---- phase 4a: obstacle cost = sum over members of c*|v| (cost.py:30,416), links 0..7; only when more than
+            // k points are non-zero (else the points phase has summed it already).  The potentials are still in the
+            // registers the selection kept them in; same slots per thread, same order as a sweep of the scratch ----
             auto member_cost = [&](int k, uint32_t u) {
                 if (u == 0u || u < tau) return;
                 const int li = s_act[k / LPI], p = k % LPI;
@@ -1074,8 +1073,28 @@ __device__ __forceinline__ void chomp_iteration(const StepArgs &a, unsigned char
                 const double vx = (X - xp) * inv_dt, vy = (Y - yp) * inv_dt, vz = (Z - zp) * inv_dt;
                 acc += (double)__uint_as_float(u) * sqrt(vx * vx + vy * vy + vz * vz);
             };
+            if (L.member_list) {
+                // members are ~1 in 5 of a warp's slots: evaluated in place, the fp64 body would run for every
+                // (warp, slot round) with a handful of live lanes.  Each warp lists its members first (in the region of
+                // the link gradients, dead until phase 4b) and walks the list with all lanes busy.
+                unsigned short *wl = reinterpret_cast<unsigned short *>(smem + L.off_lg) + warp * (RC * 32);
+                int cnt = 0;
 #pragma unroll
-            for (int q = 0; q < RC; ++q) member_cost(tid + q * nthr, cache[q]);
+                for (int q = 0; q < RC; ++q) {
+                    const bool mem = cache[q] != 0u && cache[q] >= tau;
+                    const unsigned bal = __ballot_sync(0xffffffffu, mem);
+                    if (mem) wl[cnt + __popc(bal & ((1u << lane) - 1u))] = (unsigned short)(tid + q * nthr);
+                    cnt += __popc(bal);
+                }
+                __syncwarp();
+                for (int t = lane; t < cnt; t += 32) {
+                    const int k = wl[t];
+                    member_cost(k, __float_as_uint(__ldcg(g_pot + (size_t)s_act[k / LPI] * LPI + (k % LPI))));
+                }
+            } else {
+#pragma unroll
+                for (int q = 0; q < RC; ++q) member_cost(tid + q * nthr, cache[q]);
+            }
             for (int k = tid + RC * nthr; k < n_as; k += nthr) {   // (only when n_as > 16 * blockDim)
                 if ((k % LPI) >= P) continue;
                 member_cost(k, __float_as_uint(__ldcg(g_pot + (size_t)s_act[k / LPI] * LPI + (k % LPI))));
@@ -1101,11 +1120,13 @@ __device__ __forceinline__ void chomp_iteration(const StepArgs &a, unsigned char
             wbase = __shfl_sync(0xffffffffu, wbase, 0);
             if (win) s_win[wbase + __popc(bal & ((1u << lane) - 1u))] = (unsigned short)li;
         }
-        if (nnz > 0) {   // (uniform)
+        obs_sum = red4[3];
+        if (nnz > K) {   // (uniform)
             double red1[1] = {acc};
             block_sum_n<1>(red1, s_red, bs_flip);
-            obs_sum = red1[0] * (double)n;   // added to every waypoint row (SURVEY A-3)
+            obs_sum = red1[0];
         }
+        obs_sum *= (double)n;   // added to every waypoint row (SURVEY A-3)
         for (int k = tid; k < n * NLU * NS; k += nthr) s_lg[k] = 0.0;
         __syncthreads();
         OMGB_PROF(7);
