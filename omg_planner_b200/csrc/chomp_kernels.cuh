@@ -64,7 +64,6 @@ struct SmemLayout {
     int nlu;        // links that own gradient rows: 8 in top-k mode without consider_finger (cost.py:401-402), else 10
     int red_max;    // first slot behind the sum buffers inside the reduction scratch
     int mask_hi;    // 1: more than 32 objects, the object masks are two 32-bit words
-    int member_list;   // 1: phase 4a lists the cost members per warp in the (then dead) link-gradient region
 };
 
 __host__ __device__ inline unsigned align_up(unsigned v, unsigned a) { return (v + a - 1) / a * a; }
@@ -90,8 +89,6 @@ __host__ __device__ inline SmemLayout make_layout(int n, int c, int lpi, int nob
     unsigned u = lg > sc ? lg : sc;
     o = align_up(o, 16);   // double2 sin/cos table
     L.off_lg = o; o += align_up(u, 16);
-    // top-k mode: room for every warp's list of cost members (16 slot rounds x 32 lanes, 2 bytes each)?
-    L.member_list = (topk && (unsigned)nwarps * 1024u <= u && n * NL * lpi < 65536) ? 1 : 0;
     // grad / u / viol (+ the scan scratch of metric_apply) live in the frames region: the link frames are dead once
     // the obstacle gradient is assembled; 5 * n * 9 doubles <= (n + 2) * 120
     L.off_grad = L.off_frames;
@@ -113,7 +110,7 @@ __host__ __device__ inline SmemLayout make_layout(int n, int c, int lpi, int nob
     L.off_hist = o; o += sizeof(int) * 264;
     L.off_mbar = o; o += 8;   // mbarrier of the bulk (TMA) staging copies
     L.total = align_up(o, 16);
-    (void)p;
+    (void)p; (void)lpi;
     return L;
 }
 
@@ -1073,28 +1070,8 @@ __device__ __forceinline__ void chomp_iteration(const StepArgs &a, unsigned char
                 const double vx = (X - xp) * inv_dt, vy = (Y - yp) * inv_dt, vz = (Z - zp) * inv_dt;
                 acc += (double)__uint_as_float(u) * sqrt(vx * vx + vy * vy + vz * vz);
             };
-            if (L.member_list) {
-                // members are ~1 in 5 of a warp's slots: evaluated in place, the fp64 body would run for every
-                // (warp, slot round) with a handful of live lanes.  Each warp lists its members first (in the region of
-                // the link gradients, dead until phase 4b) and walks the list with all lanes busy.
-                unsigned short *wl = reinterpret_cast<unsigned short *>(smem + L.off_lg) + warp * (RC * 32);
-                int cnt = 0;
 #pragma unroll
-                for (int q = 0; q < RC; ++q) {
-                    const bool mem = cache[q] != 0u && cache[q] >= tau;
-                    const unsigned bal = __ballot_sync(0xffffffffu, mem);
-                    if (mem) wl[cnt + __popc(bal & ((1u << lane) - 1u))] = (unsigned short)(tid + q * nthr);
-                    cnt += __popc(bal);
-                }
-                __syncwarp();
-                for (int t = lane; t < cnt; t += 32) {
-                    const int k = wl[t];
-                    member_cost(k, __float_as_uint(__ldcg(g_pot + (size_t)s_act[k / LPI] * LPI + (k % LPI))));
-                }
-            } else {
-#pragma unroll
-                for (int q = 0; q < RC; ++q) member_cost(tid + q * nthr, cache[q]);
-            }
+            for (int q = 0; q < RC; ++q) member_cost(tid + q * nthr, cache[q]);
             for (int k = tid + RC * nthr; k < n_as; k += nthr) {   // (only when n_as > 16 * blockDim)
                 if ((k % LPI) >= P) continue;
                 member_cost(k, __float_as_uint(__ldcg(g_pot + (size_t)s_act[k / LPI] * LPI + (k % LPI))));

@@ -91,9 +91,10 @@ class ChompEngine(object):
         """Upload cfg.Ainv and the goal-set projection; cached on (n, goal_set_proj, c, dt)."""
         c = cfg.constraint_rows
         ainv = np.ascontiguousarray(cfg.Ainv, dtype=np.float64)
-        # keyed on the CONTENT of Ainv (a few KB): an array modified in place, or a new one at a recycled id(), must
-        # not leave a stale metric / projection on the device
-        key = (cfg.timesteps, bool(cfg.goal_set_proj), c, float(cfg.time_interval), ainv.shape, hash(ainv.tobytes()))
+        # keyed on the CONTENT of Ainv (a few KB, compared byte for byte: cheaper than hashing it on every call): an
+        # array modified in place, or a new one at a recycled id(), must not leave a stale metric / projection on the
+        # device
+        key = (cfg.timesteps, bool(cfg.goal_set_proj), c, float(cfg.time_interval), ainv.shape, ainv.tobytes())
         if key == self._metric_key:
             return
         proj = cfg.projection_matrix(c)
@@ -233,6 +234,20 @@ class ChompEngine(object):
         3 zero-copy required (omgb_scene_set_host_mode)."""
         _lib.check(self.L.omgb_scene_set_host_mode(self._h, int(mode)), "omgb_scene_set_host_mode")
 
+    def _host_ptr(self, a):
+        """Data pointer of a numpy array, remembered per array object (ndarray.ctypes / __array_interface__ build a new
+        Python object on every access: ~2 us each, five per call).  An array's buffer cannot move while the cache holds a
+        reference to it (ndarray.resize refuses to reallocate a referenced array)."""
+        cache = self._keep.setdefault("host_ptrs", {})
+        e = cache.get(id(a))
+        if e is not None and e[0] is a:
+            return e[1]
+        if len(cache) >= 16:
+            cache.clear()
+        p = a.ctypes.data
+        cache[id(a)] = (a, p)
+        return p
+
     def step_host(self, cfg, xi, start, end, goal_rows=None, info=None):
         """Reference-facing call with HOST numpy buffers (xi updated in place, info returned).  With pinned
         buffers (torch .pin_memory() / cudaHostRegister) the fused kernel reads and writes them directly over PCIe;
@@ -253,7 +268,7 @@ class ChompEngine(object):
         if "host_prm" not in self._keep:
             self._keep["host_prm"], self._keep["host_lsw"] = _lib.StepParams(), {}
         prm = self.params_from(cfg, True, into=self._keep["host_prm"], lsw_cache=self._keep["host_lsw"])
-        ptr = lambda a: a.__array_interface__["data"][0]
+        ptr = self._host_ptr
         _lib.check(self.L.omgb_chomp_step_host(self._h, ctypes.byref(prm), B, ptr(xi), ptr(start), ptr(end),
                                                ptr(goal_rows) if c > 0 else None, ptr(info),
                                                torch.cuda.current_stream().cuda_stream),
