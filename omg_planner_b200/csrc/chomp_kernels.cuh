@@ -677,7 +677,8 @@ __device__ __forceinline__ void metric_apply(const StepArgs &a, int n, const dou
 // schedules Optimizer.update() set for this iteration (omg/optimizer.py:59-80); iteration: index inside a plan.
 template <int LPI, bool TOPK>
 __device__ __forceinline__ void chomp_iteration(const StepArgs &a, unsigned char *smem, const int b, const double w_obs,
-                                                const double w_smooth, const double step_size, const int iteration) {
+                                                const double w_smooth, const double step_size, const int iteration,
+                                                unsigned &bulk_uses) {
     const long long t_begin = clock64();
 
     const omgb_step_params_t &prm = a.prm;
@@ -750,7 +751,10 @@ __device__ __forceinline__ void chomp_iteration(const StepArgs &a, unsigned char
     const bool bulk = a.bulk_stage && ((((size_t)g_xi) | ((size_t)n_x * 8u)) & 15u) == 0;
     if (bulk && tid == 0) {
         const unsigned bytes_xi = (unsigned)n_x * 8u, bytes_obj = (unsigned)sizeof(ObjRec) * (unsigned)O;
-        mbar_init_one(mbar);
+        // the mbarrier is initialised once per CTA; a persistent CTA's later items complete its next phases (the
+        // generic-proxy accesses of the previous item to the destinations are ordered before the copies by the fence)
+        if (bulk_uses == 0u) mbar_init_one(mbar);
+        else asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         mbar_expect_tx(mbar, bytes_xi + bytes_obj);
         bulk_g2s(smem_u32(s_xi), g_xi, bytes_xi, mbar);
         bulk_g2s(smem_u32(s_objs), a.objs, bytes_obj, mbar);
@@ -770,7 +774,7 @@ __device__ __forceinline__ void chomp_iteration(const StepArgs &a, unsigned char
     if (k0 + tid + nthr < n_in) s_xi[k0 + tid + nthr] = stg1;
     for (int k = k0 + tid + 2 * nthr; k < n_in; k += nthr) s_xi[k] = __ldcg(stage_src(k));   // (long trajectories)
     __syncthreads();
-    if (bulk) mbar_wait(mbar, 0u);
+    if (bulk) { mbar_wait(mbar, bulk_uses & 1u); ++bulk_uses; }
     sph_stage(s_objs, s_sph, O);   // (read after the barriers of the FK phase)
 
     OMGB_PROF(1);
@@ -1322,7 +1326,9 @@ __global__ void __launch_bounds__(THREADS, MINB) chomp_step_kernel(const StepArg
         if (a.done && a.done[b]) copy_history(a, b, a.iteration);
         return;
     }
-    chomp_iteration<LPI, TOPK>(a, smem, b, a.prm.obstacle_weight, a.prm.smoothness_weight, a.prm.step_size, a.iteration);
+    unsigned bulk_uses = 0u;
+    chomp_iteration<LPI, TOPK>(a, smem, b, a.prm.obstacle_weight, a.prm.smoothness_weight, a.prm.step_size, a.iteration,
+                               bulk_uses);
 }
 
 // Persistent plan kernel: ONE launch runs `iters` iterations of every trajectory (the fixed-goal inner loop of
@@ -1343,7 +1349,11 @@ __global__ void __launch_bounds__(THREADS, MINB) chomp_plan_kernel(const StepArg
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ unsigned s_item;
     const unsigned total = (unsigned)a.batch * (unsigned)p.iters;
+    unsigned bulk_uses = 0u;   // bulk stagings this CTA has waited for (phase of the staging mbarrier)
     for (;;) {
+        // every thread's generic-proxy accesses to the staging destinations, then the barrier, then the next item's
+        // bulk copies (async proxy) into the same shared memory
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncthreads();   // (the previous item's shared memory is dead)
         if (threadIdx.x == 0) s_item = atomicAdd(p.counter, 1u);
         __syncthreads();
@@ -1359,7 +1369,7 @@ __global__ void __launch_bounds__(THREADS, MINB) chomp_plan_kernel(const StepArg
         const bool skip = a.done && __ldcg(a.done + b);   // frozen by stop_on_terminate
         if (!skip)
             chomp_iteration<LPI, TOPK>(a, smem, b, __ldg(p.sched + 3 * it), __ldg(p.sched + 3 * it + 1),
-                                       __ldg(p.sched + 3 * it + 2), it);
+                                       __ldg(p.sched + 3 * it + 2), it, bulk_uses);
         else
             copy_history(a, b, it);
         __syncthreads();       // every thread's global stores of this item are issued ...
