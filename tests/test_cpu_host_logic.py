@@ -1,6 +1,7 @@
 """CPU: host-side logic of the product and the C-ABI surface (no GPU compute)."""
 import os
 import re
+import subprocess
 
 import numpy as np
 import pytest
@@ -126,3 +127,16 @@ def test_scene_layout_follows_combine_sdfs():
     rob = PandaConstants()
     xi, st, en, tails = S.make_trajectories(4, 30, rob.joint_lower_limit, rob.joint_upper_limit)
     assert (tails[:, -1] == en).all() and (en[:, :7] > rob.joint_lower_limit[0, :7]).all()
+
+
+def test_step_kernel_shared_memory_layout(tmp_path):
+    """The fused step's CTA shapes rest on footprints: three CTAs per SM for 30 waypoints, two for 50-60
+    (omg_planner_b200/csrc/omgb200.cu: launch_step).  Host-compiled make_layout: regions ordered and sized, shapes fit."""
+    exe = str(tmp_path / "step_layout_check")
+    subprocess.check_call(["nvcc", "-std=c++17", "-arch=sm_100a", "-o", exe, os.path.join(ROOT, "tests", "host", "step_layout_check.cu")])
+    out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+    rows = [dict(zip(ln.split()[0::2], ln.split()[1::2])) for ln in out.stdout.strip().splitlines()]
+    assert len(rows) == 7 and all(r["bad"] == "0" for r in rows), out.stdout
+    for r in rows[:5]:
+        assert r["fits"] == "1", r
