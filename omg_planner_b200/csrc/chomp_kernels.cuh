@@ -68,9 +68,8 @@ struct SmemLayout {
 
 __host__ __device__ inline unsigned align_up(unsigned v, unsigned a) { return (v + a - 1) / a * a; }
 
-
-// Shared memory of one CTA (one trajectory).  Sized so that a 30-waypoint trajectory fits four times and a
-// 60-waypoint one twice into an SM's 228 KB: the per-point potentials of the top-k path live in a global scratch
+// Shared memory of one CTA (one trajectory).  Sized so that a 30-waypoint trajectory fits three times and a
+// 60-waypoint one twice into an SM's 228 KB (tests/host/step_layout_check.cu): the per-point potentials of the top-k path live in a global scratch
 // (written and read once by the same CTA, L2-resident), link gradients only for the links that can own a winner,
 // 32-bit object masks unless there are more than 32 objects, byte / short indices.
 __host__ __device__ inline SmemLayout make_layout(int n, int c, int lpi, int nobj, int p, int nwarps, bool topk,
