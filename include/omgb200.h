@@ -26,6 +26,8 @@
  *   omgb_learner_update        Learner.update_goal after the        omg/online_learner.py:151-160, 162-249
  *                              collision costs (cost vector, FTL /
  *                              FTC / Exp / MD / Proj, goal selection)
+ *   omgb_chomp_plan_goalset    plan() in goal-set mode with the     omg/planner.py:612-635
+ *                              learner, the whole loop in one call
  *   omgb_traj_interpolate      Trajectory.interpolate_waypoints     omg/core.py:59-78 -> omg/util.py:238-258
  *   omgb_sdf_pack              SignedDensityField.from_pth/.resize  omg/sdf_tools.py:187-193, 37-39,
  *                              + Env.combine_sdfs                   omg/core.py:366-411
@@ -270,6 +272,43 @@ int omgb_learner_update(const omgb_learner_params_t *params, int batch, const do
                         const double *goal_set, int goals_shared, const double *reach, double *p, double *sum_costs,
                         double *experts_p, double *experts_costs, double *q, const uint8_t *done, int32_t *goal_idx,
                         double *end, double *goal_rows, double *cost_vector, int32_t *selected, void *stream);
+
+/* Device buffers of a goal-set plan with goal switching (all DEVICE; the arguments omgb_goal_costs, omgb_learner_update
+ * and omgb_chomp_plan_step take, with the same layouts). */
+typedef struct {
+    double *xi;                 /* [B,n,9] in/out */
+    const double *start;        /* [B,9] */
+    double *end;                /* [B,9] in/out: the selected goal (omgb_learner_update) */
+    double *goal_rows;          /* [B,c,9] in/out: the selected goal's projection rows */
+    uint8_t *done;              /* [B] in/out: trajectories whose plan has ended (zeroed by the caller) */
+    double *info;               /* [B,16] out: the last iteration's info rows */
+    double *hist_xi;            /* [iters,B,n,9] or NULL */
+    double *hist_info;          /* [iters,B,16] or NULL */
+    const double *goal_set;     /* [B,G,9], or [G,9] when goals_shared */
+    const double *reach;        /* [B,G,c,9] / [G,c,9] or NULL (no standoff) */
+    const double *reach_goals;  /* [B,G,9] / [G,9]: the configurations the goal lines end at (reach[..., -1, :] with
+                                   standoff, else goal_set; omg/online_learner.py:121-125) */
+    double *p, *sum_costs, *experts_p, *experts_costs, *q;   /* the Learner's state (omgb_learner_update) */
+    int32_t *goal_idx;          /* [B] in/out */
+    int32_t *selected;          /* [learner_iters,B] out or NULL: Planner.selected_goals */
+    float *collision;           /* [B,G] fp32 scratch (the goal costs of the current iteration) */
+    int32_t goals_shared;
+    int32_t reserved_;
+} omgb_goalset_plan_buffers_t;
+
+/* Planner.plan's loop in goal-set mode with the online learner (omg/planner.py:612-635), enqueued by one call: for
+ * t = 0 .. iters-1:  if t < learner_iters (cfg.optim_steps): omgb_goal_costs from waypoint first_waypoint[t] (skipped
+ * for OMGB_LEARNER_PROJ) and omgb_learner_update (params `learner` with that first_waypoint);  then
+ * omgb_chomp_plan_step(iteration t, stop_on_terminate) with obstacle_weight / smoothness_weight / step_size =
+ * schedule[t] (HOST [iters,3], Optimizer.update's values for that iteration, omg/optimizer.py:59-80).
+ * Results are those of the three calls made one at a time; nothing synchronises unless timeout_s >= 0 (cfg.timeout,
+ * planner.py:629): then the host clock is compared every 8 iterations against the device's progress and the loop
+ * stops early.  *iters_enqueued (HOST, may be NULL) = iterations enqueued. */
+int omgb_chomp_plan_goalset(omgb_scene_t *scene, const omgb_step_params_t *params,
+                            const omgb_learner_params_t *learner, int iters, int learner_iters,
+                            const double *schedule, const int32_t *first_waypoint, int batch,
+                            const omgb_goalset_plan_buffers_t *buffers, double timeout_s, int *iters_enqueued,
+                            void *stream);
 
 /* ---- trajectory initialisation and the SDF asset path (no scene; they run on the calling thread's current
  * CUDA device) ------------------------------------------------------------------------------------------------ */

@@ -8,7 +8,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(_HERE)
 LIB_PATH = os.environ.get("OMGB_LIB") or os.path.join(_HERE, "lib", "libomgb200.so")   # OMGB_LIB: A/B experiments
 SOURCES = [os.path.join(_HERE, "csrc", f) for f in ("omgb200.cu", "chomp_kernels.cuh", "goal_kernels.cuh",
-                                                     "sdf_device.cuh", "sdf_asset_kernels.cuh", "traj_kernels.cuh", "learner_kernels.cuh",
+                                                     "sdf_device.cuh", "sdf_asset_kernels.cuh", "traj_kernels.cuh", "learner_kernels.cuh", "learner_bisect.h",
                                                      "ik_kernels.cu", "ik_svd_reg.cuh", "host_common.h")] + [
     os.path.join(ROOT, "include", "omgb200.h")]
 
@@ -22,7 +22,7 @@ EXPORTS = ["omgb_version", "omgb_last_error", "omgb_scene_create", "omgb_scene_d
            "omgb_sdf_loss_workspace_bytes", "omgb_sdf_loss", "omgb_chomp_step", "omgb_chomp_plan",
            "omgb_chomp_step_host", "omgb_batch_obstacle_cost", "omgb_goal_costs", "omgb_chomp_plan_history",
            "omgb_traj_interpolate", "omgb_sdf_pack", "omgb_point_sdf", "omgb_ik_solve", "omgb_hand_poses", "omgb_chomp_plan_step",
-           "omgb_learner_update"]
+           "omgb_learner_update", "omgb_chomp_plan_goalset"]
 
 
 class StepParams(ctypes.Structure):
@@ -48,6 +48,14 @@ class LearnerParams(ctypes.Structure):
                 ("normalize_cost", ctypes.c_int32), ("base_obstacle_weight", ctypes.c_double),
                 ("smoothness_base_weight", ctypes.c_double), ("dist_eps", ctypes.c_double), ("eta", ctypes.c_double),
                 ("etas", ctypes.c_double * 5)]
+
+
+class GoalsetPlanBuffers(ctypes.Structure):
+    """omgb_goalset_plan_buffers_t"""
+    _fields_ = [(k, ctypes.c_void_p) for k in (
+        "xi", "start", "end", "goal_rows", "done", "info", "hist_xi", "hist_info", "goal_set", "reach", "reach_goals",
+        "p", "sum_costs", "experts_p", "experts_costs", "q", "goal_idx", "selected", "collision")] + [
+        ("goals_shared", ctypes.c_int32), ("reserved_", ctypes.c_int32)]
 
 
 class SdfSource(ctypes.Structure):
@@ -130,6 +138,8 @@ def lib():
     L.omgb_hand_poses.argtypes = [vp, vp, ctypes.c_longlong, ci, vp, vp]
     L.omgb_chomp_plan_step.argtypes = [vp, ctypes.POINTER(StepParams), ci, ci, ci] + [vp] * 9
     L.omgb_learner_update.argtypes = [ctypes.POINTER(LearnerParams), ci, vp, vp, vp, ci] + [vp] * 13
+    L.omgb_chomp_plan_goalset.argtypes = [vp, ctypes.POINTER(StepParams), ctypes.POINTER(LearnerParams), ci, ci, vp, vp, ci,
+                                          ctypes.POINTER(GoalsetPlanBuffers), cd, ctypes.POINTER(ci), vp]
     L.omgb_chomp_step_host.argtypes = [vp, ctypes.POINTER(StepParams), ci] + [vp] * 6
     L.omgb_batch_obstacle_cost.argtypes = [vp, vp, ci, ci, vp, cd, ci, vp, vp, vp, vp]
     L.omgb_goal_costs.argtypes = [vp, ci, vp, ctypes.c_longlong, vp, ci, ci, ci, cd, ci, vp, vp]

@@ -18,6 +18,7 @@
 #include <stdint.h>
 
 #include "../../include/omgb200.h"
+#include "learner_bisect.h"
 
 namespace omgb {
 
@@ -58,7 +59,9 @@ __device__ __forceinline__ double lrn_warp_max(double v) {
 // result written to out [G] (shared).  All 32 lanes of the calling warp participate; LRN_PER_LANE = goals per lane
 // (a template parameter: 20 goals need one register set per lane, not eight -- occupancy is what hides the latency
 // of the bisection's dependent exp / reduce chain).
-template <int LRN_PER_LANE>
+// TWO_STEP: the bisection takes two steps per round (learner_bisect.h) -- same points, same comparisons, same result;
+// chosen by the launcher for small batches, where the kernel's time is this warp's dependent chain.
+template <int LRN_PER_LANE, bool TWO_STEP>
 __device__ void lrn_bregman_warp(const double *x, const double *cv, double eta, int G, double delta, double *out) {
     const int lane = threadIdx.x & 31;
     double sh[LRN_PER_LANE], v[LRN_PER_LANE], alpha[LRN_PER_LANE], y[LRN_PER_LANE];
@@ -78,17 +81,40 @@ __device__ void lrn_bregman_warp(const double *x, const double *cv, double eta, 
     const double err = 1e-6;
     for (int it = 0; it < 100; ++it) {
         // find_zero (:18-30)
-        double xx = (0.0 + x1) / 2, step = (x1 - 0.0) / 4;
-        for (int k2 = 0; k2 < 100; ++k2) {
-            double part = 0.0;
+        double xx;
+        if (TWO_STEP) {
+            xx = lrn_find_zero_two(x1, err, [&](double x0, double st, double &f0, double &fm, double &fp) {
+                const double xm = x0 - st, xp = x0 + st;
+                double p0 = 0.0, pm = 0.0, pp = 0.0;
 #pragma unroll
-            for (int k = 0; k < LRN_PER_LANE; ++k)
-                if (lane + 32 * k < G) part += sh[k] * exp(xx + (alpha[k] - v[k]));
-            const double f = lrn_warp_sum(part) - target;
-            if (fabs(f) < err) break;
-            const double sg = (f > 0.0) ? 1.0 : ((f < 0.0) ? -1.0 : 0.0);
-            xx -= step * sg;
-            step /= 2;
+                for (int k = 0; k < LRN_PER_LANE; ++k)
+                    if (lane + 32 * k < G) {
+                        p0 += sh[k] * exp(x0 + (alpha[k] - v[k]));
+                        pm += sh[k] * exp(xm + (alpha[k] - v[k]));
+                        pp += sh[k] * exp(xp + (alpha[k] - v[k]));
+                    }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {   // three interleaved lrn_warp_sum trees
+                    const double t0 = __shfl_xor_sync(0xffffffffu, p0, o), tm = __shfl_xor_sync(0xffffffffu, pm, o),
+                                 tp = __shfl_xor_sync(0xffffffffu, pp, o);
+                    p0 += t0; pm += tm; pp += tp;
+                }
+                f0 = p0 - target; fm = pm - target; fp = pp - target;
+            });
+        } else {
+            xx = (0.0 + x1) / 2;
+            double step = (x1 - 0.0) / 4;
+            for (int k2 = 0; k2 < 100; ++k2) {
+                double part = 0.0;
+#pragma unroll
+                for (int k = 0; k < LRN_PER_LANE; ++k)
+                    if (lane + 32 * k < G) part += sh[k] * exp(xx + (alpha[k] - v[k]));
+                const double f = lrn_warp_sum(part) - target;
+                if (fabs(f) < err) break;
+                const double sg = (f > 0.0) ? 1.0 : ((f < 0.0) ? -1.0 : 0.0);
+                xx -= step * sg;
+                step /= 2;
+            }
         }
         const double lam = xx;
         double dn = 0.0, nxt[LRN_PER_LANE];
@@ -118,7 +144,7 @@ __device__ void lrn_bregman_warp(const double *x, const double *cv, double eta, 
         if (lane + 32 * k < G) out[lane + 32 * k] = y[k] / ys;
 }
 
-template <int PER_LANE>
+template <int PER_LANE, bool TWO_STEP = false>
 __global__ void __launch_bounds__(LRN_THREADS, PER_LANE <= 2 ? 4 : 2) learner_update_kernel(const LearnerArgs a) {
     __shared__ double s_cv[LRN_MAX_GOALS];
     __shared__ double s_p[LRN_MAX_GOALS];
@@ -175,7 +201,7 @@ __global__ void __launch_bounds__(LRN_THREADS, PER_LANE <= 2 ? 4 : 2) learner_up
         for (int k = tid; k < LRN_EXPERTS * G; k += LRN_THREADS) s_old[k / G][k % G] = ep[k];
         __syncthreads();
         const double delta = 1.0 / (double)(4 * G + 1);
-        lrn_bregman_warp<PER_LANE>(s_old[warp], s_cv, P.etas[warp], G, delta, s_new[warp]);
+        lrn_bregman_warp<PER_LANE, TWO_STEP>(s_old[warp], s_cv, P.etas[warp], G, delta, s_new[warp]);
         __syncwarp();
         {   // experts_costs[i] = cv . p + weights . |p - p_old| (:222-224), weights = 1
             double c1 = 0.0, c2 = 0.0;

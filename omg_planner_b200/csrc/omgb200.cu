@@ -6,6 +6,7 @@
 #include <string.h>
 
 #include <atomic>
+#include <chrono>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -1451,11 +1452,97 @@ extern "C" int omgb_learner_update(const omgb_learner_params_t *prm, int batch, 
     a.selected_hist = selected; a.batch = batch;
     const int G = prm->num_goals;
     cudaStream_t st = (cudaStream_t)stream;
-    if (G <= 32) learner_update_kernel<1><<<batch, LRN_THREADS, 0, st>>>(a);
-    else if (G <= 64) learner_update_kernel<2><<<batch, LRN_THREADS, 0, st>>>(a);
+    // Few trajectories: the launch lasts as long as one warp's bisection chain -> the two-steps-per-round form
+    // (identical results, learner_bisect.h); many: the SMs are full, the extra evaluations would only cost throughput.
+    static int env_two = -1;
+    if (env_two < 0) { const char *e = getenv("OMGB_LEARNER_TWO_STEP"); env_two = e ? (atoi(e) ? 1 : 0) : 2; }
+    const bool two = prm->alg == OMGB_LEARNER_MD && (env_two == 2 ? batch <= 2 * 148 : env_two == 1);
+    if (G <= 32) {
+        if (two) learner_update_kernel<1, true><<<batch, LRN_THREADS, 0, st>>>(a);
+        else learner_update_kernel<1><<<batch, LRN_THREADS, 0, st>>>(a);
+    } else if (G <= 64) {
+        if (two) learner_update_kernel<2, true><<<batch, LRN_THREADS, 0, st>>>(a);
+        else learner_update_kernel<2><<<batch, LRN_THREADS, 0, st>>>(a);
+    }
     else if (G <= 128) learner_update_kernel<4><<<batch, LRN_THREADS, 0, st>>>(a);
     else learner_update_kernel<8><<<batch, LRN_THREADS, 0, st>>>(a);
     ++g_launches;
     OMGB_CUDA(cudaGetLastError());
+    return OMGB_OK;
+}
+
+// ----------------------------------------------------------------------------------------------------
+// A whole goal-set plan with goal switching enqueued by ONE call: per iteration goal scoring -> learner update ->
+// plan step, exactly the three entry points above with the arguments the host mirror passed them one call at a time
+// (omg/planner.py:612-635).  The loop runs here instead of in the caller's interpreter: at one trajectory (the
+// reference's own shape) the three launches of an iteration take less GPU time than the Python around them.
+// ----------------------------------------------------------------------------------------------------
+extern "C" int omgb_chomp_plan_goalset(omgb_scene_t *s, const omgb_step_params_t *prm,
+                                       const omgb_learner_params_t *learner, int iters, int learner_iters,
+                                       const double *schedule, const int32_t *first_waypoint, int batch,
+                                       const omgb_goalset_plan_buffers_t *buf, double timeout_s, int *iters_enqueued,
+                                       void *stream) {
+    if (iters_enqueued) *iters_enqueued = 0;
+    int rc_ = check_step(s, prm, batch, "omgb_chomp_plan_goalset");
+    if (rc_) return rc_;
+    if (!learner || !buf) return fail(OMGB_ERR_INVALID, "omgb_chomp_plan_goalset: null params");
+    if (iters < 0 || learner_iters < 0 || learner_iters > iters)
+        return fail(OMGB_ERR_INVALID, "omgb_chomp_plan_goalset: 0 <= learner_iters <= iters required");
+    if (!prm->goal_set_proj) return fail(OMGB_ERR_INVALID, "omgb_chomp_plan_goalset: goal_set_proj required");
+    if (batch == 0 || iters == 0) return OMGB_OK;
+    if (!schedule || (learner_iters > 0 && !first_waypoint))
+        return fail(OMGB_ERR_INVALID, "omgb_chomp_plan_goalset: null schedule");
+    if (!buf->xi || !buf->start || !buf->end || !buf->goal_rows || !buf->done || !buf->info || !buf->goal_set ||
+        !buf->reach_goals || !buf->goal_idx)
+        return fail(OMGB_ERR_INVALID, "omgb_chomp_plan_goalset: null buffer");
+    const bool score = learner->alg != OMGB_LEARNER_PROJ;
+    if (learner_iters > 0 && score && !buf->collision)
+        return fail(OMGB_ERR_INVALID, "omgb_chomp_plan_goalset: collision scratch required");
+    const int n = prm->n_waypoints;
+    omgb_step_params_t sp = *prm;
+    omgb_learner_params_t lp = *learner;
+    // cfg.timeout (omg/planner.py:629) against the DEVICE's progress: every 8 iterations an event is recorded; before
+    // the clock is read the event two checks back has completed, so at most 16 iterations are in flight past it
+    const bool timed = timeout_s >= 0.0;
+    const auto t_begin = std::chrono::steady_clock::now();
+    std::vector<cudaEvent_t> checks;
+    auto drop_checks = [&]() { for (cudaEvent_t e : checks) cudaEventDestroy(e); checks.clear(); };
+    cudaStream_t st = (cudaStream_t)stream;
+    for (int t = 0; t < iters; ++t) {
+        if (timed && t > 0 && t % 8 == 0) {
+            if (checks.size() >= 2) cudaEventSynchronize(checks[checks.size() - 2]);
+            const double el = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_begin).count();
+            if (el > timeout_s) break;
+            cudaEvent_t e;
+            if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) == cudaSuccess) {
+                cudaEventRecord(e, st);
+                checks.push_back(e);
+            }
+        }
+        if (t < learner_iters) {
+            const int first = first_waypoint[t];
+            if (first < 0 || first >= n) { drop_checks(); return fail(OMGB_ERR_INVALID, "omgb_chomp_plan_goalset: first waypoint out of range"); }
+            lp.first_waypoint = first;
+            if (score) {
+                rc_ = omgb_goal_costs(s, batch, buf->xi + (size_t)ND * first, (long long)n * ND, buf->reach_goals,
+                                      lp.num_goals, buf->goals_shared, n - first, prm->time_interval, 0, buf->collision,
+                                      stream);
+                if (rc_) { drop_checks(); return rc_; }
+            }
+            rc_ = omgb_learner_update(&lp, batch, buf->xi, score ? buf->collision : nullptr, buf->goal_set,
+                                      buf->goals_shared, buf->reach, buf->p, buf->sum_costs, buf->experts_p,
+                                      buf->experts_costs, buf->q, buf->done, buf->goal_idx, buf->end, buf->goal_rows,
+                                      nullptr, buf->selected ? buf->selected + (size_t)t * batch : nullptr, stream);
+            if (rc_) { drop_checks(); return rc_; }
+        }
+        sp.obstacle_weight = schedule[3 * t];
+        sp.smoothness_weight = schedule[3 * t + 1];
+        sp.step_size = schedule[3 * t + 2];
+        rc_ = omgb_chomp_plan_step(s, &sp, t, 1, batch, buf->xi, buf->start, buf->end, buf->goal_rows, buf->done,
+                                   buf->info, buf->hist_xi, buf->hist_info, stream);
+        if (rc_) { drop_checks(); return rc_; }
+        if (iters_enqueued) *iters_enqueued = t + 1;
+    }
+    drop_checks();
     return OMGB_OK;
 }

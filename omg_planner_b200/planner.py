@@ -232,7 +232,8 @@ class Planner(GoalSetMixin):
     def _plan_with_device_learner(self, traj, iters):
         """Goal switching without leaving the GPU: per iteration omgb_goal_costs -> omgb_learner_update (cost vector,
         FTL / FTC / Exp / MD / Proj, goal selection, new goal rows) -> omgb_chomp_plan_step (frozen trajectories,
-        history), all on one stream with no host synchronisation until the plan is over."""
+        history), all on one stream with no host synchronisation until the plan is over.  The loop over the iterations
+        runs inside the library (omgb_chomp_plan_goalset): one call enqueues the whole plan."""
         from .online_learner import DeviceLearnerState
 
         cfg, cost, lrn = self.cfg, self.cost, self.learner
@@ -252,31 +253,38 @@ class Planner(GoalSetMixin):
         selected = torch.zeros((max(n_sel, 1), B), dtype=torch.int32, device=xi.device)
         import ctypes
         vp = ctypes.c_void_p
-        stream = vp(torch.cuda.current_stream().cuda_stream)
-        prm = _lib.StepParams()
-        step0 = self.optim.step
-        t_begin, checks = time.time(), []
-        ran = 0
+        step0, t0 = self.optim.step, lrn.t
+        # Host half of the loop, ahead of time: Optimizer.update()'s schedule of every iteration (written back into cfg
+        # like the reference, omg/optimizer.py:59-80) and the waypoint each learner update scores from
+        # (omg/online_learner.py:108-110); the loop itself runs inside omgb_chomp_plan_goalset.
+        sched = np.empty((iters, 3), dtype=np.float64)
         for t in range(iters):
-            if cfg.timeout != -1 and t > 0 and t % 8 == 0:   # omg/planner.py:629 against the device's progress
-                if len(checks) >= 2:
-                    checks[-2].synchronize()                 # the device has finished iteration t - 16
-                if time.time() - t_begin > cfg.timeout:
-                    break
-                checks.append(torch.cuda.Event())
-                checks[-1].record()
-            if t < cfg.optim_steps:
-                st.update(eng, xi, end, rows, done=done, selected=selected[t])
-            self.optim.update()                                          # schedule, written back into cfg
-            ecfg = cost.engine_cfg()
-            eng.set_metric(ecfg)
-            eng.params_from(ecfg, True, into=prm)
-            _lib.check(eng.L.omgb_chomp_plan_step(eng._h, ctypes.byref(prm), t, 1, B, vp(xi.data_ptr()),
-                                                  vp(start.data_ptr()), vp(end.data_ptr()), vp(rows.data_ptr()),
-                                                  vp(done.data_ptr()), vp(info.data_ptr()), vp(hist_xi.data_ptr()),
-                                                  vp(hist_info.data_ptr()), stream), "omgb_chomp_plan_step")
-            ran = t + 1
-        if ran < iters:                                                  # stopped by cfg.timeout
+            self.optim.update()
+            sched[t] = (cfg.obstacle_weight, cfg.smoothness_weight, cfg.step_size)
+        firsts = np.array([min(1 + int(((t0 + t + 1) / cfg.optim_steps) * cfg.timesteps) - 1, cfg.timesteps - 1)
+                           for t in range(n_sel)], dtype=np.int32)
+        ecfg = cost.engine_cfg()
+        eng.set_metric(ecfg)
+        prm = eng.params_from(ecfg, True)
+        coll = torch.empty((B, lrn.N), dtype=torch.float32, device=xi.device) if lrn.alg_name != "Proj" else None
+        buf = _lib.GoalsetPlanBuffers()
+        for k, v in (("xi", xi), ("start", start), ("end", end), ("goal_rows", rows), ("done", done), ("info", info),
+                     ("hist_xi", hist_xi), ("hist_info", hist_info), ("goal_set", st.goal_set), ("reach", st.reach),
+                     ("reach_goals", st.reach_goals), ("p", st.p), ("sum_costs", st.sum_costs),
+                     ("experts_p", st.experts_p), ("experts_costs", st.experts_costs), ("q", st.q),
+                     ("goal_idx", st.goal_idx), ("selected", selected), ("collision", coll)):
+            setattr(buf, k, None if v is None else v.data_ptr())
+        buf.goals_shared = int(st.shared)
+        ran_c = ctypes.c_int(0)
+        _lib.check(eng.L.omgb_chomp_plan_goalset(
+            eng._h, ctypes.byref(prm), ctypes.byref(st.prm), iters, n_sel, vp(sched.ctypes.data),
+            vp(firsts.ctypes.data), B, ctypes.byref(buf), float(cfg.timeout) if cfg.timeout != -1 else -1.0,
+            ctypes.byref(ran_c), vp(torch.cuda.current_stream().cuda_stream)), "omgb_chomp_plan_goalset")
+        ran = ran_c.value
+        lrn.t = t0 + min(ran, n_sel)
+        if ran < iters:                                                  # stopped by cfg.timeout: cfg as the loop left it
+            self.optim.step = step0 + ran - 1
+            self.optim.update()
             iters, hist_all, hist_info = ran, hist_all[:ran + 1], hist_info[:ran]
             n_sel = min(n_sel, ran)
         stage = self.__dict__.setdefault("_stage", {})

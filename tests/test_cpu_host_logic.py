@@ -35,12 +35,17 @@ def test_header_is_plain_c(tmp_path):
 
     src = tmp_path / "h.c"
     src.write_text('#include <stdio.h>\n#include "omgb200.h"\nint main(void){printf("%zu %zu %zu\\n", '
-                   'sizeof(omgb_step_params_t), sizeof(omgb_learner_params_t), sizeof(omgb_sdf_source_t));return 0;}\n')
+                   'sizeof(omgb_step_params_t), sizeof(omgb_learner_params_t), sizeof(omgb_sdf_source_t));'
+                   'printf("%zu %zu %zu\\n", sizeof(omgb_goalset_plan_buffers_t), '
+                   'offsetof(omgb_goalset_plan_buffers_t, collision), offsetof(omgb_goalset_plan_buffers_t, goals_shared));'
+                   'return 0;}\n')
     exe = tmp_path / "h"
     subprocess.check_call(["gcc", "-std=c99", "-pedantic", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"),
                            "-o", str(exe), str(src)])
     sizes = [int(v) for v in subprocess.check_output([str(exe)]).split()]
-    assert sizes == [ctypes.sizeof(_lib.StepParams), ctypes.sizeof(_lib.LearnerParams), ctypes.sizeof(_lib.SdfSource)]
+    assert sizes == [ctypes.sizeof(_lib.StepParams), ctypes.sizeof(_lib.LearnerParams), ctypes.sizeof(_lib.SdfSource),
+                     ctypes.sizeof(_lib.GoalsetPlanBuffers), _lib.GoalsetPlanBuffers.collision.offset,
+                     _lib.GoalsetPlanBuffers.goals_shared.offset]
 
 
 def test_argument_validation_without_gpu():
@@ -76,6 +81,9 @@ def test_argument_validation_of_the_data_path_entry_points_without_gpu():
     prm.alg, prm.num_goals = 3, 300
     assert L.omgb_learner_update(ctypes.byref(prm), 2, None, None, None, 0, *([None] * 13)) == -1   # > 256 goals
     assert b"256" in L.omgb_last_error()
+    ran = ctypes.c_int(7)                                                          # whole goal-set plan: null scene
+    assert L.omgb_chomp_plan_goalset(None, None, None, 3, 1, None, None, 2, None, -1.0, ctypes.byref(ran), None) == -1
+    assert ran.value == 0
 
 
 @pytest.mark.parametrize("gsp", [True, False])

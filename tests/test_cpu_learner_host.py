@@ -46,3 +46,22 @@ def test_bregman_projection_rows_match_oracle():
         np.testing.assert_allclose(out[r], LR.bregman_projection(x[r], v[r], delta, w), rtol=1e-12, atol=1e-15)
 
 
+
+
+def test_two_step_bisection_equals_sequential_bit_for_bit(tmp_path):
+    """omg_planner_b200/csrc/learner_bisect.h compiled for the host (tests/host/bisect_check.cpp): the two-steps-per-round
+    bisection the learner kernel uses for small batches returns the sequential loop's value (find_zero,
+    omg/online_learner.py:18-30) on 50 000 projections, incl. exhausted brackets, exits at the second step of a round
+    and NaN stretches."""
+    import os
+    import subprocess
+
+    here = os.path.dirname(os.path.abspath(__file__))
+    exe = str(tmp_path / "bisect_check")
+    subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-fno-fast-math", "-std=c++14", "-o", exe,
+                           os.path.join(here, "host", "bisect_check.cpp"), "-lm"])
+    out = subprocess.run([exe, "50000"], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+    f = dict(zip(out.stdout.split()[0::2], out.stdout.split()[1::2]))
+    assert int(f["trials"]) == 50000 and int(f["mismatches"]) == 0
+    assert int(f["early_exit_second"]) > 1000 and int(f["exhausted"]) > 1000 and int(f["nan_cases"]) > 100

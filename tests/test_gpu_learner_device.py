@@ -111,6 +111,36 @@ def test_device_plan_equals_host_learner_plan(alg, standoff):
     print(alg, "goals selected per trajectory:", [sorted(set(r.tolist())) for r in out[False][0]])
 
 
+def test_device_plan_honours_cfg_timeout():
+    """cfg.timeout (omg/planner.py:629) inside omgb_chomp_plan_goalset: with a zero budget the loop stops at its first
+    clock check (iteration 8); what ran is the head of the untimed plan, bit for bit, and the bookkeeping (Optimizer.step,
+    Learner.t, selected goals, the closing info-only call) is that of a loop that ran 8 iterations."""
+    sc = S.make_scene(num_objects=6, grid=48, seed=11, grid_choices=[32, 40, 48])
+    robot = PandaConstants()
+    B, G = 5, 9
+    goals, reach = S.make_goal_sets(B, G, robot.joint_lower_limit, robot.joint_upper_limit, seed=21, spread=0.1)
+    out = {}
+    for timeout in (-1, 0.0):
+        cfg = ChompConfig(goal_set_proj=True, use_standoff=True, ol_alg="MD", optim_steps=14, extra_smooth_steps=4,
+                          pre_terminate=False)
+        cfg.timeout = timeout
+        planner, traj = _planner(sc, robot, goals, reach, cfg)
+        t0, step0 = planner.learner.t, planner.optim.step
+        planner.plan(traj)
+        out[timeout] = (planner.history_trajectories, planner.selected_goals, planner.info,
+                        planner.optim.step - step0, planner.learner.t - t0)
+    full, cut = out[-1], out[0.0]
+    assert full[3] == 18 + 1 and cut[3] == 8 + 1            # one update() per iteration + the info-only call
+    assert full[4] == 14 and cut[4] == 8
+    for b in range(B):
+        assert len(full[0][b]) == 19 and len(cut[0][b]) == 9
+        np.testing.assert_array_equal(np.asarray(cut[0][b]), np.asarray(full[0][b])[:9])
+        assert list(cut[1][b]) == list(full[1][b])[:8]
+        assert len(cut[2][b]) == 9
+        for k in range(8):
+            assert cut[2][b][k]["cost"] == full[2][b][k]["cost"]
+
+
 def test_device_cost_vector_matches_learner_mirror():
     """The cost vector the kernel builds == Learner.cost_vector (pinned to the reference by the learner fixtures)."""
     g = np.load(GOLDEN[0])

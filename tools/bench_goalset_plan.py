@@ -80,15 +80,30 @@ def main():
         traj = C.Trajectory(30, cfg=cfg, start=S.START_CONF, end=goals[0, 0])
         planner = Planner(env, traj)
         ts = []
-        for rep in range(4):
+        sprof = os.environ.get("SINGLE_PROFILE")       # cProfile of one more single-trajectory goal-set plan -> this file
+        for rep in range(5 if (sprof and name == "goal_set_md") else 4):
             traj = C.Trajectory(30, cfg=cfg, start=S.START_CONF, end=goals[0, 0])
             traj.goal_set = goals[0]
             planner.update(env, traj)
             torch.cuda.synchronize()
+            pr = None
+            if rep == 4:
+                import cProfile
+                pr = cProfile.Profile()
+                pr.enable()
             t0 = time.perf_counter()
             planner.plan(traj)
             torch.cuda.synchronize()
-            ts.append(time.perf_counter() - t0)
+            dt1 = time.perf_counter() - t0
+            if pr is not None:
+                import io
+                import pstats
+                pr.disable()
+                buf = io.StringIO()
+                pstats.Stats(pr, stream=buf).sort_stats("tottime").print_stats(30)
+                open(sprof, "w").write("single-trajectory goal-set plan, wall %.4f s (under cProfile)\n" % dt1 + buf.getvalue())
+            else:
+                ts.append(dt1)
         one[name] = {"plan_wall_ms": min(ts[1:]) * 1e3, "iterations": cfg.optim_steps + cfg.extra_smooth_steps}
         # the plugin call the reference's own loop makes: Optimizer.optimize(traj, force_update=True), one trajectory
         t0 = time.perf_counter()
