@@ -89,16 +89,17 @@ def check(path):
 
     g = np.load(path)
     jobs = []
-    for name, mode in MODES.items():
+    modes = {name: mode for name, mode in MODES.items() if "hist_" + name in g.files}   # (PARITY_MODES at dump time)
+    for name, mode in modes.items():
         rows = H.goal_rows_for(mode, g["tails"], g["end"])
         for b in range(N_TRAJ):
             jobs.append((name, mode, b, g["xi0"][b], g["start"][b], g["end"][b], None if rows is None else rows[b]))
-    ref = {name: np.zeros((ITERS, N_TRAJ, N_WPT, 9)) for name in MODES}
+    ref = {name: np.zeros((ITERS, N_TRAJ, N_WPT, 9)) for name in modes}
     with mp.get_context("fork").Pool(os.cpu_count() or 1) as pool:
         for name, b, hist in pool.imap_unordered(_oracle_worker, jobs, chunksize=4):
             ref[name][:, b] = hist
     report = {"shape": SHAPE, "scene": SCENE, "trajectories": N_TRAJ, "waypoints": N_WPT, "tolerance_rad": 1e-4, "modes": {}}
-    for name, mode in MODES.items():
+    for name, mode in modes.items():
         dofs = 9 if mode.get("consider_finger") else 7
         got = g["hist_" + name]
         full = got.shape[0] == ITERS
